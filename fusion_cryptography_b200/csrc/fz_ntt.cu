@@ -1,0 +1,415 @@
+// fz_ntt.cu -- batched negacyclic NTT / INTT / pointwise product over Z_q for d = 64 and 256.
+//
+// Replaces (bit-exactly) algebra/ntt.py:216-291 (cooley_tukey_ntt: natural in, bit-reversed
+// out), algebra/ntt.py:294-377 (gentleman_sande_intt: bit-reversed in, natural out, x n^-1),
+// algebra/polynomials.py:282-318/341-385 (pointwise add / mul with cent) and
+// algebra/polynomials.py:391-433 (transform).
+//
+// Decomposition (B200: no tensor cores -- modular integer butterflies; the aim is to keep the
+// INT32 pipes busy while every coefficient crosses HBM exactly once in and once out):
+//   * a polynomial is owned by TPP = d/16 lanes of ONE warp; each lane keeps 16 coefficients
+//     in registers, so 4 butterfly stages run with no data movement at all;
+//   * the "strided" pass (lane holds e = lane + TPP*k) covers the 4 long-stride stages; its
+//     15 twiddles are the same for every lane, so they are compile-time constant-bank
+//     operands of the IMADs (no loads, no registers);
+//   * one padded shared-memory transpose (warp-private, __syncwarp only) turns the strided
+//     ownership into 16 contiguous coefficients per lane for the remaining log2(d)-4 stages,
+//     whose lane-dependent twiddles are fetched once per thread and stay in registers while
+//     the persistent CTA loops over polynomials;
+//   * butterflies use Plantard multiplication by precomputed 64-bit constants (3 IMAD-class
+//     instructions, result already in [0, q]) with lazy [0, 2q] sums; the final stage of each
+//     transform uses the signed variant, which yields the canonical centred residue directly.
+#include "fz_common.cuh"
+#include "fz_internal.h"
+
+namespace fz {
+
+__constant__ Tw c_fwd256[256];
+__constant__ Tw c_inv256[256];
+__constant__ Tw c_fwd64[64];
+__constant__ Tw c_inv64[64];
+// [0] = n^-1, [1] = n^-1 * itw[1]  (last inverse stage with the scaling folded in)
+__constant__ Tw c_last256[2];
+__constant__ Tw c_last64[2];
+
+template <int LOGD> struct Cfg;
+template <> struct Cfg<8> {
+    static constexpr int D = 256, TPP = 16, PPW = 2, WARP_WORDS = 2 * 336;
+    static __device__ __forceinline__ const Tw* fwd() { return c_fwd256; }
+    static __device__ __forceinline__ const Tw* inv() { return c_inv256; }
+    static __device__ __forceinline__ const Tw* last() { return c_last256; }
+    // row of 16 coefficients padded to 20 words; second polynomial of the warp shifted by 16 banks
+    static __device__ __forceinline__ int base(int p) { return p * 336; }
+};
+template <> struct Cfg<6> {
+    static constexpr int D = 64, TPP = 4, PPW = 8, WARP_WORDS = 4 * 164;
+    static __device__ __forceinline__ const Tw* fwd() { return c_fwd64; }
+    static __device__ __forceinline__ const Tw* inv() { return c_inv64; }
+    static __device__ __forceinline__ const Tw* last() { return c_last64; }
+    static __device__ __forceinline__ int base(int p) { return (p >> 1) * 164 + (p & 1) * 80; }
+};
+
+__device__ __forceinline__ int row_off(int e) { return (e >> 4) * 20 + (e & 15); }
+
+// Cooley-Tukey butterfly, algebra/ntt.py:283-289: (u, v*s) -> (u + v*s, u - v*s)
+__device__ __forceinline__ void bf_ct(uint32_t& X, uint32_t& Y, uint32_t wlo, uint32_t whi) {
+    uint32_t t = pl_mul(Y, wlo, whi);
+    uint32_t xr = red_q(X);
+    X = xr + t;
+    Y = xr - t + Q;
+}
+
+// Gentleman-Sande butterfly, algebra/ntt.py:363-369: (u, v) -> (u + v, (u - v)*s); u, v in [0, q]
+__device__ __forceinline__ void bf_gs(uint32_t& U, uint32_t& V, uint32_t wlo, uint32_t whi) {
+    uint32_t a = U + V;
+    uint32_t b = U - V + Q;
+    U = red_q(a);
+    V = pl_mul(b, wlo, whi);
+}
+
+// twiddles of the contiguous pass for lane-in-polynomial tau: slot 8/t - 1 + j  <->  table[d/(2t) + (8/t)*tau + j]
+template <int LOGD>
+__device__ __forceinline__ void load_tw2(const Tw* table, int tau, Tw (&tw2)[15]) {
+    constexpr int D = Cfg<LOGD>::D;
+#pragma unroll
+    for (int t = 8; t >= 1; t >>= 1) {
+        if (t * 32 > D) continue;  // stage does not exist for this degree (d = 64: only t = 2, 1)
+#pragma unroll
+        for (int j = 0; j < 8 / t; ++j) tw2[8 / t - 1 + j] = table[D / (2 * t) + (8 / t) * tau + j];
+    }
+}
+
+// forward, long-stride stages (m = 1, 2, 4, 8); lane holds e = tau + TPP*k
+template <int LOGD>
+__device__ __forceinline__ void fwd_strided(uint32_t (&x)[16]) {
+    const Tw* tw = Cfg<LOGD>::fwd();
+#pragma unroll
+    for (int s = 1; s <= 4; ++s) {
+        const int dk = 16 >> s, m = 1 << (s - 1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (k & dk) continue;
+            const int i = k >> (5 - s);
+            bf_ct(x[k], x[k + dk], tw[m + i].lo, tw[m + i].hi);
+        }
+    }
+}
+
+// forward, short-stride stages on 16 contiguous coefficients
+template <int LOGD>
+__device__ __forceinline__ void fwd_contig(uint32_t (&y)[16], const Tw (&tw2)[15]) {
+#pragma unroll
+    for (int t = 8; t >= 1; t >>= 1) {
+        if (t * 32 > Cfg<LOGD>::D) continue;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (k & t) continue;
+            const int j = k / (2 * t);
+            bf_ct(y[k], y[k + t], tw2[8 / t - 1 + j].lo, tw2[8 / t - 1 + j].hi);
+        }
+    }
+}
+
+// inverse, short-stride stages first (t = 1, 2, 4, 8) on 16 contiguous coefficients in [0, q]
+template <int LOGD>
+__device__ __forceinline__ void inv_contig(uint32_t (&y)[16], const Tw (&tw2)[15]) {
+#pragma unroll
+    for (int t = 1; t <= 8; t <<= 1) {
+        if (t * 32 > Cfg<LOGD>::D) continue;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (k & t) continue;
+            const int j = k / (2 * t);
+            bf_gs(y[k], y[k + t], tw2[8 / t - 1 + j].lo, tw2[8 / t - 1 + j].hi);
+        }
+    }
+}
+
+// inverse, long-stride stages; the last one carries n^-1 and emits canonical centred values
+template <int LOGD>
+__device__ __forceinline__ void inv_strided(uint32_t (&x)[16], int32_t (&o)[16]) {
+    const Tw* tw = Cfg<LOGD>::inv();
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int dk = 1 << j, h = 8 >> j;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (k & dk) continue;
+            const int i = k >> (j + 1);
+            bf_gs(x[k], x[k + dk], tw[h + i].lo, tw[h + i].hi);
+        }
+    }
+    const Tw* lw = Cfg<LOGD>::last();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t a = x[k] + x[k + 8];
+        uint32_t b = x[k] - x[k + 8] + Q;
+        o[k] = pl_mul_cent(a, lw[0].lo, lw[0].hi);
+        o[k + 8] = pl_mul_cent(b, lw[1].lo, lw[1].hi);
+    }
+}
+
+// strided ownership -> contiguous ownership through the warp-private padded tile
+template <int LOGD>
+__device__ __forceinline__ void xchg_s2c(uint32_t* tile, int tau, const uint32_t (&x)[16], uint32_t (&y)[16]) {
+    constexpr int TPP = Cfg<LOGD>::TPP;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) tile[row_off(tau + TPP * k)] = x[k];
+    __syncwarp();
+    const uint4* r = reinterpret_cast<const uint4*>(tile + tau * 20);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint4 v = r[c];
+        y[4 * c] = v.x; y[4 * c + 1] = v.y; y[4 * c + 2] = v.z; y[4 * c + 3] = v.w;
+    }
+    __syncwarp();
+}
+
+template <int LOGD>
+__device__ __forceinline__ void xchg_c2s(uint32_t* tile, int tau, const uint32_t (&y)[16], uint32_t (&x)[16]) {
+    constexpr int TPP = Cfg<LOGD>::TPP;
+    uint4* w = reinterpret_cast<uint4*>(tile + tau * 20);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) w[c] = make_uint4(y[4 * c], y[4 * c + 1], y[4 * c + 2], y[4 * c + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = tile[row_off(tau + TPP * k)];
+    __syncwarp();
+}
+
+constexpr int NTT_THREADS = 128;
+
+template <int LOGD>
+__global__ void __launch_bounds__(NTT_THREADS) ntt_fwd_kernel(const int32_t* in, int32_t* out, size_t n_polys) {
+    using C = Cfg<LOGD>;
+    __shared__ __align__(16) uint32_t smem[(NTT_THREADS / 32) * C::WARP_WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tau = lane % C::TPP, pw = lane / C::TPP;
+    uint32_t* tile = smem + warp * C::WARP_WORDS + C::base(pw);
+    Tw tw2[15];
+    load_tw2<LOGD>(C::fwd(), tau, tw2);
+    const size_t per_cta = (NTT_THREADS / 32) * C::PPW;
+    for (size_t p0 = (size_t)blockIdx.x * per_cta; p0 < n_polys; p0 += (size_t)gridDim.x * per_cta) {
+        const size_t p = p0 + warp * C::PPW + pw;
+        const bool live = p < n_polys;
+        uint32_t x[16], y[16];
+        const int32_t* src = in + p * C::D + tau;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = live ? to_lazy(src[C::TPP * k]) : 0u;
+        fwd_strided<LOGD>(x);
+        xchg_s2c<LOGD>(tile, tau, x, y);
+        fwd_contig<LOGD>(y, tw2);
+        if (live) {
+            int4* dst = reinterpret_cast<int4*>(out + p * C::D + tau * 16);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                dst[c] = make_int4(cent_u(y[4 * c]), cent_u(y[4 * c + 1]), cent_u(y[4 * c + 2]), cent_u(y[4 * c + 3]));
+        }
+    }
+}
+
+template <int LOGD>
+__global__ void __launch_bounds__(NTT_THREADS) ntt_inv_kernel(const int32_t* in, int32_t* out, size_t n_polys) {
+    using C = Cfg<LOGD>;
+    __shared__ __align__(16) uint32_t smem[(NTT_THREADS / 32) * C::WARP_WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tau = lane % C::TPP, pw = lane / C::TPP;
+    uint32_t* tile = smem + warp * C::WARP_WORDS + C::base(pw);
+    Tw tw2[15];
+    load_tw2<LOGD>(C::inv(), tau, tw2);
+    const size_t per_cta = (NTT_THREADS / 32) * C::PPW;
+    for (size_t p0 = (size_t)blockIdx.x * per_cta; p0 < n_polys; p0 += (size_t)gridDim.x * per_cta) {
+        const size_t p = p0 + warp * C::PPW + pw;
+        const bool live = p < n_polys;
+        uint32_t x[16], y[16];
+        const int4* src = reinterpret_cast<const int4*>(in + p * C::D + tau * 16);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            int4 v = live ? src[c] : make_int4(0, 0, 0, 0);
+            y[4 * c] = to_red(v.x); y[4 * c + 1] = to_red(v.y); y[4 * c + 2] = to_red(v.z); y[4 * c + 3] = to_red(v.w);
+        }
+        inv_contig<LOGD>(y, tw2);
+        xchg_c2s<LOGD>(tile, tau, y, x);
+        int32_t o[16];
+        inv_strided<LOGD>(x, o);
+        if (live) {
+            int32_t* dst = out + p * C::D + tau;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) dst[C::TPP * k] = o[k];
+        }
+    }
+}
+
+// lazy [0, 2q] x lazy [0, 2q] -> [0, q], pseudo-Mersenne folds of the 62-bit product
+__device__ __forceinline__ uint32_t mul_lazy(uint32_t a, uint32_t b) {
+    unsigned long long P = (unsigned long long)red_q(a) * red_q(b);
+    unsigned long long f1 = (P >> 31) * MERS_C + (P & 0x7fffffffull);
+    uint32_t f2 = (uint32_t)(f1 >> 31) * MERS_C + (uint32_t)(f1 & 0x7fffffffull);
+    return red_q(f2);
+}
+
+// out = INTT(NTT(a) o NTT(b)): algebra/ntt.py:450-471 (ntt_poly_mult) in one pass over HBM
+template <int LOGD>
+__global__ void __launch_bounds__(NTT_THREADS) polymul_kernel(const int32_t* a, const int32_t* b, int32_t* out, size_t n_polys) {
+    using C = Cfg<LOGD>;
+    __shared__ __align__(16) uint32_t smem[(NTT_THREADS / 32) * C::WARP_WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tau = lane % C::TPP, pw = lane / C::TPP;
+    uint32_t* tile = smem + warp * C::WARP_WORDS + C::base(pw);
+    Tw twf[15], twi[15];
+    load_tw2<LOGD>(C::fwd(), tau, twf);
+    load_tw2<LOGD>(C::inv(), tau, twi);
+    const size_t per_cta = (NTT_THREADS / 32) * C::PPW;
+    for (size_t p0 = (size_t)blockIdx.x * per_cta; p0 < n_polys; p0 += (size_t)gridDim.x * per_cta) {
+        const size_t p = p0 + warp * C::PPW + pw;
+        const bool live = p < n_polys;
+        uint32_t x[16], ya[16], yb[16];
+        const int32_t* sa = a + p * C::D + tau;
+        const int32_t* sb = b + p * C::D + tau;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = live ? to_lazy(sa[C::TPP * k]) : 0u;
+        fwd_strided<LOGD>(x);
+        xchg_s2c<LOGD>(tile, tau, x, ya);
+        fwd_contig<LOGD>(ya, twf);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = live ? to_lazy(sb[C::TPP * k]) : 0u;
+        fwd_strided<LOGD>(x);
+        xchg_s2c<LOGD>(tile, tau, x, yb);
+        fwd_contig<LOGD>(yb, twf);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) ya[k] = mul_lazy(ya[k], yb[k]);
+        inv_contig<LOGD>(ya, twi);
+        xchg_c2s<LOGD>(tile, tau, ya, x);
+        int32_t o[16];
+        inv_strided<LOGD>(x, o);
+        if (live) {
+            int32_t* dst = out + p * C::D + tau;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) dst[C::TPP * k] = o[k];
+        }
+    }
+}
+
+// out = cent(a*b) or cent(cent(a*b) + c); n4 = number of int4 groups.  polynomials.py:341-385, 282-318
+template <bool ADD>
+__global__ void __launch_bounds__(256) pointwise_kernel(const int4* __restrict__ a, const int4* __restrict__ b, const int4* __restrict__ c,
+                                                          int4* __restrict__ out, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        int4 va = ld_stream(a + i), vb = ld_stream(b + i), r;
+        if (ADD) {
+            int4 vc = ld_stream(c + i);
+            r.x = cent_i64((long long)va.x * vb.x + vc.x);
+            r.y = cent_i64((long long)va.y * vb.y + vc.y);
+            r.z = cent_i64((long long)va.z * vb.z + vc.z);
+            r.w = cent_i64((long long)va.w * vb.w + vc.w);
+        } else {
+            r.x = mul_cent(va.x, vb.x); r.y = mul_cent(va.y, vb.y); r.z = mul_cent(va.z, vb.z); r.w = mul_cent(va.w, vb.w);
+        }
+        st_stream(out + i, r);
+    }
+}
+
+// ---------------------------------------------------------------- host side
+static unsigned long long h_powmod(unsigned long long b, unsigned long long e) {
+    unsigned __int128 r = 1, x = b % Q;
+    while (e) {
+        if (e & 1) r = (r * x) % Q;
+        x = (x * x) % Q;
+        e >>= 1;
+    }
+    return (unsigned long long)r;
+}
+
+static Tw h_plantard(unsigned long long w) {
+    unsigned long long b = (unsigned long long)(((unsigned __int128)(w % Q) * NEG_N2) % Q);
+    unsigned long long W = b * QINV64;  // mod 2^64
+    Tw t;
+    t.lo = (uint32_t)W;
+    t.hi = (uint32_t)(W >> 32);
+    return t;
+}
+
+static int h_brv(int i, int bits) {
+    int r = 0;
+    for (int k = 0; k < bits; ++k)
+        if (i & (1 << k)) r |= 1 << (bits - 1 - k);
+    return r;
+}
+
+// tw[k] = psi^brv(k) mod q (algebra/polynomials.py:396-397, algebra/ntt.py:74-90), as Plantard constants
+int ntt_init_tables(fz_ctx* ctx) {
+    const int levels[2][2] = {{6, 23584283}, {8, 3337519}};  // fusion.py:36-37
+    for (int L = 0; L < 2; ++L) {
+        const int logd = levels[L][0], d = 1 << logd;
+        const unsigned long long psi = levels[L][1], ipsi = h_powmod(psi, Q - 2), ninv = h_powmod(d, Q - 2);
+        Tw f[256], iv[256], last[2];
+        unsigned long long itw1 = 0;
+        for (int k = 0; k < d; ++k) {
+            unsigned long long w = h_powmod(psi, h_brv(k, logd)), iw = h_powmod(ipsi, h_brv(k, logd));
+            f[k] = h_plantard(w);
+            iv[k] = h_plantard(iw);
+            if (k == 1) itw1 = iw;
+        }
+        last[0] = h_plantard(ninv);
+        last[1] = h_plantard((unsigned long long)(((unsigned __int128)ninv * itw1) % Q));
+        cudaError_t e;
+        if (logd == 8) {
+            e = cudaMemcpyToSymbol(c_fwd256, f, sizeof(Tw) * d);
+            if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_inv256, iv, sizeof(Tw) * d);
+            if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_last256, last, sizeof(last));
+        } else {
+            e = cudaMemcpyToSymbol(c_fwd64, f, sizeof(Tw) * d);
+            if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_inv64, iv, sizeof(Tw) * d);
+            if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_last64, last, sizeof(last));
+        }
+        if (check(e, "twiddle upload")) return -1;
+    }
+    (void)ctx;
+    return 0;
+}
+
+template <typename K>
+static int persistent_grid(const fz_ctx* ctx, K kernel, int threads, size_t work_items) {
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0);
+    if (occ < 1) occ = 1;
+    size_t g = (size_t)ctx->sm_count * occ;
+    if (work_items < g) g = work_items;
+    return g < 1 ? 1 : (int)g;
+}
+
+int launch_ntt(const fz_ctx* ctx, int inverse, const int32_t* in, int32_t* out, size_t n_polys, cudaStream_t st) {
+    if (n_polys == 0) return 0;
+    if (ctx->logd == 8) {
+        const size_t items = (n_polys + 7) / 8;
+        if (inverse) ntt_inv_kernel<8><<<persistent_grid(ctx, ntt_inv_kernel<8>, NTT_THREADS, items), NTT_THREADS, 0, st>>>(in, out, n_polys);
+        else ntt_fwd_kernel<8><<<persistent_grid(ctx, ntt_fwd_kernel<8>, NTT_THREADS, items), NTT_THREADS, 0, st>>>(in, out, n_polys);
+    } else {
+        const size_t items = (n_polys + 31) / 32;
+        if (inverse) ntt_inv_kernel<6><<<persistent_grid(ctx, ntt_inv_kernel<6>, NTT_THREADS, items), NTT_THREADS, 0, st>>>(in, out, n_polys);
+        else ntt_fwd_kernel<6><<<persistent_grid(ctx, ntt_fwd_kernel<6>, NTT_THREADS, items), NTT_THREADS, 0, st>>>(in, out, n_polys);
+    }
+    return check(cudaGetLastError(), inverse ? "ntt_inv launch" : "ntt_fwd launch");
+}
+
+int launch_polymul(const fz_ctx* ctx, const int32_t* a, const int32_t* b, int32_t* out, size_t n_polys, cudaStream_t st) {
+    if (n_polys == 0) return 0;
+    if (ctx->logd == 8)
+        polymul_kernel<8><<<persistent_grid(ctx, polymul_kernel<8>, NTT_THREADS, (n_polys + 7) / 8), NTT_THREADS, 0, st>>>(a, b, out, n_polys);
+    else
+        polymul_kernel<6><<<persistent_grid(ctx, polymul_kernel<6>, NTT_THREADS, (n_polys + 31) / 32), NTT_THREADS, 0, st>>>(a, b, out, n_polys);
+    return check(cudaGetLastError(), "polymul launch");
+}
+
+int launch_pointwise(const fz_ctx* ctx, const int32_t* a, const int32_t* b, const int32_t* c, int32_t* out, size_t n_coef, cudaStream_t st) {
+    if (n_coef == 0) return 0;
+    const size_t n4 = n_coef / 4;  // d is a multiple of 4
+    size_t blocks = (n4 + 255) / 256;
+    const size_t cap = (size_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (c) pointwise_kernel<true><<<(int)blocks, 256, 0, st>>>((const int4*)a, (const int4*)b, (const int4*)c, (int4*)out, n4);
+    else pointwise_kernel<false><<<(int)blocks, 256, 0, st>>>((const int4*)a, (const int4*)b, nullptr, (int4*)out, n4);
+    return check(cudaGetLastError(), "pointwise launch");
+}
+
+}  // namespace fz

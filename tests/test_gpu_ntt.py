@@ -1,0 +1,126 @@
+"""GPU parity tests for K1-K5 (NTT / INTT / pointwise / fused polymul / matvec / sign MAC):
+CUDA path through the C ABI vs the CPU oracle and the reference-generated goldens."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+Q = 2147465729
+H = (Q - 1) // 2
+
+
+@pytest.fixture(scope="module")
+def ctxs():
+    from fusion_cryptography_b200 import native
+
+    return {sp: native.get_context(sp, 0) for sp in (128, 256)}
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+@pytest.mark.parametrize("secpar", [128, 256])
+def test_ntt_golden(ctxs, ntt_golden, secpar):
+    ctx = ctxs[secpar]
+    a = ntt_golden[f"a_{secpar}"].astype(np.int32)  # includes non-canonical int32 rows
+    assert np.array_equal(host(ctx.ntt_fwd(dev(a))), ntt_golden[f"fwd_{secpar}"])
+    assert np.array_equal(host(ctx.ntt_inv(dev(a))), ntt_golden[f"inv_{secpar}"])
+    b = ntt_golden[f"b_{secpar}"].astype(np.int32)
+    assert np.array_equal(host(ctx.pointwise_mul(dev(a), dev(b))),
+                          np.array([[((int(x) * int(y) + H) % Q) - H for x, y in zip(r, s)] for r, s in zip(a, b)]))
+    ac = np.array([[((int(x) + H) % Q) - H for x in row] for row in a], dtype=np.int32)
+    assert np.array_equal(host(ctx.pointwise_mul(dev(ac), dev(b))), ntt_golden[f"mul_{secpar}"])
+    fwd = ntt_golden[f"fwd_{secpar}"].astype(np.int32)
+    assert np.array_equal(host(ctx.pointwise_muladd(dev(ac), dev(b), dev(fwd))), ntt_golden[f"muladd_{secpar}"])
+    assert np.array_equal(host(ctx.polymul(dev(ac[8:12]), dev(b[8:12]))), ntt_golden[f"conv_{secpar}"])
+
+
+@pytest.mark.parametrize("secpar", [128, 256])
+@pytest.mark.parametrize("n", [0, 1, 2, 7, 33, 1000, 4099])
+def test_ntt_vs_oracle_ragged(ctxs, oracle, secpar, n):
+    ctx = ctxs[secpar]
+    d = ctx.d
+    rng = np.random.default_rng(1000 + n)
+    a = rng.integers(-H, H + 1, size=(n, d)).astype(np.int32)
+    b = rng.integers(-(2**31), 2**31, size=(n, d)).astype(np.int32)  # any int32
+    if n == 0:
+        assert ctx.ntt_fwd(dev(a)).numel() == 0
+        return
+    for x in (a, b):
+        assert np.array_equal(host(ctx.ntt_fwd(dev(x))), oracle.ntt_fwd(secpar, x))
+        assert np.array_equal(host(ctx.ntt_inv(dev(x))), oracle.ntt_inv(secpar, x))
+    assert np.array_equal(host(ctx.polymul(dev(a), dev(b))), oracle.polymul(secpar, a, b))
+    assert np.array_equal(host(ctx.pointwise_mul(dev(a), dev(b))), oracle.pointwise_mul(a, b))
+    # in place
+    t = dev(a)
+    ctx.ntt_fwd(t, out=t)
+    assert np.array_equal(host(t), oracle.ntt_fwd(secpar, a))
+    ctx.ntt_inv(t, out=t)
+    assert np.array_equal(host(t), a)  # INTT(NTT(f)) == f for canonical f
+
+
+def test_ntt_full_size_properties(ctxs, oracle):
+    """BASELINE config[1]: 2^20 secpar-256 polynomials.  Full comparison against the oracle
+    (the C oracle handles 2^20 polynomials in seconds) + round trip + linearity."""
+    ctx = ctxs[256]
+    n, d = 1 << 20, 256
+    rng = np.random.default_rng(0xF0510)
+    a = rng.integers(-H, H + 1, size=(n, d), dtype=np.int64).astype(np.int32)
+    ta = dev(a)
+    fa = ctx.ntt_fwd(ta)
+    oracle.set_threads(oracle.max_threads())
+    want = oracle.ntt_fwd(256, a)
+    assert np.array_equal(host(fa), want)
+    back = ctx.ntt_inv(fa)
+    assert torch.equal(back, ta)
+    del want, back
+    b = np.random.default_rng(0xF0511).integers(-H, H + 1, size=(n, d), dtype=np.int64).astype(np.int32)
+    tb = dev(b)
+    fb = ctx.ntt_fwd(tb)
+    # linearity: NTT(a + b) == NTT(a) + NTT(b)  (mod q, canonical)
+    s = ((ta.to(torch.int64) + tb.to(torch.int64) + H) % Q - H).to(torch.int32)
+    fs = ((fa.to(torch.int64) + fb.to(torch.int64) + H) % Q - H).to(torch.int32)
+    assert torch.equal(ctx.ntt_fwd(s), fs)
+    # fused polymul == unfused chain, and vs oracle on a slice
+    pm = ctx.polymul(ta, tb)
+    assert torch.equal(pm, ctx.ntt_inv(ctx.pointwise_mul(fa, fb)))
+    assert np.array_equal(host(pm[:4096]), oracle.polymul(256, a[:4096], b[:4096]))
+    assert np.array_equal(host(pm[-4096:]), oracle.polymul(256, a[-4096:], b[-4096:]))
+
+
+@pytest.mark.parametrize("secpar", [128, 256])
+@pytest.mark.parametrize("batch", [1, 3, 130])
+def test_matvec_and_sign_mac(ctxs, oracle, secpar, batch):
+    ctx = ctxs[secpar]
+    d, ell = ctx.d, ctx.ell
+    rng = np.random.default_rng(7 + batch)
+    A = rng.integers(-H, H + 1, size=(ell, d)).astype(np.int32)
+    s = rng.integers(-H, H + 1, size=(batch, ell, d)).astype(np.int32)
+    s[0, :, :4] = H
+    A[:, :2] = -H
+    assert np.array_equal(host(ctx.matvec(dev(A), dev(s))), oracle.matvec(secpar, A, s))
+    s2 = rng.integers(-(2**31), 2**31, size=(batch, ell, d)).astype(np.int32)  # streamed operand: any int32
+    assert np.array_equal(host(ctx.matvec(dev(A), dev(s2))), oracle.matvec(secpar, A, s2))
+    sk_r = rng.integers(-H, H + 1, size=(batch, ell, d)).astype(np.int32)
+    c = rng.integers(-H, H + 1, size=(batch, d)).astype(np.int32)
+    want = oracle.pointwise_muladd(s, np.broadcast_to(c[:, None, :], s.shape), sk_r)
+    assert np.array_equal(host(ctx.sign_mac(dev(s), dev(sk_r), dev(c))), want)
+
+
+def test_ntt_host_path(ctxs, oracle):
+    ctx = ctxs[256]
+    n = 70000  # > one 32 MiB chunk
+    rng = np.random.default_rng(3)
+    a = rng.integers(-H, H + 1, size=(n, 256)).astype(np.int32)
+    hin = torch.from_numpy(a).pin_memory()
+    hout = torch.empty_like(hin).pin_memory()
+    ctx.ntt_host(hin, hout)
+    assert np.array_equal(hout.numpy(), oracle.ntt_fwd(256, a))
+    ctx.ntt_host(hout, hin, inverse=True)
+    assert np.array_equal(hin.numpy(), a)
