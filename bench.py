@@ -49,7 +49,9 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples nvidia-smi clocks / throttle reasons.  Started before warm-up and stopped after a
+    short same-load tail so that even a very short timed region (K steps of ~1.5 ms) is covered;
+    samples whose host timestamp falls inside the timed window are preferred."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -58,10 +60,11 @@ class ClockSampler:
         self.index = index
         self.rows = []
         self.proc = None
+        self.window = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -70,7 +73,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self, t0: float, t1: float):
+        self.window = (t0, t1)
 
     def stop(self):
         if not self.proc:
@@ -80,21 +86,25 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        parsed = []
+        for ts, r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                parsed.append((ts, float(f[0]), float(f[1]), float(f[2]), [n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [p for p in parsed if self.window and self.window[0] <= p[0] <= self.window[1] + 0.06]
+        # "under load" = drawing clearly more than idle power while the same step loops
+        loaded = [p for p in parsed if p[3] > 250.0]
+        use, which = (inside, "timed region") if len(inside) >= 2 else (loaded, "same step looping around the timed region (region shorter than the sampling period)")
+        if not use:
+            use, which = parsed, "all samples"
+        reasons = sorted({n for p in use for n in p[4]})
+        return {"sm_mhz": statistics.median([p[1] for p in use]) if use else None, "sm_max_mhz": max([p[2] for p in use]) if use else None,
+                "power_w_max": max([p[3] for p in use]) if use else None, "reasons": reasons, "samples": len(use), "window": which}
 
 
 def cpu_pass(orc, a, bhat):
@@ -224,21 +234,32 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    t_pre = time.time()
+    while time.time() - t_pre < 0.4:  # untimed: lets the clock sampler see this load before timing
+        step()
+        torch.cuda.synchronize()
+    barrier()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_w0 = time.time()
     start.record()
     for i in range(args.steps):
         step(evs[i])
     end.record()
     barrier()
+    t_w1 = time.time()
     elapsed_ms = start.elapsed_time(end)
+    t_post = time.time()
+    while time.time() - t_post < 0.3:  # untimed same-load tail for the sampler
+        step()
+        torch.cuda.synchronize()
+    sampler.mark(t_w0, t_w1)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:

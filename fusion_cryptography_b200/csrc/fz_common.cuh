@@ -28,6 +28,20 @@ struct Tw {  // 64-bit Plantard constant of one twiddle, split in two words
     uint32_t lo, hi;
 };
 
+struct Sh {  // Shoup pair of one twiddle: w in [0, q) and wq = floor(w * 2^32 / q)
+    uint32_t w, wq;
+};
+
+// Shoup/Harvey multiplication by a precomputed constant: a*w mod q in [0, 2q) for ANY 32-bit a.
+// hi = floor(a*wq / 2^32) under-estimates floor(a*w/q) by at most 1, and 2q < 2^32, so the
+// wrapped 32-bit difference is exact.  Measured on B200: IMAD.HI issues every 4 cycles per
+// SM sub-partition, IMAD every 2 -- this form (one HI + two IMAD = 8 cycles of the FMA-heavy
+// pipe) is cheaper than Plantard's (two HI + one IMAD = 10 cycles).
+__device__ __forceinline__ uint32_t sh_mul(uint32_t a, uint32_t w, uint32_t wq) {
+    uint32_t hi = __umulhi(a, wq);
+    return a * w - hi * Q;
+}
+
 // a*w mod q in [0, q]; a is any 32-bit unsigned value
 __device__ __forceinline__ uint32_t pl_mul(uint32_t a, uint32_t wlo, uint32_t whi) {
     uint32_t u1 = __umulhi(a, wlo) + a * whi;
@@ -44,16 +58,19 @@ __device__ __forceinline__ int32_t pl_mul_cent(uint32_t a, uint32_t wlo, uint32_
 __device__ __forceinline__ uint32_t red_q(uint32_t x) { return min(x, x - Q); }
 
 // any int32 -> lazy unsigned residue in [0, 2q)
-__device__ __forceinline__ uint32_t to_lazy(int32_t x) { return (uint32_t)x + ((uint32_t)(x >> 31) & Q2); }
+__device__ __forceinline__ uint32_t to_lazy(int32_t x) {
+    uint32_t v = (uint32_t)x;
+    asm("{ .reg .pred p; setp.lt.s32 p, %1, 0; @p add.u32 %0, %0, %2; }" : "+r"(v) : "r"(x), "r"(Q2));
+    return v;
+}
 
 // any int32 -> [0, q]
 __device__ __forceinline__ uint32_t to_red(int32_t x) { return red_q(to_lazy(x)); }
 
 // [0, 2q] -> canonical centred
 __device__ __forceinline__ int32_t cent_u(uint32_t s) {
-    uint32_t c = s;
-    if (s > (uint32_t)HALF) c -= Q;
-    if (s > (uint32_t)HALF + Q) c -= Q;
+    uint32_t c = red_q(s);                 // [0, q]
+    if (c > (uint32_t)HALF) c -= Q;
     return (int32_t)c;
 }
 

@@ -16,18 +16,22 @@
 //     ownership into 16 contiguous coefficients per lane for the remaining log2(d)-4 stages,
 //     whose lane-dependent twiddles are fetched once per thread and stay in registers while
 //     the persistent CTA loops over polynomials;
-//   * butterflies use Plantard multiplication by precomputed 64-bit constants (3 IMAD-class
-//     instructions, result already in [0, q]) with lazy [0, 2q] sums; the final stage of each
-//     transform uses the signed variant, which yields the canonical centred residue directly.
+//   * butterflies multiply by precomputed Shoup pairs (IMAD.HI + 2 IMAD, result in [0, 2q), one
+//     fused add-min to [0, q)); measured on B200 the FMA-heavy pipe issues IMAD every 2 and
+//     IMAD.HI every 4 cycles per sub-partition, which makes this cheaper than Plantard or
+//     Montgomery forms.  The last inverse stage, which also carries n^-1, uses the signed
+//     Plantard product: it yields the canonical centred residue with no fix-up at all;
+//   * the next tile's coefficients are fetched into registers before the current tile's
+//     butterflies, so global-load latency is covered by arithmetic.
 #include "fz_common.cuh"
 #include "fz_internal.h"
 
 namespace fz {
 
-__constant__ Tw c_fwd256[256];
-__constant__ Tw c_inv256[256];
-__constant__ Tw c_fwd64[64];
-__constant__ Tw c_inv64[64];
+__constant__ Sh c_fwd256[256];
+__constant__ Sh c_inv256[256];
+__constant__ Sh c_fwd64[64];
+__constant__ Sh c_inv64[64];
 // [0] = n^-1, [1] = n^-1 * itw[1]  (last inverse stage with the scaling folded in)
 __constant__ Tw c_last256[2];
 __constant__ Tw c_last64[2];
@@ -35,16 +39,16 @@ __constant__ Tw c_last64[2];
 template <int LOGD> struct Cfg;
 template <> struct Cfg<8> {
     static constexpr int D = 256, TPP = 16, PPW = 2, WARP_WORDS = 2 * 336;
-    static __device__ __forceinline__ const Tw* fwd() { return c_fwd256; }
-    static __device__ __forceinline__ const Tw* inv() { return c_inv256; }
+    static __device__ __forceinline__ const Sh* fwd() { return c_fwd256; }
+    static __device__ __forceinline__ const Sh* inv() { return c_inv256; }
     static __device__ __forceinline__ const Tw* last() { return c_last256; }
     // row of 16 coefficients padded to 20 words; second polynomial of the warp shifted by 16 banks
     static __device__ __forceinline__ int base(int p) { return p * 336; }
 };
 template <> struct Cfg<6> {
     static constexpr int D = 64, TPP = 4, PPW = 8, WARP_WORDS = 4 * 164;
-    static __device__ __forceinline__ const Tw* fwd() { return c_fwd64; }
-    static __device__ __forceinline__ const Tw* inv() { return c_inv64; }
+    static __device__ __forceinline__ const Sh* fwd() { return c_fwd64; }
+    static __device__ __forceinline__ const Sh* inv() { return c_inv64; }
     static __device__ __forceinline__ const Tw* last() { return c_last64; }
     static __device__ __forceinline__ int base(int p) { return (p >> 1) * 164 + (p & 1) * 80; }
 };
@@ -52,24 +56,24 @@ template <> struct Cfg<6> {
 __device__ __forceinline__ int row_off(int e) { return (e >> 4) * 20 + (e & 15); }
 
 // Cooley-Tukey butterfly, algebra/ntt.py:283-289: (u, v*s) -> (u + v*s, u - v*s)
-__device__ __forceinline__ void bf_ct(uint32_t& X, uint32_t& Y, uint32_t wlo, uint32_t whi) {
-    uint32_t t = pl_mul(Y, wlo, whi);
+__device__ __forceinline__ void bf_ct(uint32_t& X, uint32_t& Y, uint32_t w, uint32_t wq) {
+    uint32_t t = red_q(sh_mul(Y, w, wq));
     uint32_t xr = red_q(X);
     X = xr + t;
     Y = xr - t + Q;
 }
 
 // Gentleman-Sande butterfly, algebra/ntt.py:363-369: (u, v) -> (u + v, (u - v)*s); u, v in [0, q]
-__device__ __forceinline__ void bf_gs(uint32_t& U, uint32_t& V, uint32_t wlo, uint32_t whi) {
+__device__ __forceinline__ void bf_gs(uint32_t& U, uint32_t& V, uint32_t w, uint32_t wq) {
     uint32_t a = U + V;
     uint32_t b = U - V + Q;
     U = red_q(a);
-    V = pl_mul(b, wlo, whi);
+    V = red_q(sh_mul(b, w, wq));
 }
 
 // twiddles of the contiguous pass for lane-in-polynomial tau: slot 8/t - 1 + j  <->  table[d/(2t) + (8/t)*tau + j]
 template <int LOGD>
-__device__ __forceinline__ void load_tw2(const Tw* table, int tau, Tw (&tw2)[15]) {
+__device__ __forceinline__ void load_tw2(const Sh* table, int tau, Sh (&tw2)[15]) {
     constexpr int D = Cfg<LOGD>::D;
 #pragma unroll
     for (int t = 8; t >= 1; t >>= 1) {
@@ -82,7 +86,7 @@ __device__ __forceinline__ void load_tw2(const Tw* table, int tau, Tw (&tw2)[15]
 // forward, long-stride stages (m = 1, 2, 4, 8); lane holds e = tau + TPP*k
 template <int LOGD>
 __device__ __forceinline__ void fwd_strided(uint32_t (&x)[16]) {
-    const Tw* tw = Cfg<LOGD>::fwd();
+    const Sh* tw = Cfg<LOGD>::fwd();
 #pragma unroll
     for (int s = 1; s <= 4; ++s) {
         const int dk = 16 >> s, m = 1 << (s - 1);
@@ -90,14 +94,14 @@ __device__ __forceinline__ void fwd_strided(uint32_t (&x)[16]) {
         for (int k = 0; k < 16; ++k) {
             if (k & dk) continue;
             const int i = k >> (5 - s);
-            bf_ct(x[k], x[k + dk], tw[m + i].lo, tw[m + i].hi);
+            bf_ct(x[k], x[k + dk], tw[m + i].w, tw[m + i].wq);
         }
     }
 }
 
 // forward, short-stride stages on 16 contiguous coefficients
 template <int LOGD>
-__device__ __forceinline__ void fwd_contig(uint32_t (&y)[16], const Tw (&tw2)[15]) {
+__device__ __forceinline__ void fwd_contig(uint32_t (&y)[16], const Sh (&tw2)[15]) {
 #pragma unroll
     for (int t = 8; t >= 1; t >>= 1) {
         if (t * 32 > Cfg<LOGD>::D) continue;
@@ -105,14 +109,14 @@ __device__ __forceinline__ void fwd_contig(uint32_t (&y)[16], const Tw (&tw2)[15
         for (int k = 0; k < 16; ++k) {
             if (k & t) continue;
             const int j = k / (2 * t);
-            bf_ct(y[k], y[k + t], tw2[8 / t - 1 + j].lo, tw2[8 / t - 1 + j].hi);
+            bf_ct(y[k], y[k + t], tw2[8 / t - 1 + j].w, tw2[8 / t - 1 + j].wq);
         }
     }
 }
 
 // inverse, short-stride stages first (t = 1, 2, 4, 8) on 16 contiguous coefficients in [0, q]
 template <int LOGD>
-__device__ __forceinline__ void inv_contig(uint32_t (&y)[16], const Tw (&tw2)[15]) {
+__device__ __forceinline__ void inv_contig(uint32_t (&y)[16], const Sh (&tw2)[15]) {
 #pragma unroll
     for (int t = 1; t <= 8; t <<= 1) {
         if (t * 32 > Cfg<LOGD>::D) continue;
@@ -120,7 +124,7 @@ __device__ __forceinline__ void inv_contig(uint32_t (&y)[16], const Tw (&tw2)[15
         for (int k = 0; k < 16; ++k) {
             if (k & t) continue;
             const int j = k / (2 * t);
-            bf_gs(y[k], y[k + t], tw2[8 / t - 1 + j].lo, tw2[8 / t - 1 + j].hi);
+            bf_gs(y[k], y[k + t], tw2[8 / t - 1 + j].w, tw2[8 / t - 1 + j].wq);
         }
     }
 }
@@ -128,7 +132,7 @@ __device__ __forceinline__ void inv_contig(uint32_t (&y)[16], const Tw (&tw2)[15
 // inverse, long-stride stages; the last one carries n^-1 and emits canonical centred values
 template <int LOGD>
 __device__ __forceinline__ void inv_strided(uint32_t (&x)[16], int32_t (&o)[16]) {
-    const Tw* tw = Cfg<LOGD>::inv();
+    const Sh* tw = Cfg<LOGD>::inv();
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const int dk = 1 << j, h = 8 >> j;
@@ -136,7 +140,7 @@ __device__ __forceinline__ void inv_strided(uint32_t (&x)[16], int32_t (&o)[16])
         for (int k = 0; k < 16; ++k) {
             if (k & dk) continue;
             const int i = k >> (j + 1);
-            bf_gs(x[k], x[k + dk], tw[h + i].lo, tw[h + i].hi);
+            bf_gs(x[k], x[k + dk], tw[h + i].w, tw[h + i].wq);
         }
     }
     const Tw* lw = Cfg<LOGD>::last();
@@ -186,16 +190,24 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_fwd_kernel(const int32_t* in,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tau = lane % C::TPP, pw = lane / C::TPP;
     uint32_t* tile = smem + warp * C::WARP_WORDS + C::base(pw);
-    Tw tw2[15];
+    Sh tw2[15];
     load_tw2<LOGD>(C::fwd(), tau, tw2);
-    const size_t per_cta = (NTT_THREADS / 32) * C::PPW;
-    for (size_t p0 = (size_t)blockIdx.x * per_cta; p0 < n_polys; p0 += (size_t)gridDim.x * per_cta) {
-        const size_t p = p0 + warp * C::PPW + pw;
+    const size_t per_cta = (NTT_THREADS / 32) * C::PPW, stride = (size_t)gridDim.x * per_cta;
+    size_t p = (size_t)blockIdx.x * per_cta + warp * C::PPW + pw;
+    int32_t raw[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) raw[k] = p < n_polys ? in[p * C::D + tau + C::TPP * k] : 0;
+    for (size_t p0 = (size_t)blockIdx.x * per_cta; p0 < n_polys; p0 += stride, p += stride) {
         const bool live = p < n_polys;
         uint32_t x[16], y[16];
-        const int32_t* src = in + p * C::D + tau;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = live ? to_lazy(src[C::TPP * k]) : 0u;
+        for (int k = 0; k < 16; ++k) x[k] = to_lazy(raw[k]);
+        {   // prefetch the next tile while this one is transformed
+            const size_t pn = p + stride;
+            const int32_t* src = in + pn * C::D + tau;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) raw[k] = pn < n_polys ? src[C::TPP * k] : 0;
+        }
         fwd_strided<LOGD>(x);
         xchg_s2c<LOGD>(tile, tau, x, y);
         fwd_contig<LOGD>(y, tw2);
@@ -215,18 +227,25 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_inv_kernel(const int32_t* in,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tau = lane % C::TPP, pw = lane / C::TPP;
     uint32_t* tile = smem + warp * C::WARP_WORDS + C::base(pw);
-    Tw tw2[15];
+    Sh tw2[15];
     load_tw2<LOGD>(C::inv(), tau, tw2);
-    const size_t per_cta = (NTT_THREADS / 32) * C::PPW;
-    for (size_t p0 = (size_t)blockIdx.x * per_cta; p0 < n_polys; p0 += (size_t)gridDim.x * per_cta) {
-        const size_t p = p0 + warp * C::PPW + pw;
+    const size_t per_cta = (NTT_THREADS / 32) * C::PPW, stride = (size_t)gridDim.x * per_cta;
+    size_t p = (size_t)blockIdx.x * per_cta + warp * C::PPW + pw;
+    int4 raw[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) raw[c] = p < n_polys ? reinterpret_cast<const int4*>(in + p * C::D + tau * 16)[c] : make_int4(0, 0, 0, 0);
+    for (size_t p0 = (size_t)blockIdx.x * per_cta; p0 < n_polys; p0 += stride, p += stride) {
         const bool live = p < n_polys;
         uint32_t x[16], y[16];
-        const int4* src = reinterpret_cast<const int4*>(in + p * C::D + tau * 16);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            int4 v = live ? src[c] : make_int4(0, 0, 0, 0);
-            y[4 * c] = to_red(v.x); y[4 * c + 1] = to_red(v.y); y[4 * c + 2] = to_red(v.z); y[4 * c + 3] = to_red(v.w);
+            y[4 * c] = to_red(raw[c].x); y[4 * c + 1] = to_red(raw[c].y); y[4 * c + 2] = to_red(raw[c].z); y[4 * c + 3] = to_red(raw[c].w);
+        }
+        {
+            const size_t pn = p + stride;
+            const int4* src = reinterpret_cast<const int4*>(in + pn * C::D + tau * 16);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) raw[c] = pn < n_polys ? src[c] : make_int4(0, 0, 0, 0);
         }
         inv_contig<LOGD>(y, tw2);
         xchg_c2s<LOGD>(tile, tau, y, x);
@@ -256,7 +275,7 @@ __global__ void __launch_bounds__(NTT_THREADS) polymul_kernel(const int32_t* a, 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tau = lane % C::TPP, pw = lane / C::TPP;
     uint32_t* tile = smem + warp * C::WARP_WORDS + C::base(pw);
-    Tw twf[15], twi[15];
+    Sh twf[15], twi[15];
     load_tw2<LOGD>(C::fwd(), tau, twf);
     load_tw2<LOGD>(C::inv(), tau, twi);
     const size_t per_cta = (NTT_THREADS / 32) * C::PPW;
@@ -336,30 +355,33 @@ static int h_brv(int i, int bits) {
     return r;
 }
 
-// tw[k] = psi^brv(k) mod q (algebra/polynomials.py:396-397, algebra/ntt.py:74-90), as Plantard constants
+// tw[k] = psi^brv(k) mod q (algebra/polynomials.py:396-397, algebra/ntt.py:74-90), as Shoup pairs
 int ntt_init_tables(fz_ctx* ctx) {
     const int levels[2][2] = {{6, 23584283}, {8, 3337519}};  // fusion.py:36-37
     for (int L = 0; L < 2; ++L) {
         const int logd = levels[L][0], d = 1 << logd;
         const unsigned long long psi = levels[L][1], ipsi = h_powmod(psi, Q - 2), ninv = h_powmod(d, Q - 2);
-        Tw f[256], iv[256], last[2];
+        Sh f[256], iv[256];
+        Tw last[2];
         unsigned long long itw1 = 0;
         for (int k = 0; k < d; ++k) {
             unsigned long long w = h_powmod(psi, h_brv(k, logd)), iw = h_powmod(ipsi, h_brv(k, logd));
-            f[k] = h_plantard(w);
-            iv[k] = h_plantard(iw);
+            f[k].w = (uint32_t)w;
+            f[k].wq = (uint32_t)((((unsigned __int128)w) << 32) / Q);
+            iv[k].w = (uint32_t)iw;
+            iv[k].wq = (uint32_t)((((unsigned __int128)iw) << 32) / Q);
             if (k == 1) itw1 = iw;
         }
         last[0] = h_plantard(ninv);
         last[1] = h_plantard((unsigned long long)(((unsigned __int128)ninv * itw1) % Q));
         cudaError_t e;
         if (logd == 8) {
-            e = cudaMemcpyToSymbol(c_fwd256, f, sizeof(Tw) * d);
-            if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_inv256, iv, sizeof(Tw) * d);
+            e = cudaMemcpyToSymbol(c_fwd256, f, sizeof(Sh) * d);
+            if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_inv256, iv, sizeof(Sh) * d);
             if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_last256, last, sizeof(last));
         } else {
-            e = cudaMemcpyToSymbol(c_fwd64, f, sizeof(Tw) * d);
-            if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_inv64, iv, sizeof(Tw) * d);
+            e = cudaMemcpyToSymbol(c_fwd64, f, sizeof(Sh) * d);
+            if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_inv64, iv, sizeof(Sh) * d);
             if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_last64, last, sizeof(last));
         }
         if (check(e, "twiddle upload")) return -1;
