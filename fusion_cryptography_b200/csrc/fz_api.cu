@@ -43,6 +43,25 @@ using namespace fz;
         }                                \
     } while (0)
 
+// workspace carving (caller-allocated device scratch; nothing is allocated per call)
+namespace {
+struct Carver {
+    char* base; size_t cap, used; bool ok;
+    Carver(void* p, size_t bytes) : base((char*)p), cap(bytes), used(0), ok(true) {}
+    template <typename T> T* take(size_t count) {
+        const size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+        T* r = (T*)(base + used);
+        used += bytes;
+        if (used > cap) ok = false;
+        return r;
+    }
+};
+constexpr size_t M1_STRIDE = 7424;       // >= 3 + longest str(vk) (512 values x 13 chars + 0.5 KB) + 1 + 78, multiple of 16
+constexpr size_t PIECE_STRIDE = 11264;   // >= longest "(" VK ", " INT ", " CH ")", multiple of 16
+inline size_t r256(size_t b) { return (b + 255) & ~(size_t)255; }
+inline size_t msg_stride_for(size_t max_keys) { return ((max_keys * (PIECE_STRIDE + 2) + 5 + 16) + 15) & ~(size_t)15; }
+}  // namespace
+
 extern "C" {
 
 int fz_version(void) { return 100; }
@@ -82,7 +101,7 @@ int fz_init(int device, int secpar, fz_ctx** out) {
     cudaDeviceProp prop;
     if (check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { delete c; return -2; }
     c->sm_count = prop.multiProcessorCount;
-    if (ntt_init_tables(c)) { delete c; return -2; }
+    if (ntt_init_tables(c) || hash_init_tables(c)) { delete c; return -2; }
     *out = c;
     return 0;
 }
@@ -132,12 +151,12 @@ int fz_polymul(fz_ctx* ctx, const int32_t* a, const int32_t* b, int32_t* out, si
 
 int fz_matvec(fz_ctx* ctx, const int32_t* A, const int32_t* s, int32_t* out, size_t batch, void* stream) {
     FZ_REQUIRE(ctx && (batch == 0 || (A && s && out)), "fz_matvec: NULL argument");
-    return launch_matvec(ctx, A, s, out, batch, (cudaStream_t)stream);
+    return launch_matvec(ctx, A, s, (size_t)ctx->d, (size_t)ctx->ell * ctx->d, out, batch, (cudaStream_t)stream);
 }
 
 int fz_sign_mac(fz_ctx* ctx, const int32_t* sk_l, const int32_t* sk_r, const int32_t* c_hat, int32_t* sig, size_t batch, void* stream) {
     FZ_REQUIRE(ctx && (batch == 0 || (sk_l && sk_r && c_hat && sig)), "fz_sign_mac: NULL argument");
-    return launch_sign_mac(ctx, sk_l, sk_r, c_hat, sig, batch, (cudaStream_t)stream);
+    return launch_sign_mac(ctx, sk_l, sk_r, (size_t)ctx->d, (size_t)ctx->ell * ctx->d, c_hat, sig, batch, (cudaStream_t)stream);
 }
 
 // Chunked H2D -> kernels -> D2H pipeline on internal streams (both copy engines run
@@ -193,6 +212,205 @@ int fz_ntt_host(fz_ctx* ctx, int inverse, const int32_t* host_in, int32_t* host_
 int fz_ntt_pass_host(fz_ctx* ctx, const int32_t* host_a, const int32_t* dev_bhat, int32_t* host_out, size_t n_polys) {
     FZ_REQUIRE(ctx && (n_polys == 0 || (host_a && dev_bhat && host_out)), "fz_ntt_pass_host: NULL argument");
     return host_pipeline(ctx, 2, host_a, dev_bhat, host_out, n_polys);
+}
+
+
+// ------------------------------------------------------------------------------------------
+
+// SHA3-256 / SHAKE256 over n byte strings data[offs[i]..offs[i+1]) (device pointers); generic, byte granular.
+int fz_sha3_256(fz_ctx* ctx, const uint8_t* data, const uint64_t* offs, size_t n, uint8_t* out32, void* stream) {
+    FZ_REQUIRE(ctx && (n == 0 || (data && offs && out32)), "fz_sha3_256: NULL argument");
+    return launch_sponge_bytes(ctx, data, (const unsigned long long*)offs, n, 0, 0, 0x06, out32, 32, 32, (cudaStream_t)stream);
+}
+
+int fz_shake256(fz_ctx* ctx, const uint8_t* data, const uint64_t* offs, size_t n, uint8_t* out, size_t out_len, void* stream) {
+    FZ_REQUIRE(ctx && (n == 0 || (data && offs && out)), "fz_shake256: NULL argument");
+    FZ_REQUIRE(out_len < ((size_t)1 << 32), "fz_shake256: out_len too large");
+    return launch_sponge_bytes(ctx, data, (const unsigned long long*)offs, n, 0, 0, 0x1F, out, out_len, (uint32_t)out_len, (cudaStream_t)stream);
+}
+
+int fz_hash_msg(fz_ctx* ctx, const uint8_t* msgs, const uint64_t* offs, size_t n, uint8_t* digests, void* stream) {
+    FZ_REQUIRE(ctx && (n == 0 || (msgs && offs && digests)), "fz_hash_msg: NULL argument");
+    const uint32_t prefix = (uint32_t)(ctx->secpar == 256 ? 3 : 1) | (0u << 8) | ((uint32_t)',' << 16);  // fusion.py:38-43, 407
+    return launch_sponge_bytes(ctx, msgs, (const unsigned long long*)offs, n, prefix, 3, 0x06, digests, 32, 32, (cudaStream_t)stream);
+}
+
+size_t fz_text_stride(const fz_ctx* ctx, int mode) { (void)ctx; return mode == 0 ? M1_STRIDE : PIECE_STRIDE; }
+
+int fz_format_text(fz_ctx* ctx, int mode, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, const int32_t* c_hat, size_t n,
+                   uint8_t* out, uint32_t* out_len, void* stream) {
+    FZ_REQUIRE(ctx && (n == 0 || (vk_l && vk_r && digests && out && out_len)), "fz_format_text: NULL argument");
+    FZ_REQUIRE(mode == 0 || (mode == 1 && (n == 0 || c_hat)), "fz_format_text: mode must be 0 (hash_ch message) or 1 (hash_ag piece, needs c_hat)");
+    return launch_format(ctx, mode, vk_l, vk_r, digests, c_hat, n, out, mode == 0 ? M1_STRIDE : PIECE_STRIDE, out_len, (cudaStream_t)stream);
+}
+
+int fz_decode_poly(fz_ctx* ctx, const uint8_t* bytes, size_t stride, size_t blen, size_t n, int log2_bias, int norm_bound, int weight_bound,
+                   int32_t* coef_out, void* stream) {
+    FZ_REQUIRE(ctx && (n == 0 || (bytes && coef_out)), "fz_decode_poly: NULL argument");
+    FZ_REQUIRE(weight_bound >= 0 && weight_bound <= 256, "fz_decode_poly: weight_bound must be in [0, 256]");
+    long long bound = norm_bound < 1073732864LL ? norm_bound : 1073732864LL;   // fusion.py:432
+    if (bound < 1) bound = 1;
+    int lb = 0;
+    while ((1LL << (lb + 1)) <= bound) ++lb;
+    const int frac = ((1LL << lb) != bound);
+    const int bpc = ceil_div(lb + frac + 1 + log2_bias, 8), bpi = ceil_div(ilog2(ctx->d) + log2_bias, 8);   // fusion.py:433-434
+    const size_t total = (size_t)ceil_div(weight_bound, 8) + (size_t)(bpc + bpi) * weight_bound;             // fusion.py:435-438
+    if (blen < total) {
+        set_error("Too few bytes to decode polynomial. Expected %zu but got %zu", total, blen);  // fusion.py:439-442
+        return -3;
+    }
+    return launch_decode(ctx, bytes, stride, (uint32_t)blen, n, weight_bound, (uint32_t)bound, bpc, bpi, coef_out, (cudaStream_t)stream);
+}
+
+size_t fz_hash_ch_workspace(const fz_ctx* ctx, size_t n) { (void)ctx; return r256(n * M1_STRIDE) + r256(n * 4) + 512; }
+
+// fusion.py:511-531 hash_ch for n (vk, prehash digest) pairs: c_hat_out[i] = NTT(decode(SHAKE256(dst "," str(vk_i) "," str(int_i))))
+int fz_hash_ch(fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, size_t n, int32_t* c_hat_out, void* ws, size_t ws_bytes,
+               void* stream) {
+    FZ_REQUIRE(ctx && (n == 0 || (vk_l && vk_r && digests && c_hat_out && ws)), "fz_hash_ch: NULL argument");
+    Carver cv(ws, ws_bytes);
+    uint8_t* m1 = cv.take<uint8_t>(n * M1_STRIDE);
+    uint32_t* len = cv.take<uint32_t>(n);
+    FZ_REQUIRE(cv.ok, "fz_hash_ch: workspace too small (see fz_hash_ch_workspace)");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_format(ctx, 0, vk_l, vk_r, digests, nullptr, n, m1, M1_STRIDE, len, st);
+    if (!rc) rc = launch_shake_decode(ctx, m1, M1_STRIDE, len, n, c_hat_out, st);
+    if (!rc) rc = launch_ntt(ctx, 0, c_hat_out, c_hat_out, n, st);
+    return rc;
+}
+
+size_t fz_hash_ag_workspace(const fz_ctx* ctx, size_t n_total, size_t n_aggs, size_t max_keys) {
+    return r256(n_total * PIECE_STRIDE) + r256(n_total * 4) + r256(n_total * 8) + r256(n_aggs * msg_stride_for(max_keys)) + r256(n_aggs * 4) +
+           r256(n_total * (size_t)ctx->n_ag + 16) + 2048;
+}
+
+// fusion.py:632-652 hash_ag for n_aggs aggregates whose (already sorted) signers are the slices
+// [agg_off[j], agg_off[j+1]) of vk_l_s / vk_r_s / dg_s / c_hat_s.  alpha_hat_out: [n_total][d] in the same order.
+int fz_hash_ag(fz_ctx* ctx, const int32_t* vk_l_s, const int32_t* vk_r_s, const uint8_t* dg_s, const int32_t* c_hat_s, const uint64_t* agg_off,
+               size_t n_aggs, size_t n_total, size_t max_keys, int32_t* alpha_hat_out, void* ws, size_t ws_bytes, void* stream) {
+    FZ_REQUIRE(ctx && (n_total == 0 || (vk_l_s && vk_r_s && dg_s && c_hat_s && agg_off && alpha_hat_out && ws)), "fz_hash_ag: NULL argument");
+    if (n_aggs == 0 || n_total == 0) return 0;
+    Carver cv(ws, ws_bytes);
+    const size_t mstride = msg_stride_for(max_keys);
+    uint8_t* pieces = cv.take<uint8_t>(n_total * PIECE_STRIDE);
+    uint32_t* plen = cv.take<uint32_t>(n_total);
+    unsigned long long* ppos = cv.take<unsigned long long>(n_total);
+    uint8_t* msgs = cv.take<uint8_t>(n_aggs * mstride);
+    uint32_t* mlen = cv.take<uint32_t>(n_aggs);
+    uint8_t* xof = cv.take<uint8_t>(n_total * (size_t)ctx->n_ag + 16);
+    FZ_REQUIRE(cv.ok, "fz_hash_ag: workspace too small (see fz_hash_ag_workspace)");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_format(ctx, 1, vk_l_s, vk_r_s, dg_s, c_hat_s, n_total, pieces, PIECE_STRIDE, plen, st);
+    if (!rc) rc = launch_ag_message(ctx, pieces, PIECE_STRIDE, plen, nullptr, (const unsigned long long*)agg_off, n_aggs, n_total, ppos, msgs, mstride, mlen, st);
+    if (!rc) rc = launch_shake_ag(ctx, msgs, mstride, mlen, (const unsigned long long*)agg_off, xof, n_aggs, st);
+    if (!rc) rc = launch_decode(ctx, xof, (size_t)ctx->n_ag, (uint32_t)ctx->n_ag, n_total, ctx->omega_ag, 1u, ctx->bytes_coef, ctx->bytes_idx, alpha_hat_out, st);
+    if (!rc) rc = launch_ntt(ctx, 0, alpha_hat_out, alpha_hat_out, n_total, st);
+    return rc;
+}
+
+// sorted(..., key=str(vk)) (fusion.py:661-663, 693): perm[agg_off[j] + rank] = original position; sel (optional) maps positions to key rows
+int fz_sort_keys(fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint32_t* sel, const uint64_t* agg_off, size_t n_aggs, size_t max_keys,
+                 uint32_t* perm, void* stream) {
+    FZ_REQUIRE(ctx && (n_aggs == 0 || (vk_l && vk_r && agg_off && perm)), "fz_sort_keys: NULL argument");
+    FZ_REQUIRE(max_keys <= 28000, "fz_sort_keys: more than 28000 keys per aggregate is not supported");
+    return launch_sort(ctx, vk_l, vk_r, sel, (const unsigned long long*)agg_off, n_aggs, max_keys, perm, (cudaStream_t)stream);
+}
+
+int fz_gather_sorted(fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, const uint32_t* sel, const uint32_t* perm,
+                     size_t n_total, int32_t* vk_l_s, int32_t* vk_r_s, uint8_t* dg_s, void* stream) {
+    FZ_REQUIRE(ctx && (n_total == 0 || (vk_l && vk_r && digests && vk_l_s && vk_r_s && dg_s)), "fz_gather_sorted: NULL argument");
+    return launch_gather_sorted(ctx, vk_l, vk_r, digests, sel, perm, n_total, vk_l_s, vk_r_s, dg_s, (cudaStream_t)stream);
+}
+
+size_t fz_aggregate_sum_workspace(const fz_ctx* ctx, size_t n_aggs, size_t max_keys) {
+    const int split = aggregate_split(ctx, n_aggs, max_keys);
+    return split == 1 ? 256 : r256((size_t)split * n_aggs * ctx->ell * ctx->d * 4) + 256;
+}
+
+// fusion.py:670-677: out[j] = sum_p sigs[perm[p]] * alpha[p] over the sorted positions p of aggregate j
+int fz_aggregate_sum(fz_ctx* ctx, const int32_t* sigs, const uint32_t* perm, const int32_t* alpha, const uint64_t* agg_off, size_t n_aggs, size_t max_keys,
+                     int32_t* out, void* ws, size_t ws_bytes, void* stream) {
+    FZ_REQUIRE(ctx && (n_aggs == 0 || (sigs && alpha && agg_off && out)), "fz_aggregate_sum: NULL argument");
+    const int split = aggregate_split(ctx, n_aggs, max_keys);
+    Carver cv(ws, ws_bytes);
+    int32_t* part = split == 1 ? nullptr : cv.take<int32_t>((size_t)split * n_aggs * ctx->ell * ctx->d);
+    FZ_REQUIRE(cv.ok && (split == 1 || ws), "fz_aggregate_sum: workspace too small (see fz_aggregate_sum_workspace)");
+    return launch_aggregate(ctx, sigs, perm, alpha, (const unsigned long long*)agg_off, n_aggs, split, part, out, (cudaStream_t)stream);
+}
+
+// modular sum of n_parts partial aggregates laid out [n_aggs][n_parts][ell][d] (e.g. all-gathered from other ranks)
+int fz_fold_partials(fz_ctx* ctx, const int32_t* parts, int n_parts, size_t n_aggs, int32_t* out, void* stream) {
+    FZ_REQUIRE(ctx && (n_aggs == 0 || (parts && out)) && n_parts >= 1 && n_parts <= 4096, "fz_fold_partials: bad argument");
+    return launch_fold_partials(ctx, parts, out, n_aggs, n_parts, (cudaStream_t)stream);
+}
+
+size_t fz_verify_check_workspace(const fz_ctx* ctx, size_t n_aggs) {
+    return 2 * r256(n_aggs * ctx->d * 4) + r256(n_aggs * (size_t)ctx->ell * ctx->d * 4) + 1024;
+}
+
+// fusion.py:690-692 + 706-728 on sorted inputs: codes[j] = 0 ok | 3 target mismatch | 4 norm too large
+int fz_verify_check(fz_ctx* ctx, const int32_t* A, const int32_t* vk_l_s, const int32_t* vk_r_s, const int32_t* c_hat_s, const int32_t* alpha_s,
+                    const int32_t* agg, const uint64_t* agg_off, size_t n_aggs, uint8_t* codes, void* ws, size_t ws_bytes, void* stream) {
+    FZ_REQUIRE(ctx && (n_aggs == 0 || (A && vk_l_s && vk_r_s && c_hat_s && alpha_s && agg && agg_off && codes && ws)), "fz_verify_check: NULL argument");
+    Carver cv(ws, ws_bytes);
+    int32_t* target = cv.take<int32_t>(n_aggs * ctx->d);
+    int32_t* observed = cv.take<int32_t>(n_aggs * ctx->d);
+    int32_t* coef = cv.take<int32_t>(n_aggs * (size_t)ctx->ell * ctx->d);
+    FZ_REQUIRE(cv.ok, "fz_verify_check: workspace too small (see fz_verify_check_workspace)");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_verify_target(ctx, vk_l_s, vk_r_s, c_hat_s, alpha_s, (const unsigned long long*)agg_off, n_aggs, target, st);
+    if (!rc) rc = launch_matvec(ctx, A, agg, (size_t)ctx->d, (size_t)ctx->ell * ctx->d, observed, n_aggs, st);
+    if (!rc) rc = launch_ntt(ctx, 1, agg, coef, n_aggs * ctx->ell, st);
+    if (!rc) rc = launch_verify_finalize(ctx, target, observed, coef, n_aggs, codes, st);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------ samplers / keygen
+// keys: [n][key_stride] little-endian 32-bit limbs of abs(seed) (CPython random.seed), klen[n] limbs used (1..8)
+int fz_sample_coef(fz_ctx* ctx, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, int norm_bound, int weight_bound, int32_t* out,
+                   void* stream) {
+    FZ_REQUIRE(ctx && (n == 0 || (keys && klen && out)) && key_stride >= 1, "fz_sample_coef: bad argument");
+    long long bound = norm_bound < 1073732864LL ? norm_bound : 1073732864LL;  // polynomials.py:450
+    FZ_REQUIRE(bound >= 1, "fz_sample_coef: norm_bound must be >= 1");
+    return launch_sample(ctx, 0, keys, key_stride, klen, n, (uint32_t)bound, weight_bound, out, (cudaStream_t)stream);
+}
+
+int fz_sample_ntt(fz_ctx* ctx, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, int32_t* out, void* stream) {
+    FZ_REQUIRE(ctx && (n == 0 || (keys && klen && out)) && key_stride >= 1, "fz_sample_ntt: bad argument");
+    return launch_sample(ctx, 1, keys, key_stride, klen, n, 0, 0, out, (cudaStream_t)stream);
+}
+
+size_t fz_keygen_workspace(const fz_ctx* ctx, size_t n) { return r256(2 * n * 4 * 4) + r256(2 * n * 4) + r256(2 * n * ctx->d * 4) + 1024; }
+
+// fusion.py:338-373 for n u64 seeds (seed_i for the left key, seed_i + 1 for the right key).
+// sk_l / sk_r ([n][ell][d]) may be NULL (keys are then not materialised); sk_hat ([n][2][d], optional) receives the
+// one distinct row of each side (quirk Q1: all ell rows of a seeded key are the same polynomial).
+int fz_keygen(fz_ctx* ctx, const int32_t* A, const uint64_t* seeds, size_t n, int32_t* sk_l, int32_t* sk_r, int32_t* sk_hat, int32_t* vk_l, int32_t* vk_r,
+              void* ws, size_t ws_bytes, void* stream) {
+    FZ_REQUIRE(ctx && (n == 0 || (A && seeds && vk_l && vk_r && ws)), "fz_keygen: NULL argument");
+    Carver cv(ws, ws_bytes);
+    uint32_t* keys = cv.take<uint32_t>(2 * n * 4);
+    int32_t* klen = cv.take<int32_t>(2 * n);
+    int32_t* tmp = sk_hat ? sk_hat : cv.take<int32_t>(2 * n * ctx->d);
+    FZ_REQUIRE(cv.ok, "fz_keygen: workspace too small (see fz_keygen_workspace)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t d = ctx->d;
+    int rc = launch_seeds_to_keys(ctx, (const unsigned long long*)seeds, n, keys, klen, st);
+    if (!rc) rc = launch_sample(ctx, 0, keys, 4, klen, 2 * n, 52u, ctx->d, tmp, st);   // beta_sk = 52, omega_sk = d (fusion.py:87, 90)
+    if (!rc) rc = launch_ntt(ctx, 0, tmp, tmp, 2 * n, st);
+    // vk = A . sk with every row of sk equal to the sampled polynomial (row stride 0)
+    if (!rc) rc = launch_matvec(ctx, A, tmp, 0, 2 * d, vk_l, n, st);
+    if (!rc) rc = launch_matvec(ctx, A, tmp + d, 0, 2 * d, vk_r, n, st);
+    if (!rc && sk_l) rc = launch_replicate_rows(ctx, tmp, sk_l, n, ctx->ell, 2 * d, st);
+    if (!rc && sk_r) rc = launch_replicate_rows(ctx, tmp + d, sk_r, n, ctx->ell, 2 * d, st);
+    return rc;
+}
+
+// fusion.py:557 with broadcast rows: sig[b][r] = sk_hat[b][0] * c_hat[b] + sk_hat[b][1] for every r (keys from fz_keygen's sk_hat)
+int fz_sign_mac_rows(fz_ctx* ctx, const int32_t* sk_hat, const int32_t* c_hat, int32_t* sig, size_t batch, void* stream) {
+    FZ_REQUIRE(ctx && (batch == 0 || (sk_hat && c_hat && sig)), "fz_sign_mac_rows: NULL argument");
+    const size_t d = ctx->d;
+    return launch_sign_mac(ctx, sk_hat, sk_hat + d, 0, 2 * d, c_hat, sig, batch, (cudaStream_t)stream);
 }
 
 }  // extern "C"

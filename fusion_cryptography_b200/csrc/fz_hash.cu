@@ -1,0 +1,607 @@
+// fz_hash.cu -- device-side derivation of challenges and aggregation coefficients, bit-exact
+// with the reference's hashlib / str() pipeline:
+//   * generic batched SHA3-256 / SHAKE256 over byte strings (fusion.py:405-409 prehash)
+//   * repr() formatter: int32 coefficients -> the exact ASCII of str(OneTimeVerificationKey) and
+//     str(SignatureChallenge) (fusion.py:328-329, 382-383; matrices.py:40-41; polynomials.py:257-258)
+//   * hash_ch: SHAKE256(dst "," str(vk) "," str(prehash)) squeezed straight into the
+//     sparse-ternary decoder (fusion.py:412-419, 422-508)
+//   * hash_ag: one serial SHAKE256 per aggregate over str(list(zip(keys, prehashes, challenges)))
+//     and slice decoding (fusion.py:573-629)
+#include <cstdio>
+#include "fz_common.cuh"
+#include "fz_internal.h"
+#include "fz_keccak.cuh"
+
+namespace fz {
+
+// ------------------------------------------------------------------------------------------
+// generic sponge: one thread per message, bytes absorbed from global memory
+// out[i*out_stride .. +out_len) = XOF(prefix || data[offs[i]..offs[i+1]))
+__global__ void __launch_bounds__(128) sponge_bytes_kernel(const uint8_t* __restrict__ data, const unsigned long long* __restrict__ offs, size_t n,
+                                                             uint32_t prefix, int prefix_len, uint8_t suffix, uint8_t* __restrict__ out,
+                                                             size_t out_stride, uint32_t out_len) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* msg = data + offs[i];
+    const size_t mlen = (size_t)(offs[i + 1] - offs[i]);
+    const size_t total = mlen + prefix_len;
+    unsigned long long a[25];
+#pragma unroll
+    for (int k = 0; k < 25; ++k) a[k] = 0;
+    unsigned long long blk[KECCAK_RATE_LANES];
+    size_t pos = 0;
+    for (;;) {
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) blk[k] = 0;
+        const size_t take = total - pos < (size_t)KECCAK_RATE ? total - pos : (size_t)KECCAK_RATE;
+        for (size_t j = 0; j < take; ++j) {
+            const size_t g = pos + j;
+            const uint8_t b = g < (size_t)prefix_len ? (uint8_t)(prefix >> (8 * g)) : msg[g - prefix_len];
+            blk[j >> 3] |= (unsigned long long)b << (8 * (j & 7));
+        }
+        pos += take;
+        const bool last = take < (size_t)KECCAK_RATE;
+        if (last) {
+            blk[take >> 3] ^= (unsigned long long)suffix << (8 * (take & 7));
+            blk[16] ^= 0x8000000000000000ULL;
+        }
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) a[k] ^= blk[k];
+        keccak_f(a);
+        if (last) break;
+    }
+    uint8_t* o = out + i * out_stride;
+    uint32_t produced = 0;
+    while (produced < out_len) {
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) blk[k] = a[k];
+        const uint32_t take = out_len - produced < (uint32_t)KECCAK_RATE ? out_len - produced : (uint32_t)KECCAK_RATE;
+        for (uint32_t j = 0; j < take; ++j) o[produced + j] = (uint8_t)(blk[j >> 3] >> (8 * (j & 7)));
+        produced += take;
+        if (produced < out_len) keccak_f(a);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// repr formatter
+struct FmtConst {
+    // fixed text fragments of one level, assembled on the host at init
+    char poly_head[160];   // "PolynomialNTTRepresentation(modulus=..., values=["
+    int poly_head_len;
+    char gm_head[112];     // "GeneralMatrix(elem_class=<class 'algebra.polynomials.PolynomialNTTRepresentation'>, matrix=[["
+    int gm_head_len;
+};
+__constant__ FmtConst c_fmt[2];  // [0] secpar 128, [1] secpar 256
+
+__device__ __forceinline__ int dec_len(int32_t v) {
+    uint32_t u = v < 0 ? (uint32_t)(-(long long)v) : (uint32_t)v;
+    int n = 1;
+    if (u >= 10u) n = 2;
+    if (u >= 100u) n = 3;
+    if (u >= 1000u) n = 4;
+    if (u >= 10000u) n = 5;
+    if (u >= 100000u) n = 6;
+    if (u >= 1000000u) n = 7;
+    if (u >= 10000000u) n = 8;
+    if (u >= 100000000u) n = 9;
+    if (u >= 1000000000u) n = 10;
+    return n + (v < 0 ? 1 : 0);
+}
+
+// writes the decimal text of v (Python str(int)) at dst, returns its length
+__device__ __forceinline__ int dec_write(uint8_t* dst, int32_t v) {
+    const int len = dec_len(v);
+    uint32_t u = v < 0 ? (uint32_t)(-(long long)v) : (uint32_t)v;
+    int p = len;
+    do {
+        const uint32_t q10 = u / 10u;
+        dst[--p] = (uint8_t)('0' + (u - q10 * 10u));
+        u = q10;
+    } while (u);
+    if (v < 0) dst[0] = '-';
+    return len;
+}
+
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    total = __shfl_sync(0xffffffffu, x, 31);
+    return x - v;
+}
+
+__device__ __forceinline__ int put_str(uint8_t* dst, const char* s, int len, int lane) {
+    for (int i = lane; i < len; i += 32) dst[i] = (uint8_t)s[i];
+    return len;
+}
+
+// One warp writes "v0, v1, ..., v_{d-1}" (the inside of a Python list of ints) into shared memory.
+__device__ int warp_format_values(uint8_t* dst, const int32_t* __restrict__ vals, int d, int lane) {
+    const int per = d / 32;  // 8 (d = 256) or 2 (d = 64)
+    int32_t v[8];
+    int my = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (j < per) {
+            v[j] = vals[lane * per + j];
+            my += dec_len(v[j]) + 2;  // ", " after every value; the trailing one is dropped below
+        }
+    int total;
+    int off = warp_excl_scan(my, lane, total);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (j < per) {
+            off += dec_write(dst + off, v[j]);
+            if (!(lane == 31 && j == per - 1)) { dst[off] = ','; dst[off + 1] = ' '; }
+            off += 2;
+        }
+    return total - 2;
+}
+
+// "PolynomialNTTRepresentation(...values=[...])"
+__device__ int warp_format_poly(uint8_t* dst, const FmtConst& fc, const int32_t* vals, int d, int lane) {
+    int o = put_str(dst, fc.poly_head, fc.poly_head_len, lane);
+    o += warp_format_values(dst + o, vals, d, lane);
+    if (lane == 0) { dst[o] = ']'; dst[o + 1] = ')'; }
+    return o + 2;
+}
+
+// "GeneralMatrix(elem_class=..., matrix=[[POLY]])"
+__device__ int warp_format_gm1(uint8_t* dst, const FmtConst& fc, const int32_t* vals, int d, int lane) {
+    int o = put_str(dst, fc.gm_head, fc.gm_head_len, lane);
+    o += warp_format_poly(dst + o, fc, vals, d, lane);
+    if (lane == 0) { dst[o] = ']'; dst[o + 1] = ']'; dst[o + 2] = ')'; }
+    return o + 3;
+}
+
+// decimal of int.from_bytes(digest, "little") (fusion.py:409 then str()), one lane, returns length (<= 78)
+__device__ int format_le256(uint8_t* dst, const uint8_t* __restrict__ dg) {
+    uint32_t limb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        limb[i] = (uint32_t)dg[4 * i] | ((uint32_t)dg[4 * i + 1] << 8) | ((uint32_t)dg[4 * i + 2] << 16) | ((uint32_t)dg[4 * i + 3] << 24);
+    uint8_t tmp[88];  // up to 9 groups of 9 digits before the leading zeros are stripped
+    int n = 0;
+    for (;;) {
+        uint32_t nz = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nz |= limb[i];
+        if (!nz) break;
+        // divide by 10^9, emit 9 digits
+        unsigned long long rem = 0;
+#pragma unroll
+        for (int i = 7; i >= 0; --i) {
+            unsigned long long cur = (rem << 32) | limb[i];
+            limb[i] = (uint32_t)(cur / 1000000000ULL);
+            rem = cur - (unsigned long long)limb[i] * 1000000000ULL;
+        }
+        uint32_t r = (uint32_t)rem;
+        for (int k = 0; k < 9; ++k) { tmp[n++] = (uint8_t)('0' + r % 10u); r /= 10u; }
+    }
+    while (n > 1 && tmp[n - 1] == '0') --n;  // strip leading zeros of the most significant group
+    if (n == 0) tmp[n++] = '0';
+    for (int i = 0; i < n; ++i) dst[i] = tmp[n - 1 - i];
+    return n;
+}
+
+constexpr int FMT_WARPS = 4;
+constexpr int FMT_SMEM_PER_WARP = 11264;  // >= longest piece "(" VK ", " INT ", " CH ")": 768 values x 13 chars + 0.7 KB fixed text
+
+__device__ __forceinline__ void copy_out(uint8_t* __restrict__ dst, const uint8_t* src, int len, int lane) {
+    // dst is 16-byte aligned, src is 16-byte aligned shared memory; pad bytes beyond len are don't-care
+    const int n16 = (len + 15) >> 4;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (int i = lane; i < n16; i += 32) d4[i] = s4[i];
+}
+
+// mode 0: hash_ch message   dst "," VK "," INT                                  (fusion.py:416-418)
+// mode 1: hash_ag piece     "(" VK ", " INT ", " "SignatureChallenge(c_hat=" POLY ")" ")"   (fusion.py:589)
+// One warp per signer; text is assembled in shared memory and copied out with 16-byte stores.
+__global__ void __launch_bounds__(FMT_WARPS * 32) format_kernel(int mode, int level, int d, uint8_t dst0, const int32_t* __restrict__ vk_l,
+                                                                 const int32_t* __restrict__ vk_r, const uint8_t* __restrict__ digests,
+                                                                 const int32_t* __restrict__ c_hat, size_t n, uint8_t* __restrict__ out, size_t out_stride,
+                                                                 uint32_t* __restrict__ out_len) {
+    extern __shared__ __align__(16) uint8_t fsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* buf = fsm + (size_t)warp * FMT_SMEM_PER_WARP;
+    const FmtConst& fc = c_fmt[level];
+    for (size_t i = (size_t)blockIdx.x * FMT_WARPS + warp; i < n; i += (size_t)gridDim.x * FMT_WARPS) {
+        int o = 0;
+        if (mode == 0) {
+            if (lane == 0) { buf[0] = dst0; buf[1] = 1; buf[2] = ','; }
+            o = 3;
+        } else {
+            if (lane == 0) buf[0] = '(';
+            o = 1;
+        }
+        const char h1[] = "OneTimeVerificationKey(left_vk_hat=";
+        const char h2[] = ", right_vk_hat=";
+        o += put_str(buf + o, h1, 35, lane);
+        o += warp_format_gm1(buf + o, fc, vk_l + i * d, d, lane);
+        o += put_str(buf + o, h2, 15, lane);
+        o += warp_format_gm1(buf + o, fc, vk_r + i * d, d, lane);
+        if (lane == 0) buf[o] = ')';
+        o += 1;
+        if (mode == 0) {
+            if (lane == 0) buf[o] = ',';
+            o += 1;
+        } else {
+            if (lane == 0) { buf[o] = ','; buf[o + 1] = ' '; }
+            o += 2;
+        }
+        __syncwarp();
+        int li = 0;
+        if (lane == 0) li = format_le256(buf + o, digests + i * 32);
+        li = __shfl_sync(0xffffffffu, li, 0);
+        o += li;
+        if (mode == 1) {
+            const char h3[] = ", SignatureChallenge(c_hat=";
+            o += put_str(buf + o, h3, 27, lane);
+            o += warp_format_poly(buf + o, fc, c_hat + i * d, d, lane);
+            if (lane == 0) { buf[o] = ')'; buf[o + 1] = ')'; }
+            o += 2;
+        }
+        __syncwarp();
+        // zero the tail of the last 16-byte group so the copy never publishes stale bytes
+        for (int k = o + lane; k < ((o + 15) & ~15); k += 32) buf[k] = 0;
+        __syncwarp();
+        copy_out(out + i * out_stride, buf, o, lane);
+        if (lane == 0) out_len[i] = (uint32_t)o;
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// sparse ternary decoder (fusion.py:422-481) as a byte-driven state machine.
+// Phases: signum bytes -> weight magnitudes (bpc bytes each) -> partial Fisher-Yates (bpi bytes each).
+// c_magic[m] = ceil(2^32 / m): for m <= 256 and v < 2^24, umulhi(v, c_magic[m]) == floor(v / m) exactly.
+__constant__ uint32_t c_magic[257];
+
+struct Decoder {
+    int d, weight, bpc, bpi, bfs;
+    uint32_t bound;
+    int phase;      // 0 signums, 1 magnitudes, 2 shuffle, 3 done
+    int item;       // index within the phase
+    int left;       // bytes left in the current item
+    unsigned long long acc;   // magnitude accumulator (general bound)
+    uint32_t acc32, m, magic; // shuffle accumulator, modulus i+1 and its reciprocal
+    unsigned long long sg[4]; // big-endian integer of the signum bytes (weight <= 256 bits)
+};
+
+__device__ __forceinline__ int sign_of(const Decoder& s, int i) {  // bit i (LSB first) of the big-endian signum integer
+    return 2 * (int)((s.sg[(i >> 6) & 3] >> (i & 63)) & 1ULL) - 1;
+}
+
+__device__ __forceinline__ void dec_set_shuffle_item(Decoder& s, int i) {
+    s.item = i; s.left = s.bpi; s.acc32 = 0;
+    s.m = (uint32_t)(i + 1);
+    s.magic = c_magic[s.m <= 256 ? s.m : 0];
+}
+
+// finish the current item (called when its bytes are exhausted OR the byte string ended: Python slices
+// past the end yield shorter/empty byte strings and int.from_bytes(b"") == 0 -- SURVEY quirk Q4)
+__device__ __forceinline__ void dec_finish_item(Decoder& s, int32_t* c) {
+    if (s.phase == 0) {
+        s.phase = 1; s.item = 0; s.left = s.bpc; s.acc = 0;
+        if (s.weight == 0) { s.phase = 2; dec_set_shuffle_item(s, s.d - 1); }
+    } else if (s.phase == 1) {
+        const int i = s.item;
+        // magnitude = (int(bytes) % bound) + 1, times signum (fusion.py:463-465)
+        const long long mag = (long long)(s.bound == 1 ? 0ULL : s.acc % s.bound) + 1;
+        if (i < s.d) c[i] = (int32_t)(mag * sign_of(s, i));
+        s.item++; s.left = s.bpc; s.acc = 0;
+        if (s.item >= s.weight) { s.phase = 2; dec_set_shuffle_item(s, s.d - 1); }
+    } else if (s.phase == 2) {
+        const int i = s.item;
+        const int j = (int)s.acc32;  // already reduced mod i + 1
+        const int32_t t = c[i]; c[i] = c[j]; c[j] = t;
+        dec_set_shuffle_item(s, i - 1);
+    }
+    // fusion.py:472-473: shuffle only if num_coefs < degree, for i = d-1 ... weight+1
+    if (s.phase == 2 && (s.item <= s.weight || s.weight >= s.d)) s.phase = 3;
+}
+
+__device__ __forceinline__ void dec_init(Decoder& s, int32_t* c, int d, int weight, uint32_t bound, int bpc, int bpi) {
+    s.d = d; s.weight = weight; s.bound = bound; s.bpc = bpc; s.bpi = bpi;
+    s.bfs = (weight + 7) / 8;
+    s.phase = 0; s.item = 0; s.left = s.bfs; s.acc = 0; s.acc32 = 0; s.m = 1; s.magic = 0;
+    s.sg[0] = s.sg[1] = s.sg[2] = s.sg[3] = 0;
+    while (s.left == 0 && s.phase != 3) dec_finish_item(s, c);
+}
+
+__device__ __forceinline__ void dec_byte(Decoder& s, int32_t* c, uint32_t b) {
+    if (s.phase == 2) {
+        // Horner step with exact reciprocal: acc32 < m <= 256  =>  v < 2^16 + 2^8
+        const uint32_t v = (s.acc32 << 8) | b;
+        s.acc32 = v - __umulhi(v, s.magic) * s.m;
+    } else if (s.phase == 1) {
+        if (s.bound != 1) s.acc = ((s.acc << 8) | b) % s.bound;
+    } else {
+        s.sg[3] = (s.sg[3] << 8) | (s.sg[2] >> 56);
+        s.sg[2] = (s.sg[2] << 8) | (s.sg[1] >> 56);
+        s.sg[1] = (s.sg[1] << 8) | (s.sg[0] >> 56);
+        s.sg[0] = (s.sg[0] << 8) | b;
+    }
+    if (--s.left == 0) dec_finish_item(s, c);
+}
+
+// drain: the byte string is exhausted; remaining items see empty / truncated slices
+__device__ __forceinline__ void dec_drain(Decoder& s, int32_t* c) {
+    while (s.phase != 3) dec_finish_item(s, c);
+}
+
+constexpr int HC_THREADS = 64;
+
+// hash_ch core: one thread per signer.  msg: [n][stride] (8-byte aligned), 17 x 8-byte loads per block.
+// Squeezes n_used bytes and feeds them to the decoder; writes d int32 coefficients (NOT yet transformed).
+__global__ void __launch_bounds__(HC_THREADS) shake_decode_kernel(const uint8_t* __restrict__ msg, size_t stride, const uint32_t* __restrict__ len,
+                                                                    size_t n, int d, int weight, uint32_t bound, int bpc, int bpi, uint32_t n_used,
+                                                                    int32_t* __restrict__ coef_out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long* m = reinterpret_cast<const unsigned long long*>(msg + i * stride);
+    const uint32_t L = len[i];
+    unsigned long long a[25];
+#pragma unroll
+    for (int k = 0; k < 25; ++k) a[k] = 0;
+    const uint32_t nfull = L / KECCAK_RATE;
+    for (uint32_t b = 0; b < nfull; ++b) {
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) a[k] ^= m[(size_t)b * KECCAK_RATE_LANES + k];
+        keccak_f(a);
+    }
+    {
+        unsigned long long blk[KECCAK_RATE_LANES];
+        const uint32_t rem = L - nfull * KECCAK_RATE;
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) {
+            unsigned long long w = 0;
+            if ((uint32_t)(8 * k) < rem) {
+                w = m[(size_t)nfull * KECCAK_RATE_LANES + k];
+                const uint32_t valid = rem - 8 * k;
+                if (valid < 8) w &= (1ULL << (8 * valid)) - 1ULL;
+            }
+            blk[k] = w;
+        }
+        blk[rem >> 3] ^= 0x1FULL << (8 * (rem & 7));
+        blk[16] ^= 0x8000000000000000ULL;
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) a[k] ^= blk[k];
+        keccak_f(a);
+    }
+    int32_t c[256];
+    for (int k = 0; k < d; ++k) c[k] = 0;
+    Decoder s;
+    dec_init(s, c, d, weight, bound, bpc, bpi);
+    uint32_t produced = 0;
+    while (produced < n_used && s.phase != 3) {
+        unsigned long long blk[KECCAK_RATE_LANES];
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) blk[k] = a[k];
+        const uint32_t take = n_used - produced < (uint32_t)KECCAK_RATE ? n_used - produced : (uint32_t)KECCAK_RATE;
+        for (uint32_t j = 0; j < take && s.phase != 3; ++j) dec_byte(s, c, (uint32_t)(blk[j >> 3] >> (8 * (j & 7))) & 0xffu);
+        produced += take;
+        if (produced < n_used && s.phase != 3) keccak_f(a);
+    }
+    dec_drain(s, c);
+    int32_t* o = coef_out + i * d;
+    for (int k = 0; k < d; ++k) o[k] = c[k];
+}
+
+// standalone decoder over caller-supplied bytes (one thread per polynomial): bytes[i*stride .. +blen)
+__global__ void __launch_bounds__(HC_THREADS) decode_kernel(const uint8_t* __restrict__ bytes, size_t stride, uint32_t blen, size_t n, int d, int weight,
+                                                             uint32_t bound, int bpc, int bpi, int32_t* __restrict__ coef_out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* b = bytes + i * stride;
+    int32_t c[256];
+    for (int k = 0; k < d; ++k) c[k] = 0;
+    Decoder s;
+    dec_init(s, c, d, weight, bound, bpc, bpi);
+    for (uint32_t j = 0; j < blen && s.phase != 3; ++j) dec_byte(s, c, b[j]);
+    dec_drain(s, c);
+    int32_t* o = coef_out + i * d;
+    for (int k = 0; k < d; ++k) o[k] = c[k];
+}
+
+// ------------------------------------------------------------------------------------------
+// hash_ag message layout: per aggregate j with sorted signer list order[agg_off[j] .. agg_off[j+1]):
+//   message = dst(2) "," "[" piece_0 ", " piece_1 ... "]"
+// One CTA per aggregate computes the exclusive scan of piece lengths (+2 separators).
+__global__ void __launch_bounds__(256) ag_layout_kernel(const uint32_t* __restrict__ piece_len, const uint32_t* __restrict__ order,
+                                                          const unsigned long long* __restrict__ agg_off, size_t msg_stride,
+                                                          unsigned long long* __restrict__ piece_pos, uint32_t* __restrict__ msg_len) {
+    __shared__ unsigned long long warp_sum[8];
+    __shared__ unsigned long long carry;
+    const size_t j = blockIdx.x;
+    const size_t lo = agg_off[j], hi = agg_off[j + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 4;  // dst0 dst1 ',' '['
+    __syncthreads();
+    for (size_t base = lo; base < hi; base += 256) {
+        const size_t p = base + threadIdx.x;
+        unsigned long long v = 0;
+        if (p < hi) v = (unsigned long long)piece_len[order ? order[p] : (uint32_t)p] + (p > lo ? 2 : 0);
+        unsigned long long x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sum[warp] = x;
+        __syncthreads();
+        unsigned long long wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += warp_sum[w];
+        const unsigned long long c0 = carry;
+        if (p < hi) piece_pos[p] = j * msg_stride + c0 + wbase + x - v + (p > lo ? 2 : 0);  // start of the piece text itself
+        __syncthreads();
+        if (threadIdx.x == 255) carry = c0 + wbase + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) msg_len[j] = (uint32_t)(carry + 1);  // closing ']'
+}
+
+// copies piece text to its place in the aggregate's message; one CTA per sorted position
+__global__ void __launch_bounds__(128) ag_pack_kernel(const uint8_t* __restrict__ pieces, size_t piece_stride, const uint32_t* __restrict__ piece_len,
+                                                        const uint32_t* __restrict__ order, const unsigned long long* __restrict__ agg_off,
+                                                        const unsigned long long* __restrict__ piece_pos, size_t msg_stride, uint8_t dst0,
+                                                        uint8_t* __restrict__ msgs, const uint32_t* __restrict__ msg_len, size_t n_aggs, size_t n_total) {
+    const size_t p = blockIdx.x;
+    if (p < n_total) {
+        const uint32_t sidx = order ? order[p] : (uint32_t)p;
+        const uint8_t* src = pieces + (size_t)sidx * piece_stride;
+        const uint32_t L = piece_len[sidx];
+        uint8_t* dst = msgs + piece_pos[p];
+        for (uint32_t k = threadIdx.x; k < L; k += blockDim.x) dst[k] = src[k];
+        // separator before every piece but the first of its aggregate: detect via position
+        if (threadIdx.x == 0) {
+            // find whether p is the first of its aggregate: piece_pos[p] - (agg base) == 4
+            const unsigned long long rel = piece_pos[p] % msg_stride;
+            if (rel != 4) { dst[-2] = ','; dst[-1] = ' '; }
+        }
+    } else {
+        // header / footer blocks: one per aggregate
+        const size_t j = p - n_total;
+        if (j < n_aggs && threadIdx.x == 0) {
+            uint8_t* m = msgs + j * msg_stride;
+            m[0] = dst0; m[1] = 2; m[2] = ','; m[3] = '[';
+            m[msg_len[j] - 1] = ']';
+        }
+    }
+}
+
+// one serial sponge per aggregate: absorb msgs[j], squeeze out_len[j] bytes to xof + xof_off[j]
+__global__ void __launch_bounds__(32) shake_ag_kernel(const uint8_t* __restrict__ msgs, size_t msg_stride, const uint32_t* __restrict__ msg_len,
+                                                        const unsigned long long* __restrict__ agg_off, uint32_t n_ag, uint8_t* __restrict__ xof,
+                                                        size_t n_aggs) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_aggs) return;
+    const unsigned long long* m = reinterpret_cast<const unsigned long long*>(msgs + j * msg_stride);
+    const uint32_t L = msg_len[j];
+    unsigned long long a[25];
+#pragma unroll
+    for (int k = 0; k < 25; ++k) a[k] = 0;
+    const uint32_t nfull = L / KECCAK_RATE;
+    for (uint32_t b = 0; b < nfull; ++b) {
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) a[k] ^= m[(size_t)b * KECCAK_RATE_LANES + k];
+        keccak_f(a);
+    }
+    {
+        unsigned long long blk[KECCAK_RATE_LANES];
+        const uint32_t rem = L - nfull * KECCAK_RATE;
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) {
+            unsigned long long w = 0;
+            if ((uint32_t)(8 * k) < rem) {
+                w = m[(size_t)nfull * KECCAK_RATE_LANES + k];
+                const uint32_t valid = rem - 8 * k;
+                if (valid < 8) w &= (1ULL << (8 * valid)) - 1ULL;
+            }
+            blk[k] = w;
+        }
+        blk[rem >> 3] ^= 0x1FULL << (8 * (rem & 7));
+        blk[16] ^= 0x8000000000000000ULL;
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) a[k] ^= blk[k];
+        keccak_f(a);
+    }
+    // squeeze (hi - lo) * n_ag bytes, contiguous at xof + lo * n_ag  (fusion.py:583-591, 599-605)
+    const unsigned long long lo = agg_off[j], hi = agg_off[j + 1];
+    unsigned long long total = (hi - lo) * (unsigned long long)n_ag, produced = 0;
+    uint8_t* o = xof + lo * (unsigned long long)n_ag;
+    while (produced < total) {
+        unsigned long long blk[KECCAK_RATE_LANES];
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) blk[k] = a[k];
+        const uint32_t take = total - produced < (unsigned long long)KECCAK_RATE ? (uint32_t)(total - produced) : (uint32_t)KECCAK_RATE;
+        for (uint32_t k = 0; k < take; ++k) o[produced + k] = (uint8_t)(blk[k >> 3] >> (8 * (k & 7)));
+        produced += take;
+        if (produced < total) keccak_f(a);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+int hash_init_tables(fz_ctx* ctx) {
+    FmtConst h[2];
+    const int degs[2] = {64, 256};
+    const unsigned roots[2] = {23584283u, 3337519u}, iroots[2] = {540632852u, 1978410468u};
+    for (int L = 0; L < 2; ++L) {
+        h[L].poly_head_len = snprintf(h[L].poly_head, sizeof(h[L].poly_head),
+                                      "PolynomialNTTRepresentation(modulus=2147465729, degree=%d, root=%u, inv_root=%u, root_order=%d, values=[",
+                                      degs[L], roots[L], iroots[L], 2 * degs[L]);
+        h[L].gm_head_len = snprintf(h[L].gm_head, sizeof(h[L].gm_head),
+                                    "GeneralMatrix(elem_class=<class 'algebra.polynomials.PolynomialNTTRepresentation'>, matrix=[[");
+    }
+    (void)ctx;
+    uint32_t magic[257];
+    magic[0] = 0; magic[1] = 0;  // m = 1 never occurs in the shuffle (i >= 1)
+    for (uint32_t m = 2; m <= 256; ++m) magic[m] = 0xFFFFFFFFu / m + 1u;
+    if (check(cudaMemcpyToSymbol(c_magic, magic, sizeof(magic)), "decoder constants upload")) return -2;
+    return check(cudaMemcpyToSymbol(c_fmt, h, sizeof(h)), "format constants upload");
+}
+
+static int grid_for(size_t n, int per_block) { return (int)((n + per_block - 1) / per_block); }
+
+int launch_sponge_bytes(const fz_ctx* ctx, const uint8_t* data, const unsigned long long* offs, size_t n, uint32_t prefix, int prefix_len,
+                        uint8_t suffix, uint8_t* out, size_t out_stride, uint32_t out_len, cudaStream_t st) {
+    if (n == 0) return 0;
+    sponge_bytes_kernel<<<grid_for(n, 128), 128, 0, st>>>(data, offs, n, prefix, prefix_len, suffix, out, out_stride, out_len);
+    (void)ctx;
+    return check(cudaGetLastError(), "sponge_bytes launch");
+}
+
+int launch_format(const fz_ctx* ctx, int mode, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, const int32_t* c_hat, size_t n,
+                  uint8_t* out, size_t out_stride, uint32_t* out_len, cudaStream_t st) {
+    if (n == 0) return 0;
+    static bool attr_set = false;
+    const int smem = FMT_WARPS * FMT_SMEM_PER_WARP;
+    if (!attr_set) {
+        if (check(cudaFuncSetAttribute(format_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "format smem attr")) return -2;
+        attr_set = true;
+    }
+    size_t blocks = (n + FMT_WARPS - 1) / FMT_WARPS;
+    const size_t cap = (size_t)ctx->sm_count * 5;
+    if (blocks > cap) blocks = cap;
+    format_kernel<<<(int)blocks, FMT_WARPS * 32, smem, st>>>(mode, ctx->secpar == 256 ? 1 : 0, ctx->d, (uint8_t)(ctx->secpar == 256 ? 3 : 1), vk_l, vk_r,
+                                                              digests, c_hat, n, out, out_stride, out_len);
+    return check(cudaGetLastError(), "format launch");
+}
+
+int launch_shake_decode(const fz_ctx* ctx, const uint8_t* msg, size_t stride, const uint32_t* len, size_t n, int32_t* coef_out, cudaStream_t st) {
+    if (n == 0) return 0;
+    shake_decode_kernel<<<grid_for(n, HC_THREADS), HC_THREADS, 0, st>>>(msg, stride, len, n, ctx->d, ctx->omega_ch, 1u, ctx->bytes_coef, ctx->bytes_idx,
+                                                                           (uint32_t)ctx->n_ch_used, coef_out);
+    return check(cudaGetLastError(), "shake_decode launch");
+}
+
+int launch_decode(const fz_ctx* ctx, const uint8_t* bytes, size_t stride, uint32_t blen, size_t n, int weight, uint32_t bound, int bpc, int bpi,
+                  int32_t* coef_out, cudaStream_t st) {
+    if (n == 0) return 0;
+    decode_kernel<<<grid_for(n, HC_THREADS), HC_THREADS, 0, st>>>(bytes, stride, blen, n, ctx->d, weight, bound, bpc, bpi, coef_out);
+    return check(cudaGetLastError(), "decode launch");
+}
+
+int launch_ag_message(const fz_ctx* ctx, const uint8_t* pieces, size_t piece_stride, const uint32_t* piece_len, const uint32_t* order,
+                      const unsigned long long* agg_off, size_t n_aggs, size_t n_total, unsigned long long* piece_pos, uint8_t* msgs, size_t msg_stride,
+                      uint32_t* msg_len, cudaStream_t st) {
+    if (n_aggs == 0) return 0;
+    ag_layout_kernel<<<(int)n_aggs, 256, 0, st>>>(piece_len, order, agg_off, msg_stride, piece_pos, msg_len);
+    if (check(cudaGetLastError(), "ag_layout launch")) return -2;
+    ag_pack_kernel<<<(int)(n_total + n_aggs), 128, 0, st>>>(pieces, piece_stride, piece_len, order, agg_off, piece_pos, msg_stride,
+                                                            (uint8_t)(ctx->secpar == 256 ? 3 : 1), msgs, msg_len, n_aggs, n_total);
+    return check(cudaGetLastError(), "ag_pack launch");
+}
+
+int launch_shake_ag(const fz_ctx* ctx, const uint8_t* msgs, size_t msg_stride, const uint32_t* msg_len, const unsigned long long* agg_off, uint8_t* xof,
+                    size_t n_aggs, cudaStream_t st) {
+    if (n_aggs == 0) return 0;
+    shake_ag_kernel<<<grid_for(n_aggs, 32), 32, 0, st>>>(msgs, msg_stride, msg_len, agg_off, (uint32_t)ctx->n_ag, xof, n_aggs);
+    return check(cudaGetLastError(), "shake_ag launch");
+}
+
+}  // namespace fz

@@ -32,7 +32,45 @@ int launch_polymul(const fz_ctx* ctx, const int32_t* a, const int32_t* b, int32_
 int launch_pointwise(const fz_ctx* ctx, const int32_t* a, const int32_t* b, const int32_t* c, int32_t* out, size_t n_coef, cudaStream_t st);
 
 // fz_stream.cu
-int launch_matvec(const fz_ctx* ctx, const int32_t* A, const int32_t* s, int32_t* out, size_t batch, cudaStream_t st);
-int launch_sign_mac(const fz_ctx* ctx, const int32_t* sk_l, const int32_t* sk_r, const int32_t* c_hat, int32_t* sig, size_t batch, cudaStream_t st);
+int launch_matvec(const fz_ctx* ctx, const int32_t* A, const int32_t* s, size_t s_row_stride, size_t s_batch_stride, int32_t* out, size_t batch,
+                  cudaStream_t st);
+int launch_sign_mac(const fz_ctx* ctx, const int32_t* sk_l, const int32_t* sk_r, size_t sk_row_stride, size_t sk_batch_stride, const int32_t* c_hat,
+                    int32_t* sig, size_t batch, cudaStream_t st);
+
+
+// fz_hash.cu
+int hash_init_tables(fz_ctx* ctx);
+int launch_sponge_bytes(const fz_ctx* ctx, const uint8_t* data, const unsigned long long* offs, size_t n, uint32_t prefix, int prefix_len,
+                        uint8_t suffix, uint8_t* out, size_t out_stride, uint32_t out_len, cudaStream_t st);
+int launch_format(const fz_ctx* ctx, int mode, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, const int32_t* c_hat, size_t n,
+                  uint8_t* out, size_t out_stride, uint32_t* out_len, cudaStream_t st);
+int launch_shake_decode(const fz_ctx* ctx, const uint8_t* msg, size_t stride, const uint32_t* len, size_t n, int32_t* coef_out, cudaStream_t st);
+int launch_decode(const fz_ctx* ctx, const uint8_t* bytes, size_t stride, uint32_t blen, size_t n, int weight, uint32_t bound, int bpc, int bpi,
+                  int32_t* coef_out, cudaStream_t st);
+int launch_ag_message(const fz_ctx* ctx, const uint8_t* pieces, size_t piece_stride, const uint32_t* piece_len, const uint32_t* order,
+                      const unsigned long long* agg_off, size_t n_aggs, size_t n_total, unsigned long long* piece_pos, uint8_t* msgs, size_t msg_stride,
+                      uint32_t* msg_len, cudaStream_t st);
+int launch_shake_ag(const fz_ctx* ctx, const uint8_t* msgs, size_t msg_stride, const uint32_t* msg_len, const unsigned long long* agg_off, uint8_t* xof,
+                    size_t n_aggs, cudaStream_t st);
+
+// fz_sample.cu
+int launch_sample(const fz_ctx* ctx, int mode, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, uint32_t bound, int weight,
+                  int32_t* out, cudaStream_t st);
+int launch_seeds_to_keys(const fz_ctx* ctx, const unsigned long long* seeds, size_t n, uint32_t* keys, int32_t* klen, cudaStream_t st);
+int launch_replicate_rows(const fz_ctx* ctx, const int32_t* src, int32_t* dst, size_t batch, int rows, size_t src_batch_stride, cudaStream_t st);
+
+// fz_scheme.cu
+int launch_sort(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint32_t* sel, const unsigned long long* agg_off, size_t n_aggs,
+                size_t max_keys, uint32_t* perm, cudaStream_t st);
+int launch_gather_sorted(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, const uint32_t* sel, const uint32_t* perm,
+                         size_t n_total, int32_t* vk_l_s, int32_t* vk_r_s, uint8_t* dg_s, cudaStream_t st);
+int aggregate_split(const fz_ctx* ctx, size_t n_aggs, size_t max_keys);
+int launch_aggregate(const fz_ctx* ctx, const int32_t* sigs, const uint32_t* perm, const int32_t* alpha, const unsigned long long* agg_off, size_t n_aggs,
+                     int split, int32_t* part, int32_t* out, cudaStream_t st);
+int launch_fold_partials(const fz_ctx* ctx, const int32_t* part, int32_t* out, size_t n_aggs, int n_parts, cudaStream_t st);
+int launch_verify_target(const fz_ctx* ctx, const int32_t* vk_l_s, const int32_t* vk_r_s, const int32_t* c_hat, const int32_t* alpha,
+                         const unsigned long long* agg_off, size_t n_aggs, int32_t* target, cudaStream_t st);
+int launch_verify_finalize(const fz_ctx* ctx, const int32_t* target, const int32_t* observed, const int32_t* coef, size_t n_aggs, uint8_t* codes,
+                           cudaStream_t st);
 
 }  // namespace fz

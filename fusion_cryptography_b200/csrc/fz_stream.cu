@@ -33,26 +33,27 @@ __device__ __forceinline__ int4 cent4(const long long (&acc)[4]) {
 
 // out[b][k] = cent( sum_r A[r][k] * s[b][r][k] ).  A: [ell][d] canonical, s: [batch][ell][d], out: [batch][d].
 // thread <-> (b, 4 consecutive k); the ell rows of s[b] are streamed with 4 loads in flight.
-__global__ void __launch_bounds__(256) matvec_kernel(const int4* __restrict__ A, const int4* __restrict__ s, int4* __restrict__ out,
-                                                       size_t batch, int ell, int d4) {
+// s is addressed as s[b * batch_stride4 + r * row_stride4 + c] (row_stride4 = 0 broadcasts one polynomial to every row).
+__global__ void __launch_bounds__(256) matvec_kernel(const int4* __restrict__ A, const int4* __restrict__ s, size_t row_stride4, size_t batch_stride4,
+                                                       int4* __restrict__ out, size_t batch, int ell, int d4) {
     const size_t total = batch * (size_t)d4;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const size_t b = idx / d4;
         const int c = (int)(idx % d4);
-        const int4* sp = s + b * (size_t)ell * d4 + c;
+        const int4* sp = s + b * batch_stride4 + c;
         const int4* ap = A + c;
         long long acc[4] = {0, 0, 0, 0};
         int r = 0;
         for (; r + 4 <= ell; r += 4) {
-            int4 s0 = ld_stream(sp + (size_t)(r + 0) * d4), s1 = ld_stream(sp + (size_t)(r + 1) * d4);
-            int4 s2 = ld_stream(sp + (size_t)(r + 2) * d4), s3 = ld_stream(sp + (size_t)(r + 3) * d4);
+            int4 s0 = ld_stream(sp + (size_t)(r + 0) * row_stride4), s1 = ld_stream(sp + (size_t)(r + 1) * row_stride4);
+            int4 s2 = ld_stream(sp + (size_t)(r + 2) * row_stride4), s3 = ld_stream(sp + (size_t)(r + 3) * row_stride4);
             int4 a0 = __ldg(ap + (size_t)(r + 0) * d4), a1 = __ldg(ap + (size_t)(r + 1) * d4);
             int4 a2 = __ldg(ap + (size_t)(r + 2) * d4), a3 = __ldg(ap + (size_t)(r + 3) * d4);
             mac4(acc, a0, s0); mac4(acc, a1, s1); fold4(acc);
             mac4(acc, a2, s2); mac4(acc, a3, s3); fold4(acc);
         }
         for (; r < ell; ++r) {
-            mac4(acc, __ldg(ap + (size_t)r * d4), ld_stream(sp + (size_t)r * d4));
+            mac4(acc, __ldg(ap + (size_t)r * d4), ld_stream(sp + (size_t)r * row_stride4));
             fold4(acc);
         }
         out[idx] = cent4(acc);
@@ -60,13 +61,16 @@ __global__ void __launch_bounds__(256) matvec_kernel(const int4* __restrict__ A,
 }
 
 // sig[b][r][k] = cent( sk_l[b][r][k] * c_hat[b][k] + sk_r[b][r][k] )   (fusion.py:557)
-__global__ void __launch_bounds__(256) sign_mac_kernel(const int4* __restrict__ sk_l, const int4* __restrict__ sk_r, const int4* __restrict__ c_hat,
-                                                         int4* __restrict__ sig, size_t batch, int ell, int d4) {
+__global__ void __launch_bounds__(256) sign_mac_kernel(const int4* __restrict__ sk_l, const int4* __restrict__ sk_r, size_t row_stride4,
+                                                         size_t batch_stride4, const int4* __restrict__ c_hat, int4* __restrict__ sig, size_t batch, int ell,
+                                                         int d4) {
     const size_t per_key = (size_t)ell * d4, total = batch * per_key;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const size_t b = idx / per_key;
         const int c = (int)(idx % d4);
-        int4 l = ld_stream(sk_l + idx), r = ld_stream(sk_r + idx), ch = __ldg(c_hat + b * d4 + c), o;
+        const size_t row = (idx % per_key) / d4;
+        const size_t si = b * batch_stride4 + row * row_stride4 + c;
+        int4 l = ld_stream(sk_l + si), r = ld_stream(sk_r + si), ch = __ldg(c_hat + b * d4 + c), o;
         o.x = cent_i64((long long)l.x * ch.x + r.x);
         o.y = cent_i64((long long)l.y * ch.y + r.y);
         o.z = cent_i64((long long)l.z * ch.z + r.z);
@@ -82,18 +86,21 @@ static int stream_grid(const fz_ctx* ctx, size_t items, int threads) {
     return blocks < 1 ? 1 : (int)blocks;
 }
 
-int launch_matvec(const fz_ctx* ctx, const int32_t* A, const int32_t* s, int32_t* out, size_t batch, cudaStream_t st) {
+int launch_matvec(const fz_ctx* ctx, const int32_t* A, const int32_t* s, size_t s_row_stride, size_t s_batch_stride, int32_t* out, size_t batch,
+                  cudaStream_t st) {
     if (batch == 0) return 0;
     const int d4 = ctx->d / 4;
-    matvec_kernel<<<stream_grid(ctx, batch * d4, 256), 256, 0, st>>>((const int4*)A, (const int4*)s, (int4*)out, batch, ctx->ell, d4);
+    matvec_kernel<<<stream_grid(ctx, batch * d4, 256), 256, 0, st>>>((const int4*)A, (const int4*)s, s_row_stride / 4, s_batch_stride / 4, (int4*)out, batch,
+                                                                     ctx->ell, d4);
     return check(cudaGetLastError(), "matvec launch");
 }
 
-int launch_sign_mac(const fz_ctx* ctx, const int32_t* sk_l, const int32_t* sk_r, const int32_t* c_hat, int32_t* sig, size_t batch, cudaStream_t st) {
+int launch_sign_mac(const fz_ctx* ctx, const int32_t* sk_l, const int32_t* sk_r, size_t sk_row_stride, size_t sk_batch_stride, const int32_t* c_hat,
+                    int32_t* sig, size_t batch, cudaStream_t st) {
     if (batch == 0) return 0;
     const int d4 = ctx->d / 4;
-    sign_mac_kernel<<<stream_grid(ctx, batch * ctx->ell * d4, 256), 256, 0, st>>>((const int4*)sk_l, (const int4*)sk_r, (const int4*)c_hat, (int4*)sig,
-                                                                                  batch, ctx->ell, d4);
+    sign_mac_kernel<<<stream_grid(ctx, batch * ctx->ell * d4, 256), 256, 0, st>>>((const int4*)sk_l, (const int4*)sk_r, sk_row_stride / 4, sk_batch_stride / 4,
+                                                                                  (const int4*)c_hat, (int4*)sig, batch, ctx->ell, d4);
     return check(cudaGetLastError(), "sign_mac launch");
 }
 

@@ -199,3 +199,231 @@ def get_context(secpar: int, device: Optional[int] = None) -> Context:
     if key not in _contexts:
         _contexts[key] = Context(secpar, device)
     return _contexts[key]
+
+
+# ---------------------------------------------------------------------------------------------
+# Hashing / samplers / scheme stages (K7-K11).  Methods are attached to Context below.
+def _u8(self, x, name="bytes") -> torch.Tensor:
+    if not isinstance(x, torch.Tensor):
+        x = torch.frombuffer(bytearray(x), dtype=torch.uint8) if len(x) else torch.empty(0, dtype=torch.uint8)
+    if x.dtype != torch.uint8:
+        raise TypeError(f"{name} must be uint8")
+    return x.to(self.device).contiguous()
+
+
+def _pack_messages(self, msgs):
+    """list of bytes -> (device uint8 buffer, device int64 offsets[n+1])"""
+    offs = [0]
+    for m in msgs:
+        offs.append(offs[-1] + len(m))
+    data = b"".join(msgs) + b"\0"
+    buf = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(self.device)
+    return buf, torch.tensor(offs, dtype=torch.int64, device=self.device)
+
+
+def _ws(self, nbytes: int) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+
+
+def sha3_256(self, msgs):
+    buf, offs = self._pack_messages(msgs)
+    out = torch.empty((len(msgs), 32), dtype=torch.uint8, device=self.device)
+    self._chk(self.lib.fz_sha3_256(self._h, _ptr(buf), _ptr(offs), C.c_size_t(len(msgs)), _ptr(out), self._stream()))
+    return out
+
+
+def shake256(self, msgs, out_len: int):
+    buf, offs = self._pack_messages(msgs)
+    out = torch.empty((len(msgs), max(out_len, 1)), dtype=torch.uint8, device=self.device)
+    self._chk(self.lib.fz_shake256(self._h, _ptr(buf), _ptr(offs), C.c_size_t(len(msgs)), _ptr(out), C.c_size_t(out_len), self._stream()))
+    return out[:, :out_len]
+
+
+def hash_msg(self, msgs) -> torch.Tensor:
+    """fusion.py:405-409 on a list of message byte strings -> [n, 32] digests (int = little endian)."""
+    buf, offs = self._pack_messages(msgs)
+    out = torch.empty((len(msgs), 32), dtype=torch.uint8, device=self.device)
+    self._chk(self.lib.fz_hash_msg(self._h, _ptr(buf), _ptr(offs), C.c_size_t(len(msgs)), _ptr(out), self._stream()))
+    return out
+
+
+def format_text(self, mode: int, vk_l, vk_r, digests, c_hat=None):
+    vk_l, vk_r = self._dev(vk_l), self._dev(vk_r)
+    n = vk_l.numel() // self.d
+    digests = self._u8(digests)
+    c_hat = None if c_hat is None else self._dev(c_hat)
+    self.lib.fz_text_stride.restype = C.c_size_t
+    stride = int(self.lib.fz_text_stride(self._h, C.c_int(mode)))
+    out = torch.zeros((n, stride), dtype=torch.uint8, device=self.device)
+    lens = torch.empty(n, dtype=torch.int32, device=self.device)
+    self._chk(self.lib.fz_format_text(self._h, C.c_int(mode), _ptr(vk_l), _ptr(vk_r), _ptr(digests), _ptr(c_hat), C.c_size_t(n), _ptr(out), _ptr(lens),
+                                      self._stream()))
+    return out, lens
+
+
+def decode_poly(self, data: torch.Tensor, blen: int, log2_bias: int, norm_bound: int, weight_bound: int) -> torch.Tensor:
+    """data: [n, stride] uint8 device tensor; decodes the first blen bytes of each row (fusion.py:422-481)."""
+    data = self._u8(data)
+    n, stride = data.shape
+    out = torch.empty((n, self.d), dtype=torch.int32, device=self.device)
+    rc = self.lib.fz_decode_poly(self._h, _ptr(data), C.c_size_t(stride), C.c_size_t(blen), C.c_size_t(n), C.c_int(log2_bias), C.c_int(norm_bound),
+                                 C.c_int(weight_bound), _ptr(out), self._stream())
+    if rc == -3:
+        raise ValueError(self.lib.fz_last_error().decode())
+    self._chk(rc)
+    return out
+
+
+def hash_ch(self, vk_l, vk_r, digests) -> torch.Tensor:
+    vk_l, vk_r, digests = self._dev(vk_l), self._dev(vk_r), self._u8(digests)
+    n = vk_l.numel() // self.d
+    self.lib.fz_hash_ch_workspace.restype = C.c_size_t
+    ws = self._ws(self.lib.fz_hash_ch_workspace(self._h, C.c_size_t(n)))
+    out = torch.empty((n, self.d), dtype=torch.int32, device=self.device)
+    self._chk(self.lib.fz_hash_ch(self._h, _ptr(vk_l), _ptr(vk_r), _ptr(digests), C.c_size_t(n), _ptr(out), _ptr(ws), C.c_size_t(ws.numel()), self._stream()))
+    return out
+
+
+def _agg_off(self, counts):
+    off = [0]
+    for c in counts:
+        off.append(off[-1] + int(c))
+    return torch.tensor(off, dtype=torch.int64, device=self.device), off[-1], (max(counts) if len(counts) else 0)
+
+
+def hash_ag(self, vk_l_s, vk_r_s, dg_s, c_hat_s, counts) -> torch.Tensor:
+    """counts[j] = number of (already sorted) signers of aggregate j."""
+    vk_l_s, vk_r_s, dg_s, c_hat_s = self._dev(vk_l_s), self._dev(vk_r_s), self._u8(dg_s), self._dev(c_hat_s)
+    agg_off, n_total, max_keys = self._agg_off(counts)
+    self.lib.fz_hash_ag_workspace.restype = C.c_size_t
+    ws = self._ws(self.lib.fz_hash_ag_workspace(self._h, C.c_size_t(n_total), C.c_size_t(len(counts)), C.c_size_t(max_keys)))
+    out = torch.empty((n_total, self.d), dtype=torch.int32, device=self.device)
+    self._chk(self.lib.fz_hash_ag(self._h, _ptr(vk_l_s), _ptr(vk_r_s), _ptr(dg_s), _ptr(c_hat_s), _ptr(agg_off), C.c_size_t(len(counts)), C.c_size_t(n_total),
+                                  C.c_size_t(max_keys), _ptr(out), _ptr(ws), C.c_size_t(ws.numel()), self._stream()))
+    return out
+
+
+def sort_keys(self, vk_l, vk_r, counts, sel=None) -> torch.Tensor:
+    vk_l, vk_r = self._dev(vk_l), self._dev(vk_r)
+    agg_off, n_total, max_keys = self._agg_off(counts)
+    if sel is not None:
+        sel = sel.to(self.device, dtype=torch.int32).contiguous()
+    perm = torch.empty(n_total, dtype=torch.int32, device=self.device)
+    self._chk(self.lib.fz_sort_keys(self._h, _ptr(vk_l), _ptr(vk_r), _ptr(sel), _ptr(agg_off), C.c_size_t(len(counts)), C.c_size_t(max_keys), _ptr(perm),
+                                    self._stream()))
+    return perm
+
+
+def gather_sorted(self, vk_l, vk_r, digests, perm, sel=None):
+    vk_l, vk_r, digests = self._dev(vk_l), self._dev(vk_r), self._u8(digests)
+    n_total = perm.numel()
+    if sel is not None:
+        sel = sel.to(self.device, dtype=torch.int32).contiguous()
+    vl = torch.empty((n_total, self.d), dtype=torch.int32, device=self.device)
+    vr = torch.empty((n_total, self.d), dtype=torch.int32, device=self.device)
+    dg = torch.empty((n_total, 32), dtype=torch.uint8, device=self.device)
+    self._chk(self.lib.fz_gather_sorted(self._h, _ptr(vk_l), _ptr(vk_r), _ptr(digests), _ptr(sel), _ptr(perm), C.c_size_t(n_total), _ptr(vl), _ptr(vr), _ptr(dg),
+                                        self._stream()))
+    return vl, vr, dg
+
+
+def aggregate_sum(self, sigs, perm, alpha, counts) -> torch.Tensor:
+    sigs, alpha = self._dev(sigs), self._dev(alpha)
+    agg_off, n_total, max_keys = self._agg_off(counts)
+    self.lib.fz_aggregate_sum_workspace.restype = C.c_size_t
+    ws = self._ws(self.lib.fz_aggregate_sum_workspace(self._h, C.c_size_t(len(counts)), C.c_size_t(max_keys)))
+    out = torch.empty((len(counts), self.ell, self.d), dtype=torch.int32, device=self.device)
+    self._chk(self.lib.fz_aggregate_sum(self._h, _ptr(sigs), _ptr(perm), _ptr(alpha), _ptr(agg_off), C.c_size_t(len(counts)), C.c_size_t(max_keys), _ptr(out),
+                                        _ptr(ws), C.c_size_t(ws.numel()), self._stream()))
+    return out
+
+
+def fold_partials(self, parts: torch.Tensor, n_parts: int, n_aggs: int) -> torch.Tensor:
+    parts = self._dev(parts)
+    out = torch.empty((n_aggs, self.ell, self.d), dtype=torch.int32, device=self.device)
+    self._chk(self.lib.fz_fold_partials(self._h, _ptr(parts), C.c_int(n_parts), C.c_size_t(n_aggs), _ptr(out), self._stream()))
+    return out
+
+
+def verify_check(self, A, vk_l_s, vk_r_s, c_hat_s, alpha_s, agg, counts) -> torch.Tensor:
+    A, vk_l_s, vk_r_s, c_hat_s, alpha_s, agg = (self._dev(t) for t in (A, vk_l_s, vk_r_s, c_hat_s, alpha_s, agg))
+    agg_off, n_total, max_keys = self._agg_off(counts)
+    self.lib.fz_verify_check_workspace.restype = C.c_size_t
+    ws = self._ws(self.lib.fz_verify_check_workspace(self._h, C.c_size_t(len(counts))))
+    codes = torch.empty(len(counts), dtype=torch.uint8, device=self.device)
+    self._chk(self.lib.fz_verify_check(self._h, _ptr(A), _ptr(vk_l_s), _ptr(vk_r_s), _ptr(c_hat_s), _ptr(alpha_s), _ptr(agg), _ptr(agg_off),
+                                       C.c_size_t(len(counts)), _ptr(codes), _ptr(ws), C.c_size_t(ws.numel()), self._stream()))
+    return codes
+
+
+def _seed_keys(self, seeds):
+    """Python ints (any sign, up to 256 bits) -> ([n, 8] uint32 limbs, [n] int32 limb counts) on the device."""
+    import numpy as np
+
+    n = len(seeds)
+    keys = np.zeros((n, 8), dtype=np.uint32)
+    klen = np.zeros(n, dtype=np.int32)
+    for i, s in enumerate(seeds):
+        v = abs(int(s))
+        if v >> 256:
+            raise ValueError("seeds above 256 bits are not supported by the device sampler")
+        k = 0
+        while True:
+            keys[i, k] = v & 0xFFFFFFFF
+            v >>= 32
+            k += 1
+            if not v:
+                break
+        klen[i] = k
+    return torch.from_numpy(keys.view(np.int32)).to(self.device), torch.from_numpy(klen).to(self.device)
+
+
+def sample_coef(self, seeds, norm_bound: int = 52, weight_bound=None) -> torch.Tensor:
+    """algebra/polynomials.py:436-467 for a list of integer seeds -> [n, d]."""
+    keys, klen = self._seed_keys(seeds)
+    out = torch.empty((len(seeds), self.d), dtype=torch.int32, device=self.device)
+    wb = self.d if weight_bound is None else weight_bound
+    self._chk(self.lib.fz_sample_coef(self._h, _ptr(keys), C.c_int(8), _ptr(klen), C.c_size_t(len(seeds)), C.c_int(norm_bound), C.c_int(wb), _ptr(out),
+                                      self._stream()))
+    return out
+
+
+def sample_ntt(self, seeds) -> torch.Tensor:
+    """algebra/polynomials.py:470-488 for a list of integer seeds -> [n, d]."""
+    keys, klen = self._seed_keys(seeds)
+    out = torch.empty((len(seeds), self.d), dtype=torch.int32, device=self.device)
+    self._chk(self.lib.fz_sample_ntt(self._h, _ptr(keys), C.c_int(8), _ptr(klen), C.c_size_t(len(seeds)), _ptr(out), self._stream()))
+    return out
+
+
+def keygen(self, A, seeds, want_sk: bool = True):
+    """fusion.py:338-373 for u64 seeds.  Returns (sk_l, sk_r, sk_hat, vk_l, vk_r); sk_l / sk_r are None unless want_sk."""
+    A = self._dev(A)
+    if not isinstance(seeds, torch.Tensor):
+        import numpy as np
+        seeds = torch.from_numpy(np.asarray(seeds, dtype=np.uint64).view(np.int64))
+    seeds = seeds.to(self.device).contiguous()
+    n = seeds.numel()
+    self.lib.fz_keygen_workspace.restype = C.c_size_t
+    ws = self._ws(self.lib.fz_keygen_workspace(self._h, C.c_size_t(n)))
+    sk_l = torch.empty((n, self.ell, self.d), dtype=torch.int32, device=self.device) if want_sk else None
+    sk_r = torch.empty((n, self.ell, self.d), dtype=torch.int32, device=self.device) if want_sk else None
+    sk_hat = torch.empty((n, 2, self.d), dtype=torch.int32, device=self.device)
+    vk_l = torch.empty((n, self.d), dtype=torch.int32, device=self.device)
+    vk_r = torch.empty((n, self.d), dtype=torch.int32, device=self.device)
+    self._chk(self.lib.fz_keygen(self._h, _ptr(A), _ptr(seeds), C.c_size_t(n), _ptr(sk_l), _ptr(sk_r), _ptr(sk_hat), _ptr(vk_l), _ptr(vk_r), _ptr(ws),
+                                 C.c_size_t(ws.numel()), self._stream()))
+    return sk_l, sk_r, sk_hat, vk_l, vk_r
+
+
+def sign_mac_rows(self, sk_hat, c_hat, out=None) -> torch.Tensor:
+    sk_hat, c_hat = self._dev(sk_hat), self._dev(c_hat)
+    n = c_hat.numel() // self.d
+    out = torch.empty((n, self.ell, self.d), dtype=torch.int32, device=self.device) if out is None else out
+    self._chk(self.lib.fz_sign_mac_rows(self._h, _ptr(sk_hat), _ptr(c_hat), _ptr(out), C.c_size_t(n), self._stream()))
+    return out
+
+
+for _f in (_u8, _pack_messages, _ws, sha3_256, shake256, hash_msg, format_text, decode_poly, hash_ch, _agg_off, hash_ag, sort_keys, gather_sorted,
+           aggregate_sum, fold_partials, verify_check, _seed_keys, sample_coef, sample_ntt, keygen, sign_mac_rows):
+    setattr(Context, _f.__name__, _f)

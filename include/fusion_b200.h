@@ -60,6 +60,62 @@ int fz_matvec(fz_ctx* ctx, const int32_t* A, const int32_t* s, int32_t* out, siz
 /* fusion.py:557: sig[b] = sk_l[b] * c_hat[b] + sk_r[b]  (matrices.py:109-114 then :74-91) */
 int fz_sign_mac(fz_ctx* ctx, const int32_t* sk_l, const int32_t* sk_r, const int32_t* c_hat, int32_t* sig, size_t batch, void* stream);
 
+/* ---- hashing: SHA3-256 / SHAKE256 (hashlib call sites fusion/fusion.py:408, 419, 591) ------------------- */
+/* generic batched hashes over device byte strings data[offs[i]..offs[i+1]); out32: [n][32]; out: [n][out_len] */
+int fz_sha3_256(fz_ctx* ctx, const uint8_t* data, const uint64_t* offs, size_t n, uint8_t* out32, void* stream);
+int fz_shake256(fz_ctx* ctx, const uint8_t* data, const uint64_t* offs, size_t n, uint8_t* out, size_t out_len, void* stream);
+/* fusion.py:405-409 hash_message_to_int: digests[i] = SHA3-256(dst "," msg_i); the int is the little-endian value of the 32 bytes */
+int fz_hash_msg(fz_ctx* ctx, const uint8_t* msgs, const uint64_t* offs, size_t n, uint8_t* digests, void* stream);
+/* str(OneTimeVerificationKey) / str(SignatureChallenge) as hashed at fusion.py:416-418 (mode 0: dst "," VK "," INT) and
+ * fusion.py:589 (mode 1: one "(VK, INT, CH)" list element).  out: [n][fz_text_stride(mode)] bytes, out_len[n]. */
+size_t fz_text_stride(const fz_ctx* ctx, int mode);
+int fz_format_text(fz_ctx* ctx, int mode, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, const int32_t* c_hat, size_t n,
+                   uint8_t* out, uint32_t* out_len, void* stream);
+/* fusion.py:422-481 decode_bytes_to_polynomial_coefficients on n byte strings bytes[i*stride .. +blen); returns -3
+ * ("Too few bytes ...", the reference's ValueError) when blen is too small.  coef_out: [n][d]. */
+int fz_decode_poly(fz_ctx* ctx, const uint8_t* bytes, size_t stride, size_t blen, size_t n, int log2_bias, int norm_bound, int weight_bound,
+                   int32_t* coef_out, void* stream);
+/* fusion.py:511-531 hash_ch (prehash digests from fz_hash_msg): c_hat_out: [n][d] */
+size_t fz_hash_ch_workspace(const fz_ctx* ctx, size_t n);
+int fz_hash_ch(fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, size_t n, int32_t* c_hat_out, void* ws, size_t ws_bytes,
+               void* stream);
+/* fusion.py:632-652 hash_ag for n_aggs aggregates; inputs already sorted (fz_sort_keys + fz_gather_sorted); aggregate j
+ * owns positions [agg_off[j], agg_off[j+1]) (device array of n_aggs + 1 offsets).  alpha_hat_out: [n_total][d]. */
+size_t fz_hash_ag_workspace(const fz_ctx* ctx, size_t n_total, size_t n_aggs, size_t max_keys);
+int fz_hash_ag(fz_ctx* ctx, const int32_t* vk_l_s, const int32_t* vk_r_s, const uint8_t* dg_s, const int32_t* c_hat_s, const uint64_t* agg_off,
+               size_t n_aggs, size_t n_total, size_t max_keys, int32_t* alpha_hat_out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- aggregate / verify ------------------------------------------------------------------------------- */
+/* sorted(zip(...), key=lambda x: str(x[0])) at fusion.py:661-663 and :693.  sel (optional) maps a position to a row of
+ * vk_l / vk_r; perm[agg_off[j] + rank] = position.  Stable. */
+int fz_sort_keys(fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint32_t* sel, const uint64_t* agg_off, size_t n_aggs, size_t max_keys,
+                 uint32_t* perm, void* stream);
+int fz_gather_sorted(fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, const uint32_t* sel, const uint32_t* perm,
+                     size_t n_total, int32_t* vk_l_s, int32_t* vk_r_s, uint8_t* dg_s, void* stream);
+/* fusion.py:670-677: out[j] = sum_p sigs[perm[p]] * alpha[p]; sigs: [n_sigs][ell][d], out: [n_aggs][ell][d] */
+size_t fz_aggregate_sum_workspace(const fz_ctx* ctx, size_t n_aggs, size_t max_keys);
+int fz_aggregate_sum(fz_ctx* ctx, const int32_t* sigs, const uint32_t* perm, const int32_t* alpha, const uint64_t* agg_off, size_t n_aggs, size_t max_keys,
+                     int32_t* out, void* ws, size_t ws_bytes, void* stream);
+/* modular sum of partial aggregates [n_aggs][n_parts][ell][d] (the multi-GPU reduce of partial sums) */
+int fz_fold_partials(fz_ctx* ctx, const int32_t* parts, int n_parts, size_t n_aggs, int32_t* out, void* stream);
+/* fusion.py:690-692, 706-728 on sorted inputs: codes[j] = 0 (True, "") | 3 "Target doesn't match image of aggregate
+ * signature." | 4 "Norm of aggregate signature too large."  (reasons 1, 2 are argument checks done by the caller) */
+size_t fz_verify_check_workspace(const fz_ctx* ctx, size_t n_aggs);
+int fz_verify_check(fz_ctx* ctx, const int32_t* A, const int32_t* vk_l_s, const int32_t* vk_r_s, const int32_t* c_hat_s, const int32_t* alpha_s,
+                    const int32_t* agg, const uint64_t* agg_off, size_t n_aggs, uint8_t* codes, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- seeded samplers and keygen (CPython random: MT19937 + randrange; algebra/polynomials.py:436-488) ----- */
+/* keys: [n][key_stride] little-endian 32-bit limbs of abs(seed), klen[n] in 1..8 */
+int fz_sample_coef(fz_ctx* ctx, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, int norm_bound, int weight_bound, int32_t* out,
+                   void* stream);
+int fz_sample_ntt(fz_ctx* ctx, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, int32_t* out, void* stream);
+/* fusion.py:338-373 keygen for n u64 seeds; sk_l / sk_r ([n][ell][d]) and sk_hat ([n][2][d]) are optional outputs */
+size_t fz_keygen_workspace(const fz_ctx* ctx, size_t n);
+int fz_keygen(fz_ctx* ctx, const int32_t* A, const uint64_t* seeds, size_t n, int32_t* sk_l, int32_t* sk_r, int32_t* sk_hat, int32_t* vk_l, int32_t* vk_r,
+              void* ws, size_t ws_bytes, void* stream);
+/* fusion.py:557 for keys kept as their one distinct row (sk_hat from fz_keygen): sig: [batch][ell][d] */
+int fz_sign_mac_rows(fz_ctx* ctx, const int32_t* sk_hat, const int32_t* c_hat, int32_t* sig, size_t batch, void* stream);
+
 /* Host-buffer convenience used by the end-to-end measurement: copies n_polys polynomials from
  * pinned or pageable host memory, transforms them (inverse = 0/1) and copies the result back,
  * chunked and double-buffered on internal streams.  Synchronous. */
