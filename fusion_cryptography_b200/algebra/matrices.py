@@ -1,0 +1,194 @@
+"""Host mirror of the reference's ``algebra.matrices.GeneralMatrix`` (algebra/matrices.py): same
+validation, ``str()`` format (which the scheme hashes), operators and error classes.  Products and sums
+of matrices of scheme polynomials run as single kernels (fz_matvec / fz_sign_mac / pointwise); other
+element classes fall back to the reference's element-wise semantics through the elements' own operators.
+"""
+from __future__ import annotations
+
+from typing import List, Union
+
+try:
+    from .polynomials import PolynomialCoefficientRepresentation, PolynomialNTTRepresentation, _eq_zero
+except ImportError:  # drop-in layout
+    from algebra.polynomials import PolynomialCoefficientRepresentation, PolynomialNTTRepresentation, _eq_zero
+
+
+def is_algebraic_class(cls):
+    return all(hasattr(cls, m) for m in ("__eq__", "__add__", "__neg__", "__sub__", "__mul__"))
+
+
+class GeneralMatrix:
+    elem_class: type
+    matrix: List[List[object]]
+
+    def __init__(self, matrix: List[list]):
+        if not isinstance(matrix, list):
+            raise ValueError("Matrix must be a list")
+        elif not matrix:
+            raise ValueError("Matrix must not be empty.")
+        elif any(not isinstance(x, list) for x in matrix):
+            raise ValueError("Matrix must be a list of lists")
+        elif any(not x for x in matrix):
+            raise ValueError("Matrix must not contain empty lists")
+        elif not all(len(row) == len(matrix[0]) for row in matrix):
+            raise ValueError("All rows must have the same length")
+        elif not is_algebraic_class(cls=matrix[0][0].__class__):
+            raise ValueError("Matrix must contain only instances of the same algebraic class")
+        elif not all(all(isinstance(item, matrix[0][0].__class__) for item in row) for row in matrix):
+            raise ValueError("Matrix must contain only instances of the same algebraic class")
+        self.elem_class = matrix[0][0].__class__
+        self.matrix = matrix
+        self._base = None  # device tensor [rows, cols, d] the elements are views of (set by the kernels' wrappers)
+
+    # ------------------------------------------------------------------ device plumbing
+    @classmethod
+    def _from_tensor(cls, ring, elem_class, t):
+        """t: int32 device tensor [rows, cols, d]; elements become views of it."""
+        rows, cols = t.shape[0], t.shape[1]
+        m = cls.__new__(cls)
+        m.elem_class = elem_class
+        m.matrix = [[elem_class._from_tensor(ring, t[i, j]) for j in range(cols)] for i in range(rows)]
+        m._base = t
+        return m
+
+    def _is_scheme_ntt(self) -> bool:
+        return self.elem_class is PolynomialNTTRepresentation
+
+    def _tensor(self):
+        """int32 device tensor [rows, cols, d]; reuses the kernel output the elements still point into."""
+        import torch
+
+        base = getattr(self, "_base", None)
+        if base is not None and len(self.matrix) == base.shape[0] and all(
+                len(row) == base.shape[1] and all(getattr(e, "_vals", 0) is None and e._t is not None for e in row) for row in self.matrix):
+            ok = True
+            for i, row in enumerate(self.matrix):
+                for j, e in enumerate(row):
+                    if e._t.data_ptr() != base[i, j].data_ptr():
+                        ok = False
+                        break
+                if not ok:
+                    break
+            if ok:
+                return base
+        return torch.stack([torch.stack([e._tensor() for e in row]) for row in self.matrix])
+
+    def _all_zero(self) -> bool:
+        return all(all(_eq_zero(item) for item in row) for row in self.matrix)
+
+    def _ring(self):
+        return self.matrix[0][0]._ring()
+
+    def _same_ring(self) -> bool:
+        r = self._ring()
+        return all(e._ring() == r for row in self.matrix for e in row)
+
+    # ------------------------------------------------------------------ reference API
+    def __str__(self):
+        return f"GeneralMatrix(elem_class={self.elem_class}, matrix={self.matrix})"
+
+    def __repr__(self):
+        return self.__str__()
+
+    def __len__(self):
+        return len(self.matrix)
+
+    def __iter__(self):
+        return iter(self.matrix)
+
+    def __getitem__(self, item):
+        return self.matrix[item]
+
+    def __setitem__(self, key, value):
+        self.matrix[key] = value
+
+    def __delitem__(self, key):
+        self.matrix[key] = 0
+
+    def __eq__(self, other):
+        if (isinstance(other, GeneralMatrix) and other._all_zero()) or (not isinstance(other, GeneralMatrix) and _eq_zero(other)):
+            return self._all_zero()
+        elif not isinstance(other, GeneralMatrix) or self.elem_class != other.elem_class:
+            return False
+        elif len(self.matrix) != len(other.matrix) or len(self.matrix[0]) != len(other.matrix[0]):
+            return False
+        return self.matrix == other.matrix
+
+    __hash__ = None
+
+    def __add__(self, other):
+        if (isinstance(other, GeneralMatrix) and other._all_zero()) or (not isinstance(other, GeneralMatrix) and _eq_zero(other)):
+            return self
+        elif not isinstance(other, GeneralMatrix) or self.elem_class != other.elem_class:
+            raise NotImplementedError("Can only add GeneralMatrix objects of the same algebraic class")
+        elif len(self.matrix) != len(other.matrix) or len(self.matrix[0]) != len(other.matrix[0]):
+            raise ValueError("Matrix dimensions must match")
+        if self.elem_class in (PolynomialNTTRepresentation, PolynomialCoefficientRepresentation) and self._same_ring() and other._same_ring() \
+                and self._ring() == other._ring():
+            ctx = self.matrix[0][0]._ctx()
+            return GeneralMatrix._from_tensor(self._ring(), self.elem_class, ctx.pointwise_add(self._tensor(), other._tensor()))
+        return GeneralMatrix(matrix=[[self.matrix[i][j] + other.matrix[i][j] for j in range(len(self.matrix[0]))] for i in range(len(self.matrix))])
+
+    def __radd__(self, other):
+        if other == 0:
+            return self
+        return self + other
+
+    def __neg__(self):
+        return GeneralMatrix(matrix=[[-self.matrix[i][j] for j in range(len(self.matrix[0]))] for i in range(len(self.matrix))])
+
+    def __sub__(self, other):
+        return self + (-other)
+
+    def __mul__(self, other):
+        if isinstance(other, self.elem_class):
+            # matrix * element (reference :109-114): every entry times one polynomial
+            if self._is_scheme_ntt() and self._same_ring() and other._ring() == self._ring() and not _eq_zero(other):
+                ctx = other._ctx()
+                t = self._tensor()
+                out = ctx.pointwise_mul(t, other._tensor().expand_as(t).contiguous())
+                return GeneralMatrix._from_tensor(self._ring(), self.elem_class, out)
+            return GeneralMatrix(matrix=[[self.matrix[i][j] * other for j in range(len(self.matrix[0]))] for i in range(len(self.matrix))])
+        elif not isinstance(other, GeneralMatrix) or self.elem_class != other.elem_class:
+            raise TypeError("Can only multiply matrices of the same algebraic class")
+        elif len(self.matrix[0]) != len(other.matrix):
+            raise ValueError("Matrix dimension mismatch")
+        rows, inner, cols = len(self.matrix), len(self.matrix[0]), len(other.matrix[0])
+        if self._is_scheme_ntt() and self._same_ring() and other._same_ring() and self._ring() == other._ring():
+            ctx = self.matrix[0][0]._ctx()
+            if rows == 1 and cols == 1 and inner == ctx.ell:
+                # (1 x ell) . (ell x 1): the scheme's A.s / A.z (reference :121-131) as one fused MAC kernel
+                out = ctx.matvec(self._tensor().reshape(inner, ctx.d), other._tensor().reshape(1, inner, ctx.d))
+                return GeneralMatrix._from_tensor(self._ring(), self.elem_class, out.reshape(1, 1, ctx.d))
+        result = GeneralMatrix.__new__(GeneralMatrix)
+        result.elem_class = self.elem_class
+        result._base = None
+        result.matrix = [[0 for _ in range(cols)] for _ in range(rows)]
+        for i in range(rows):
+            for j in range(cols):
+                acc = self.matrix[i][0] * other.matrix[0][j]
+                for k in range(1, inner):
+                    acc += self.matrix[i][k] * other.matrix[k][j]
+                result.matrix[i][j] = acc
+        return result
+
+    def __mod__(self, other):
+        if not isinstance(other, int):
+            raise TypeError("Can only take the remainder of a matrix with an integer")
+        elif other <= 1:
+            raise ValueError("Modulus must be greater than 1")
+        return GeneralMatrix(matrix=[[self.matrix[i][j] % other for j in range(len(self.matrix[0]))] for i in range(len(self.matrix))])
+
+    def norm(self, p: Union[int, str]):
+        if not all(hasattr(z, "norm") for y in self.matrix for z in y):
+            raise NotImplementedError("Matrix elements must have a norm method")
+        elif p == "infty":
+            return max(max(z.norm(p=p) for z in y) for y in self.matrix)
+
+    def weight(self):
+        if not all(hasattr(z, "weight") for y in self.matrix for z in y):
+            raise NotImplementedError("Matrix elements must have a weight method")
+        return max(max(z.weight() for z in y) for y in self.matrix)
+
+
+GeneralMatrix.__module__ = "algebra.matrices"

@@ -1,0 +1,215 @@
+"""Host mirror of the reference's ``algebra.ntt`` module (same names, argument meaning and error
+behaviour), with the transforms executed by the sm_100a kernels of libfusion_b200.
+
+Reference: algebra/ntt.py.  The number-theory helpers (:17-213) are once-per-parameter-set host
+utilities (out of the hot path) and stay on the host; ``cooley_tukey_ntt`` (:216-291),
+``gentleman_sande_intt`` (:294-377) and ``ntt_poly_mult`` (:380-484) run on the GPU for the scheme's
+parameter sets (q = 2147465729 with d = 64 or 256 and the twiddle tables of psi = 23584283 / 3337519).
+Other (modulus, degree, table) combinations raise NotImplementedError: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from math import ceil, log2
+from typing import Dict, List, Optional, Tuple
+
+try:
+    from .. import native as _native
+except ImportError:  # imported as top-level `algebra.ntt` (drop-in layout)
+    import native as _native
+
+_PRIME_CACHE: Dict[int, bool] = {}
+_ROOT_CACHE: Dict[Tuple[int, int], Optional[int]] = {}
+_TABLES: Dict[int, Tuple[List[int], List[int]]] = {}
+
+SCHEME_Q = 2147465729
+_SCHEME = {64: (128, 23584283, 540632852), 256: (256, 3337519, 1978410468)}  # degree -> (secpar, root, inv_root)
+
+
+def is_odd_prime(val: int) -> bool:
+    if val not in _PRIME_CACHE:
+        ok = isinstance(val, int) and val >= 3 and val % 2 == 1
+        if ok:
+            f = 3
+            while f * f <= val:
+                if val % f == 0:
+                    ok = False
+                    break
+                f += 2
+        _PRIME_CACHE[val] = bool(ok)
+    return _PRIME_CACHE[val]
+
+
+def has_primitive_root_of_unity(modulus: int, root_order: int) -> bool:
+    if not (isinstance(modulus, int) and isinstance(root_order, int) and modulus >= 3 and root_order >= 2):
+        return False
+    return (modulus - 1) % root_order == 0
+
+
+def is_pow_two_geq_two(val: int) -> bool:
+    return isinstance(val, int) and val >= 2 and (val & (val - 1)) == 0
+
+
+def bit_reverse_copy(val: list):
+    if not isinstance(val, list):
+        raise ValueError("Input must be a list")
+    n = len(val)
+    bits = n.bit_length() - 1
+    out = []
+    for i in range(n):
+        r = 0
+        for b in range(bits):
+            if i >> b & 1:
+                r |= 1 << (bits - 1 - b)
+        out.append(val[r])
+    return out
+
+
+def cent(val: int, modulus: int, halfmod: int, logmod: int) -> int:
+    """Canonical centred residue (reference algebra/ntt.py:93-123); scalar host helper."""
+    if not (isinstance(val, int) and isinstance(modulus, int) and isinstance(halfmod, int) and isinstance(logmod, int)):
+        raise TypeError("Input must be integers")
+    if modulus < 2:
+        raise ValueError("Modulus must be at least 2")
+    if halfmod < 1:
+        raise ValueError("Halfmod must be at least 1")
+    if logmod < 1:
+        raise ValueError("Logmod must be at least 1")
+    y = val % modulus
+    return y - (1 + ((y - halfmod - 1) >> logmod)) * modulus
+
+
+def is_root_of_unity(val: int, modulus: int, root_order: int) -> bool:
+    if not (isinstance(val, int) and isinstance(modulus, int) and isinstance(root_order, int) and modulus >= 2 and root_order >= 1):
+        return False
+    return pow(val, root_order, modulus) == 1
+
+
+def is_primitive_root(val: int, modulus: int, root_order: int) -> bool:
+    if not is_root_of_unity(val, modulus, root_order):
+        return False
+    # for a power-of-two order it is enough to look at order/2; the general case walks the proper divisors
+    k = 1
+    acc = val % modulus
+    while k < root_order:
+        if acc == 1:
+            return False
+        acc = acc * val % modulus
+        k += 1
+    return True
+
+
+def find_primitive_root(modulus: int, root_order: int) -> Optional[int]:
+    key = (modulus, root_order)
+    if key not in _ROOT_CACHE:
+        _ROOT_CACHE[key] = None
+        if isinstance(modulus, int) and isinstance(root_order, int) and modulus >= 2 and root_order >= 1 and has_primitive_root_of_unity(modulus, root_order):
+            r = 2
+            while r < modulus and not is_primitive_root(r, modulus, root_order):
+                r += 1
+            if not is_primitive_root(r, modulus, root_order):
+                raise RuntimeError(f"No primitive root found with modulus={modulus}, root_order={root_order}. This error should never occur.")
+            _ROOT_CACHE[key] = r
+    return _ROOT_CACHE[key]
+
+
+def scheme_tables(degree: int) -> Tuple[List[int], List[int]]:
+    """bit-reversed power tables of the scheme's psi and psi^-1 (algebra/polynomials.py:396-397, 414-417)."""
+    if degree not in _TABLES:
+        _, root, inv_root = _SCHEME[degree]
+        _TABLES[degree] = (bit_reverse_copy([pow(root, i, SCHEME_Q) for i in range(degree)]),
+                           bit_reverse_copy([pow(inv_root, i, SCHEME_Q) for i in range(degree)]))
+    return _TABLES[degree]
+
+
+def _validate(val, modulus, root_order, table, table_name):
+    if not isinstance(val, list):
+        raise TypeError(f"val must be a list, but got {type(val)}")
+    if not isinstance(modulus, int):
+        raise TypeError(f"modulus must be an int, but got {type(modulus)}")
+    if not isinstance(table, list):
+        raise TypeError(f"{table_name} must be a list, but got {type(table)}")
+    if not all(isinstance(v, int) for v in table):
+        raise TypeError(f"{table_name} must be a list of ints, but got {type(table)}")
+    if not isinstance(root_order, int):
+        raise TypeError(f"root_order must be an int, but got {type(root_order)}")
+    if not all(isinstance(v, int) for v in val):
+        raise TypeError(f"val must be a list of ints, but got {type(val)}")
+    if not is_odd_prime(modulus):
+        raise ValueError(f"modulus={modulus} must be an odd prime")
+    if not has_primitive_root_of_unity(modulus, root_order):
+        raise ValueError(f"modulus={modulus} does not have a primitive root of order root_order={root_order}")
+    if not is_pow_two_geq_two(len(val)):
+        raise ValueError(f"len(val)={len(val)} must be a power of 2 greater than 1")
+    if root_order != 2 * len(val) and root_order != len(val):
+        raise ValueError(f"root_order={root_order} must be degree or twice the degree, {len(val)}")
+    if root_order == len(val):
+        raise NotImplementedError(f"root_order={root_order}=degree={len(val)} is not implemented")
+
+
+def _require_scheme(modulus: int, degree: int, table: List[int], inverse: bool) -> int:
+    if modulus != SCHEME_Q or degree not in _SCHEME or [t % modulus for t in table] != scheme_tables(degree)[1 if inverse else 0]:
+        raise NotImplementedError(
+            "libfusion_b200 transforms only the scheme's parameter sets (q = 2147465729, degree 64 or 256, the reference's "
+            "root-power tables); there is no CPU fallback for other moduli, degrees or tables")
+    return _SCHEME[degree][0]
+
+
+def _centre_list(vals: List[int], modulus: int) -> List[int]:
+    h = modulus // 2
+    return [((v + h) % modulus) - h for v in vals]
+
+
+def _run(secpar: int, vals: List[int], op: str) -> List[int]:
+    import torch
+
+    ctx = _native.get_context(secpar)
+    t = torch.tensor(_centre_list(vals, SCHEME_Q), dtype=torch.int32)
+    out = getattr(ctx, op)(t)
+    return out.cpu().tolist()
+
+
+def cooley_tukey_ntt(val: List[int], modulus: int, root_order: int, bit_rev_root_powers: List[int]) -> List[int]:
+    """In place forward negacyclic NTT, natural order in, bit-reversed order out (reference :216-291)."""
+    _validate(val, modulus, root_order, bit_rev_root_powers, "root_powers")
+    secpar = _require_scheme(modulus, len(val), bit_rev_root_powers, inverse=False)
+    val[:] = _run(secpar, val, "ntt_fwd")
+    return val
+
+
+def gentleman_sande_intt(val: List[int], modulus: int, root_order: int, bit_rev_inv_root_powers: List[int]) -> List[int]:
+    """In place inverse transform incl. the n^-1 scaling (reference :294-377)."""
+    _validate(val, modulus, root_order, bit_rev_inv_root_powers, "inv_root_powers")
+    secpar = _require_scheme(modulus, len(val), bit_rev_inv_root_powers, inverse=True)
+    val[:] = _run(secpar, val, "ntt_inv")
+    return val
+
+
+def ntt_poly_mult(f: List[int], g: List[int], modulus: int, root: int, inv_root: int, root_order: int) -> List[int]:
+    """INTT(NTT(f) * NTT(g)) (reference :380-484).  Like the reference, f and g are left holding the
+    canonical centred form of their input (they go through a forward and an inverse transform)."""
+    if not (isinstance(f, list) and isinstance(g, list) and isinstance(modulus, int) and isinstance(root, int) and isinstance(inv_root, int)
+            and isinstance(root_order, int)):
+        raise ValueError("Input f and g must be lists of integers, input modulus must be integer, and input root and inv_root must be integer.")
+    if not is_odd_prime(modulus):
+        raise ValueError("Modulus must be an odd prime.")
+    if not is_pow_two_geq_two(root_order):
+        raise ValueError("Root order must be a power of two greater than or equal to 2.")
+    if not len(f) == len(g) == root_order // 2:
+        raise ValueError(f"f and g must be coefficient representation of degree root_order//2 - 1 polynomial, but had len(f)={len(f)}, len(g)={len(g)}")
+    if not has_primitive_root_of_unity(modulus, root_order):
+        raise ValueError("Modulus does not have a primitive root of unity of order root_order.")
+    if not is_primitive_root(root, modulus, root_order):
+        raise ValueError("Input root must be a primitive root of unity.")
+    if (root * inv_root) % modulus != 1:
+        raise ValueError("Input inv_root must be the inverse of the root of unity.")
+    degree = len(f)
+    if modulus != SCHEME_Q or degree not in _SCHEME or root != _SCHEME[degree][1]:
+        raise NotImplementedError("libfusion_b200 multiplies only in the scheme's rings (q = 2147465729, degree 64 / 256, the reference's psi)")
+    import torch
+
+    ctx = _native.get_context(_SCHEME[degree][0])
+    fc, gc = _centre_list(f, modulus), _centre_list(g, modulus)
+    out = ctx.polymul(torch.tensor(fc, dtype=torch.int32), torch.tensor(gc, dtype=torch.int32)).cpu().tolist()
+    f[:] = fc
+    g[:] = gc
+    return out

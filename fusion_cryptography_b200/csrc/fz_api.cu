@@ -139,6 +139,11 @@ int fz_pointwise_mul(fz_ctx* ctx, const int32_t* a, const int32_t* b, int32_t* o
     return launch_pointwise(ctx, a, b, nullptr, out, n_polys * ctx->d, (cudaStream_t)stream);
 }
 
+int fz_pointwise_add(fz_ctx* ctx, const int32_t* a, const int32_t* b, int32_t* out, size_t n_polys, void* stream) {
+    FZ_REQUIRE(ctx && (n_polys == 0 || (a && b && out)), "fz_pointwise_add: NULL argument");
+    return launch_pointwise_add(ctx, a, b, out, n_polys * ctx->d, (cudaStream_t)stream);
+}
+
 int fz_pointwise_muladd(fz_ctx* ctx, const int32_t* a, const int32_t* b, const int32_t* c, int32_t* out, size_t n_polys, void* stream) {
     FZ_REQUIRE(ctx && (n_polys == 0 || (a && b && c && out)), "fz_pointwise_muladd: NULL argument");
     return launch_pointwise(ctx, a, b, c, out, n_polys * ctx->d, (cudaStream_t)stream);

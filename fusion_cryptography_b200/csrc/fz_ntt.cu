@@ -309,6 +309,16 @@ __global__ void __launch_bounds__(NTT_THREADS) polymul_kernel(const int32_t* a, 
     }
 }
 
+// out = cent(a + b); polynomials.py:282-318 (__add__), also the coefficient representation's :114-148
+__global__ void __launch_bounds__(256) pointwise_add_kernel(const int4* __restrict__ a, const int4* __restrict__ b, int4* __restrict__ out, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        int4 va = ld_stream(a + i), vb = ld_stream(b + i), r;
+        r.x = cent_i64((long long)va.x + vb.x); r.y = cent_i64((long long)va.y + vb.y);
+        r.z = cent_i64((long long)va.z + vb.z); r.w = cent_i64((long long)va.w + vb.w);
+        st_stream(out + i, r);
+    }
+}
+
 // out = cent(a*b) or cent(cent(a*b) + c); n4 = number of int4 groups.  polynomials.py:341-385, 282-318
 template <bool ADD>
 __global__ void __launch_bounds__(256) pointwise_kernel(const int4* __restrict__ a, const int4* __restrict__ b, const int4* __restrict__ c,
@@ -421,6 +431,16 @@ int launch_polymul(const fz_ctx* ctx, const int32_t* a, const int32_t* b, int32_
     else
         polymul_kernel<6><<<persistent_grid(ctx, polymul_kernel<6>, NTT_THREADS, (n_polys + 31) / 32), NTT_THREADS, 0, st>>>(a, b, out, n_polys);
     return check(cudaGetLastError(), "polymul launch");
+}
+
+int launch_pointwise_add(const fz_ctx* ctx, const int32_t* a, const int32_t* b, int32_t* out, size_t n_coef, cudaStream_t st) {
+    if (n_coef == 0) return 0;
+    const size_t n4 = n_coef / 4;
+    size_t blocks = (n4 + 255) / 256;
+    const size_t cap = (size_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    pointwise_add_kernel<<<(int)blocks, 256, 0, st>>>((const int4*)a, (const int4*)b, (int4*)out, n4);
+    return check(cudaGetLastError(), "pointwise_add launch");
 }
 
 int launch_pointwise(const fz_ctx* ctx, const int32_t* a, const int32_t* b, const int32_t* c, int32_t* out, size_t n_coef, cudaStream_t st) {

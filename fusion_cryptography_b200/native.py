@@ -131,6 +131,15 @@ class Context:
         self._chk(self.lib.fz_pointwise_mul(self._h, _ptr(a), _ptr(b), _ptr(out), C.c_size_t(n), self._stream()))
         return out
 
+    def pointwise_add(self, a, b, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        a, b = self._dev(a, "a"), self._dev(b, "b")
+        if a.shape != b.shape:
+            raise ValueError("pointwise_add: shape mismatch")
+        n = self._polys(a, "a")
+        out = torch.empty_like(a) if out is None else out
+        self._chk(self.lib.fz_pointwise_add(self._h, _ptr(a), _ptr(b), _ptr(out), C.c_size_t(n), self._stream()))
+        return out
+
     def pointwise_muladd(self, a, b, c, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         a, b, c = self._dev(a, "a"), self._dev(b, "b"), self._dev(c, "c")
         if a.shape != b.shape or a.shape != c.shape:

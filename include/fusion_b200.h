@@ -48,6 +48,8 @@ int fz_ntt_fwd(fz_ctx* ctx, const int32_t* in, int32_t* out, size_t n_polys, voi
 int fz_ntt_inv(fz_ctx* ctx, const int32_t* in, int32_t* out, size_t n_polys, void* stream);
 /* PolynomialNTTRepresentation.__mul__ (algebra/polynomials.py:341-385) on n_polys polynomials */
 int fz_pointwise_mul(fz_ctx* ctx, const int32_t* a, const int32_t* b, int32_t* out, size_t n_polys, void* stream);
+/* __add__ of either representation (algebra/polynomials.py:114-148, 282-318): out = a + b */
+int fz_pointwise_add(fz_ctx* ctx, const int32_t* a, const int32_t* b, int32_t* out, size_t n_polys, void* stream);
 /* __mul__ then __add__ (algebra/polynomials.py:341-385, 282-318): out = a*b + c */
 int fz_pointwise_muladd(fz_ctx* ctx, const int32_t* a, const int32_t* b, const int32_t* c, int32_t* out, size_t n_polys, void* stream);
 /* algebra/ntt.py:380-484 ntt_poly_mult (result only): out = INTT(NTT(a) o NTT(b)), fused */
