@@ -175,6 +175,82 @@ def run_reference(args, rank, world):
     }), flush=True)
 
 
+def scheme_extras(args, ctx, rank, world, dist):
+    """BASELINE metric, second half: sign/s and aggregate-verify sigs/s (configs[2]-[4]) at secpar 256, per-GPU shards
+    (by signer / by aggregate, no data-path collective), whole-job numbers = sum over ranks / max time."""
+    import numpy as np
+    import torch
+
+    from fusion_cryptography_b200.batch import Engine, KeyBatch
+
+    eng = Engine(SECPAR, seed=42, device=ctx.device_index)
+    dev = ctx.device
+    ell, d, cap = eng.ell, eng.d, ctx.capacity
+    nk = args.extra_keys
+    seeds = (10**6 + 2 * (rank * nk + np.arange(nk))).astype(np.uint64)
+    msgs = [f"msg-{rank * nk + i:07d}".encode() for i in range(nk)]
+
+    def timed(fn, reps=1):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / 1000.0 / reps, out
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    eng.keygen_sign(seeds[:256], msgs[:256])  # warm-up
+    t_ks, (vk_l, vk_r, sigs) = timed(lambda: eng.keygen_sign(seeds, msgs, chunk=4096))
+    t_ks = allmax(t_ks)
+    kb = eng.keygen(seeds)
+    c_hat = eng.challenges(kb.vk_l, kb.vk_r, msgs)
+    t_hash, _ = timed(lambda: eng.challenges(kb.vk_l, kb.vk_r, msgs))
+    t_mac, _ = timed(lambda: ctx.sign_mac_rows(kb.sk_hat, c_hat, out=sigs), reps=5)
+    # general (ell distinct rows) sign MAC, the roofline kernel of SURVEY 8d: reads 2 * ell KiB, writes ell KiB per key
+    nkg = min(nk, 4096)
+    kg = eng.keygen(seeds[:nkg], want_sk=True)
+    t_macg, _ = timed(lambda: ctx.sign_mac(kg.sk_l, kg.sk_r, c_hat[:nkg], out=sigs[:nkg]), reps=5)
+    del kg
+    # aggregates at capacity over sliding windows of the key pool (SURVEY C4 / C5)
+    na = args.extra_aggs
+    counts = [cap] * na
+    base = (np.arange(na)[:, None] * 97 + np.arange(cap)[None, :]) % nk
+    sel = torch.from_numpy(base.reshape(-1).astype(np.int32))
+    amsgs = [msgs[i] for i in base.reshape(-1)]   # key i always signs msgs[i]: its one signature is reused across windows
+    t_agg, aggs = timed(lambda: eng.aggregate(kb.vk_l, kb.vk_r, amsgs, sigs, counts, sel=sel, sig_sel=sel, max_positions=1 << 18))
+    t_ver, codes = timed(lambda: eng.verify(kb.vk_l, kb.vk_r, amsgs, aggs, counts, sel=sel, max_positions=1 << 18))
+    ok = bool((codes == 0).all().item())
+    # the streaming aggregation sum alone (alpha precomputed): 86,016 B per signer
+    perm, vl_s, vr_s, c_s, alpha = eng._sorted_hash(kb.vk_l, kb.vk_r, ctx.hash_msg(amsgs), counts, sel.to(dev))
+    rows = sel.to(dev)[perm.long()].to(torch.int32).contiguous()
+    t_sum, _ = timed(lambda: ctx.aggregate_sum(sigs, rows, alpha, counts), reps=5)
+    t_sum1, _ = timed(lambda: ctx.aggregate_sum(sigs, rows[:cap].contiguous(), alpha[:cap].contiguous(), [cap]), reps=10)
+    t_agg, t_ver = allmax(t_agg), allmax(t_ver)
+    tot = na * cap
+    return {
+        "secpar": SECPAR, "n_gpus": world,
+        "keygen_sign": {"keys_per_gpu": nk, "value": nk * world / t_ks, "unit": "sign/s", "seconds": t_ks,
+                        "note": "seeds -> MT19937 sampler -> NTT -> A.sk -> SHA3/SHAKE challenge -> decode -> NTT -> sk_l*c+sk_r, sk never materialised as ell rows"},
+        "aggregate": {"aggregates_per_gpu": na, "signers_per_aggregate": cap, "value": tot * world / t_agg, "unit": "sigs/s", "seconds": t_agg},
+        "verify": {"aggregates_per_gpu": na, "signers_per_aggregate": cap, "value": tot * world / t_ver, "unit": "sigs/s", "seconds": t_ver, "all_accept": ok},
+        "kernels": {
+            "hash_ch": {"value": nk / t_hash, "unit": "challenges/s/GPU", "bound": "alu (LOP3/SHF)"},
+            "sign_mac_rows": {"GB/s": nk * ell * d * 4 / t_mac / 1e9, "ms": 1000 * t_mac, "bytes": "ell KiB written per key (keys as one row)"},
+            "sign_mac": {"GB/s": nkg * 3 * ell * d * 4 / t_macg / 1e9, "ms": 1000 * t_macg, "bytes": "3 * ell KiB per key (SURVEY 8d: 257,024 B)"},
+            "aggregate_sum": {"GB/s": tot * (ell + 1) * d * 4 / t_sum / 1e9, "ms": 1000 * t_sum, "bytes": "(ell + 1) KiB per signer (SURVEY 8d: 86,016 B)",
+                              "single_capacity_aggregate_us": 1e6 * t_sum1, "single_GB/s": cap * (ell + 1) * d * 4 / t_sum1 / 1e9},
+        },
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -183,6 +259,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--polys", type=int, default=N_POLYS, help="polynomials per GPU (default: the BASELINE size 2^20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the keygen+sign / aggregate / verify throughput section")
+    ap.add_argument("--extra-keys", type=int, default=8192, help="one-time keys per GPU for the sign leg")
+    ap.add_argument("--extra-aggs", type=int, default=32, help="capacity-sized aggregates per GPU for the aggregate/verify leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -291,6 +370,7 @@ def main():
     e2e_s = float(te.item())
     same = bool(torch.equal(hout.to(dev), c))
 
+    extra = scheme_extras(args, ctx, rank, world, dist if world > 1 else None) if not args.no_extras else None
     if rank == 0:
         peak, peak_src = peaks()
         value = n * world * args.steps / (elapsed_ms / 1000.0)
@@ -320,6 +400,11 @@ def main():
             "gpu_launches": 3 * args.steps,
             "clocks": clocks,
         }
+        if extra is not None:
+            for k in ("sign_mac", "aggregate_sum"):
+                if k in extra.get("kernels", {}):
+                    extra["kernels"][k]["frac_of_hbm_peak"] = extra["kernels"][k]["GB/s"] / peak
+            line["extra"] = extra
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
