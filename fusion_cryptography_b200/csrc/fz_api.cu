@@ -101,7 +101,7 @@ int fz_init(int device, int secpar, fz_ctx** out) {
     cudaDeviceProp prop;
     if (check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { delete c; return -2; }
     c->sm_count = prop.multiProcessorCount;
-    if (ntt_init_tables(c) || hash_init_tables(c)) { delete c; return -2; }
+    if (ntt_init_tables(c) || hash_init_tables(c) || hashstream_init_tables(c)) { delete c; return -2; }
     *out = c;
     return 0;
 }
@@ -112,6 +112,16 @@ int fz_destroy(fz_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     delete ctx;
     return 0;
+}
+
+// named integer option: "buffered_hash" = 1 selects the scratch-buffer hashing pipeline (fz_hash.cu) instead of the
+// streaming generator (fz_hashstream.cu); both are bit-identical (tests/test_gpu_scheme.py)
+int fz_set_option(fz_ctx* c, const char* name, long long value) {
+    FZ_REQUIRE(c && name, "fz_set_option: NULL argument");
+    if (!strcmp(name, "buffered_hash")) { c->buffered_hash = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "hash_ag_impl")) { c->hash_ag_impl = (int)value; return 0; }
+    fz::set_error("fz_set_option: unknown option %s", name);
+    return -1;
 }
 
 long long fz_param(const fz_ctx* c, const char* name) {
@@ -267,12 +277,18 @@ int fz_decode_poly(fz_ctx* ctx, const uint8_t* bytes, size_t stride, size_t blen
     return launch_decode(ctx, bytes, stride, (uint32_t)blen, n, weight_bound, (uint32_t)bound, bpc, bpi, coef_out, (cudaStream_t)stream);
 }
 
-size_t fz_hash_ch_workspace(const fz_ctx* ctx, size_t n) { (void)ctx; return r256(n * M1_STRIDE) + r256(n * 4) + 512; }
+size_t fz_hash_ch_workspace(const fz_ctx* ctx, size_t n) { return ctx->buffered_hash ? r256(n * M1_STRIDE) + r256(n * 4) + 512 : 256; }
 
 // fusion.py:511-531 hash_ch for n (vk, prehash digest) pairs: c_hat_out[i] = NTT(decode(SHAKE256(dst "," str(vk_i) "," str(int_i))))
 int fz_hash_ch(fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, size_t n, int32_t* c_hat_out, void* ws, size_t ws_bytes,
                void* stream) {
-    FZ_REQUIRE(ctx && (n == 0 || (vk_l && vk_r && digests && c_hat_out && ws)), "fz_hash_ch: NULL argument");
+    FZ_REQUIRE(ctx && (n == 0 || (vk_l && vk_r && digests && c_hat_out)), "fz_hash_ch: NULL argument");
+    if (!ctx->buffered_hash) {
+        int rc = launch_hash_ch_stream(ctx, vk_l, vk_r, digests, n, c_hat_out, (cudaStream_t)stream);
+        if (!rc) rc = launch_ntt(ctx, 0, c_hat_out, c_hat_out, n, (cudaStream_t)stream);
+        return rc;
+    }
+    FZ_REQUIRE(n == 0 || ws, "fz_hash_ch: workspace required in buffered mode");
     Carver cv(ws, ws_bytes);
     uint8_t* m1 = cv.take<uint8_t>(n * M1_STRIDE);
     uint32_t* len = cv.take<uint32_t>(n);
@@ -285,6 +301,7 @@ int fz_hash_ch(fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint
 }
 
 size_t fz_hash_ag_workspace(const fz_ctx* ctx, size_t n_total, size_t n_aggs, size_t max_keys) {
+    if (!ctx->buffered_hash) return 256;
     return r256(n_total * PIECE_STRIDE) + r256(n_total * 4) + r256(n_total * 8) + r256(n_aggs * msg_stride_for(max_keys)) + r256(n_aggs * 4) +
            r256(n_total * (size_t)ctx->n_ag + 16) + 2048;
 }
@@ -293,8 +310,18 @@ size_t fz_hash_ag_workspace(const fz_ctx* ctx, size_t n_total, size_t n_aggs, si
 // [agg_off[j], agg_off[j+1]) of vk_l_s / vk_r_s / dg_s / c_hat_s.  alpha_hat_out: [n_total][d] in the same order.
 int fz_hash_ag(fz_ctx* ctx, const int32_t* vk_l_s, const int32_t* vk_r_s, const uint8_t* dg_s, const int32_t* c_hat_s, const uint64_t* agg_off,
                size_t n_aggs, size_t n_total, size_t max_keys, int32_t* alpha_hat_out, void* ws, size_t ws_bytes, void* stream) {
-    FZ_REQUIRE(ctx && (n_total == 0 || (vk_l_s && vk_r_s && dg_s && c_hat_s && agg_off && alpha_hat_out && ws)), "fz_hash_ag: NULL argument");
+    FZ_REQUIRE(ctx && (n_total == 0 || (vk_l_s && vk_r_s && dg_s && c_hat_s && agg_off && alpha_hat_out)), "fz_hash_ag: NULL argument");
     if (n_aggs == 0 || n_total == 0) return 0;
+    if (!ctx->buffered_hash) {
+        // one serial sponge per aggregate: a warp per aggregate minimises the chain latency, a thread per aggregate
+        // maximises throughput once there are enough aggregates to fill the machine
+        const bool warp = ctx->hash_ag_impl == 3 || (ctx->hash_ag_impl == 0 && n_aggs < 8192);
+        int rc = warp ? launch_hash_ag_warp(ctx, vk_l_s, vk_r_s, dg_s, c_hat_s, (const unsigned long long*)agg_off, n_aggs, alpha_hat_out, (cudaStream_t)stream)
+                      : launch_hash_ag_stream(ctx, vk_l_s, vk_r_s, dg_s, c_hat_s, (const unsigned long long*)agg_off, n_aggs, alpha_hat_out, (cudaStream_t)stream);
+        if (!rc) rc = launch_ntt(ctx, 0, alpha_hat_out, alpha_hat_out, n_total, (cudaStream_t)stream);
+        return rc;
+    }
+    FZ_REQUIRE(ws, "fz_hash_ag: workspace required in buffered mode");
     Carver cv(ws, ws_bytes);
     const size_t mstride = msg_stride_for(max_keys);
     uint8_t* pieces = cv.take<uint8_t>(n_total * PIECE_STRIDE);

@@ -1,0 +1,775 @@
+// fz_hashstream.cu -- scratch-free challenge / aggregation-coefficient derivation.
+//
+// hash_ch (fusion.py:511-531) and hash_ag (fusion.py:632-652) absorb the *text* of Python reprs
+// (str(OneTimeVerificationKey), str(SignatureChallenge), decimal prehash).  The
+// first implementation (fz_hash.cu) materialises that text in HBM (7-11 KB per signer) before hashing
+// it, which caps how many aggregates can be in flight.  Here every sponge thread GENERATES the text it
+// absorbs, 16 bytes (one value or one chunk of fixed text) at a time, straight from the int32
+// coefficients: no intermediate buffers, no extra HBM traffic, and the squeezed bytes go straight into
+// the sparse-ternary decoder.  hash_ag stays one serial sponge per aggregate (it is one SHAKE256 call
+// in the reference); parallelism comes from many aggregates / signers in flight.
+//
+// Work per thread is a resumable token generator (phase, index) so that the threads of a warp can be
+// at different places of their texts while the Keccak-f calls stay convergent:
+//     loop: { fill: emit tokens until >= 136 bytes are buffered;  absorb 17 lanes;  permute }
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fz_common.cuh"
+#include "fz_internal.h"
+#include "fz_keccak.cuh"
+
+namespace fz {
+
+// decoder (shared with fz_hash.cu through this small duplicate of the constant table)
+__constant__ uint32_t c_magic2[257];
+
+struct SegTable {   // byte offsets / lengths into the fixed-text pool of one level; every segment starts 16-byte aligned
+    uint32_t off[8], len[8];
+};
+// segment ids
+enum { SEG_CH_OPEN = 0, SEG_MID = 1, SEG_CH_CLOSE = 2, SEG_AG_OPEN_FIRST = 3, SEG_AG_OPEN_NEXT = 4, SEG_AG_AFTER_VK = 5, SEG_AG_BEFORE_C = 6, SEG_AG_CLOSE = 7 };
+
+__device__ __align__(16) uint8_t g_text[2][4096];
+__constant__ SegTable c_seg[2];
+
+// ---------------------------------------------------------------------------------- byte queue
+// Whole 64-bit words go to a small local array with plain stores (no read-modify-write on the serial path); the
+// partial word lives in registers.
+constexpr int Q_WORDS = 26;  // 17 rate lanes + room for one 4-value step (<= 52 bytes) plus a 16-byte token of overshoot
+struct Queue {
+    unsigned long long blk[Q_WORDS];
+    unsigned long long cur;  // partial word, nb valid low bytes
+    int nb, wi;              // bytes in cur, complete words in blk
+};
+
+__device__ __forceinline__ void q_reset(Queue& q) { q.cur = 0; q.nb = 0; q.wi = 0; }
+__device__ __forceinline__ int q_bytes(const Queue& q) { return q.wi * 8 + q.nb; }
+
+// append the low n (<= 16) bytes of (lo, hi); bytes above n must be zero
+__device__ __forceinline__ void q_push(Queue& q, unsigned long long lo, unsigned long long hi, int n) {
+    unsigned long long w0, w1, w2;
+    if (q.nb == 0) {
+        w0 = lo; w1 = hi; w2 = 0;
+    } else {
+        const int sh = q.nb * 8;
+        w0 = q.cur | (lo << sh);
+        w1 = (lo >> (64 - sh)) | (hi << sh);
+        w2 = hi >> (64 - sh);
+    }
+    const int tot = q.nb + n;
+    if (tot >= 16) {
+        q.blk[q.wi] = w0; q.blk[q.wi + 1] = w1; q.wi += 2; q.cur = w2;
+    } else if (tot >= 8) {
+        q.blk[q.wi] = w0; q.wi += 1; q.cur = w1;
+    } else {
+        q.cur = w0;
+    }
+    q.nb = tot & 7;
+}
+
+// absorb the 17 full lanes and keep what is beyond them
+__device__ __forceinline__ void q_absorb_full(Queue& q, unsigned long long (&a)[25]) {
+#pragma unroll
+    for (int k = 0; k < KECCAK_RATE_LANES; ++k) a[k] ^= q.blk[k];
+    const int extra = q.wi - KECCAK_RATE_LANES;
+    for (int k = 0; k < extra; ++k) q.blk[k] = q.blk[KECCAK_RATE_LANES + k];
+    q.wi = extra;
+}
+
+// final (partial) block with SHAKE padding; fewer than 136 bytes are buffered
+__device__ __forceinline__ void q_absorb_last(Queue& q, unsigned long long (&a)[25]) {
+    q.blk[q.wi] = q.cur;
+    for (int k = q.wi + 1; k < KECCAK_RATE_LANES; ++k) q.blk[k] = 0;
+    q.blk[q.wi] ^= 0x1FULL << (q.nb * 8);
+    q.blk[16] ^= 0x8000000000000000ULL;
+#pragma unroll
+    for (int k = 0; k < KECCAK_RATE_LANES; ++k) a[k] ^= q.blk[k];
+}
+
+// ---------------------------------------------------------------------------------- value formatting
+// decimal text of v followed by ", " (sep) -> up to 13 bytes, first character in the lowest byte
+__device__ __forceinline__ int fmt_value(int32_t v, bool sep, unsigned long long& lo, unsigned long long& hi) {
+    uint32_t u = v < 0 ? (uint32_t)(-(long long)v) : (uint32_t)v;
+    // zero padded digits m0..m9 (m0 most significant) from nine INDEPENDENT constant divisions (short dependency chain)
+    const uint32_t q1 = u / 10u, q2 = u / 100u, q3 = u / 1000u, q4 = u / 10000u, q5 = u / 100000u;
+    const uint32_t q6 = u / 1000000u, q7 = u / 10000000u, q8 = u / 100000000u, q9 = u / 1000000000u;
+    const uint32_t m9 = u - 10u * q1, m8 = q1 - 10u * q2, m7 = q2 - 10u * q3, m6 = q3 - 10u * q4, m5 = q4 - 10u * q5;
+    const uint32_t m4 = q5 - 10u * q6, m3 = q6 - 10u * q7, m2 = q7 - 10u * q8, m1 = q8 - 10u * q9, m0 = q9;
+    const uint32_t w0 = (m0 | (m1 << 8) | (m2 << 16) | (m3 << 24)) + 0x30303030u;
+    const uint32_t w1 = (m4 | (m5 << 8) | (m6 << 16) | (m7 << 24)) + 0x30303030u;
+    const uint32_t w2 = (m8 | (m9 << 8)) + 0x3030u;
+    int nd = 1;
+    if (u >= 10u) nd = 2;
+    if (u >= 100u) nd = 3;
+    if (u >= 1000u) nd = 4;
+    if (u >= 10000u) nd = 5;
+    if (u >= 100000u) nd = 6;
+    if (u >= 1000000u) nd = 7;
+    if (u >= 10000000u) nd = 8;
+    if (u >= 100000000u) nd = 9;
+    if (u >= 1000000000u) nd = 10;
+    // drop the 10 - nd leading zeros: 80-bit right shift by whole bytes
+    unsigned long long s_lo = ((unsigned long long)w1 << 32) | w0, s_hi = w2;
+    const int skip = 10 - nd;
+    if (skip >= 8) {
+        s_lo = s_hi >> ((skip - 8) * 8);
+        s_hi = 0;
+    } else if (skip > 0) {
+        s_lo = (s_lo >> (skip * 8)) | (s_hi << (64 - skip * 8));
+        s_hi = s_hi >> (skip * 8);
+    }
+    int len = nd;
+    if (v < 0) {  // prepend '-'
+        s_hi = (s_hi << 8) | (s_lo >> 56);
+        s_lo = (s_lo << 8) | 0x2dULL;
+        ++len;
+    }
+    if (sep) {  // append ", "
+        if (len < 7) s_lo |= 0x202cULL << (len * 8);
+        else if (len == 7) { s_lo |= 0x2cULL << 56; s_hi |= 0x20ULL; }
+        else s_hi |= 0x202cULL << ((len - 8) * 8);
+        len += 2;
+    }
+    lo = s_lo;
+    hi = s_hi;
+    return len;
+}
+
+// decimal text of int.from_bytes(digest, "little") into buf (<= 78 bytes), returns length
+__device__ int fmt_le256(const uint8_t* __restrict__ dg, uint8_t* buf) {
+    uint32_t limb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        limb[i] = (uint32_t)dg[4 * i] | ((uint32_t)dg[4 * i + 1] << 8) | ((uint32_t)dg[4 * i + 2] << 16) | ((uint32_t)dg[4 * i + 3] << 24);
+    uint8_t tmp[88];
+    int n = 0;
+    for (;;) {
+        uint32_t nz = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nz |= limb[i];
+        if (!nz) break;
+        unsigned long long rem = 0;
+#pragma unroll
+        for (int i = 7; i >= 0; --i) {
+            const unsigned long long cur = (rem << 32) | limb[i];
+            limb[i] = (uint32_t)(cur / 1000000000ULL);
+            rem = cur - (unsigned long long)limb[i] * 1000000000ULL;
+        }
+        uint32_t r = (uint32_t)rem;
+        for (int k = 0; k < 9; ++k) { tmp[n++] = (uint8_t)('0' + r % 10u); r /= 10u; }
+    }
+    while (n > 1 && tmp[n - 1] == '0') --n;
+    if (n == 0) tmp[n++] = '0';
+    for (int i = 0; i < n; ++i) buf[i] = tmp[n - 1 - i];
+    for (int i = n; i < 96; ++i) buf[i] = 0;
+    return n;
+}
+
+// ---------------------------------------------------------------------------------- token generator
+// A text is a list of items; items are fixed segments, value lists or the prehash decimal.
+struct Gen {
+    int item;        // index in the program
+    int idx;         // token index inside the item
+    int int_len;     // length of the decimal prehash of the current signer
+    uint8_t intbuf[96];
+};
+
+__device__ __forceinline__ bool gen_segment(Gen& g, Queue& q, int level, int seg) {  // returns true when the item is finished
+    const uint32_t len = c_seg[level].len[seg];
+    const uint8_t* p = g_text[level] + c_seg[level].off[seg] + 16 * g.idx;
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const int n = (int)len - 16 * g.idx < 16 ? (int)len - 16 * g.idx : 16;
+    q_push(q, ((unsigned long long)t.y << 32) | t.x, ((unsigned long long)t.w << 32) | t.z, n);
+    ++g.idx;
+    return 16 * g.idx >= (int)len;
+}
+
+// four values per step (one 16-byte load); d is a multiple of 4
+__device__ __forceinline__ bool gen_values(Gen& g, Queue& q, const int32_t* __restrict__ vals, int d) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(vals) + g.idx);
+    unsigned long long lo, hi;
+    int n = fmt_value(v.x, true, lo, hi); q_push(q, lo, hi, n);
+    n = fmt_value(v.y, true, lo, hi); q_push(q, lo, hi, n);
+    n = fmt_value(v.z, true, lo, hi); q_push(q, lo, hi, n);
+    n = fmt_value(v.w, 4 * g.idx + 4 != d, lo, hi); q_push(q, lo, hi, n);
+    ++g.idx;
+    return 4 * g.idx >= d;
+}
+
+__device__ __forceinline__ bool gen_int(Gen& g, Queue& q, const uint8_t* __restrict__ digest) {
+    if (g.idx == 0) g.int_len = fmt_le256(digest, g.intbuf);
+    unsigned long long lo = 0, hi = 0;
+    const int base = 16 * g.idx;
+    const int n = g.int_len - base < 16 ? g.int_len - base : 16;
+    for (int k = 0; k < 8; ++k) lo |= (unsigned long long)g.intbuf[base + k] << (8 * k);
+    for (int k = 0; k < 8; ++k) hi |= (unsigned long long)g.intbuf[base + 8 + k] << (8 * k);
+    q_push(q, lo, hi, n);
+    ++g.idx;
+    return 16 * g.idx >= g.int_len;
+}
+
+// ---------------------------------------------------------------------------------- decoder (fusion.py:422-481)
+struct Dec {
+    int d, weight, bpc, bpi;
+    uint32_t bound;
+    int phase, item, left;
+    unsigned long long acc;
+    uint32_t acc32, m, magic;
+    unsigned long long sg[4];
+};
+__device__ __forceinline__ int dsign(const Dec& s, int i) { return 2 * (int)((s.sg[(i >> 6) & 3] >> (i & 63)) & 1ULL) - 1; }
+__device__ __forceinline__ void dset(Dec& s, int i) {
+    s.item = i; s.left = s.bpi; s.acc32 = 0; s.m = (uint32_t)(i + 1); s.magic = c_magic2[s.m <= 256 ? s.m : 0];
+}
+__device__ __forceinline__ void dfinish(Dec& s, int32_t* c) {
+    if (s.phase == 0) {
+        s.phase = 1; s.item = 0; s.left = s.bpc; s.acc = 0;
+        if (s.weight == 0) { s.phase = 2; dset(s, s.d - 1); }
+    } else if (s.phase == 1) {
+        const int i = s.item;
+        const long long mag = (long long)(s.bound == 1 ? 0ULL : s.acc % s.bound) + 1;
+        if (i < s.d) c[i] = (int32_t)(mag * dsign(s, i));
+        s.item++; s.left = s.bpc; s.acc = 0;
+        if (s.item >= s.weight) { s.phase = 2; dset(s, s.d - 1); }
+    } else if (s.phase == 2) {
+        const int i = s.item, j = (int)s.acc32;
+        const int32_t t = c[i]; c[i] = c[j]; c[j] = t;
+        dset(s, i - 1);
+    }
+    if (s.phase == 2 && (s.item <= s.weight || s.weight >= s.d)) s.phase = 3;
+}
+__device__ __forceinline__ void dinit(Dec& s, int32_t* c, int d, int weight, uint32_t bound, int bpc, int bpi) {
+    s.d = d; s.weight = weight; s.bound = bound; s.bpc = bpc; s.bpi = bpi;
+    s.phase = 0; s.item = 0; s.left = (weight + 7) / 8; s.acc = 0; s.acc32 = 0; s.m = 1; s.magic = 0;
+    s.sg[0] = s.sg[1] = s.sg[2] = s.sg[3] = 0;
+    while (s.left == 0 && s.phase != 3) dfinish(s, c);
+}
+__device__ __forceinline__ void dbyte(Dec& s, int32_t* c, uint32_t b) {
+    if (s.phase == 2) {
+        const uint32_t v = (s.acc32 << 8) | b;
+        s.acc32 = v - __umulhi(v, s.magic) * s.m;
+    } else if (s.phase == 1) {
+        if (s.bound != 1) s.acc = ((s.acc << 8) | b) % s.bound;
+    } else {
+        s.sg[3] = (s.sg[3] << 8) | (s.sg[2] >> 56);
+        s.sg[2] = (s.sg[2] << 8) | (s.sg[1] >> 56);
+        s.sg[1] = (s.sg[1] << 8) | (s.sg[0] >> 56);
+        s.sg[0] = (s.sg[0] << 8) | b;
+    }
+    if (--s.left == 0) dfinish(s, c);
+}
+
+// ---------------------------------------------------------------------------------- hash_ch
+// one thread per signer: text = dst "," str(vk) "," str(prehash)   (fusion.py:416-418), then squeeze + decode
+constexpr int HS_THREADS = 64;
+
+__global__ void __launch_bounds__(HS_THREADS) hash_ch_stream_kernel(const int32_t* __restrict__ vk_l, const int32_t* __restrict__ vk_r,
+                                                                     const uint8_t* __restrict__ digests, size_t n, int level, int d, int weight, int bpc,
+                                                                     int bpi, uint32_t n_used, int32_t* __restrict__ coef_out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long a[25];
+#pragma unroll
+    for (int k = 0; k < 25; ++k) a[k] = 0;
+    Queue q;
+    q_reset(q);
+    Gen g;
+    g.item = 0; g.idx = 0; g.int_len = 0;
+    const int32_t* vl = vk_l + i * d;
+    const int32_t* vr = vk_r + i * d;
+    // program: 0 SEG_CH_OPEN, 1 values(vk_l), 2 SEG_MID, 3 values(vk_r), 4 SEG_CH_CLOSE, 5 INT, 6 done
+    for (;;) {
+        while (q_bytes(q) < KECCAK_RATE && g.item < 6) {
+            bool fin;
+            switch (g.item) {
+                case 0: fin = gen_segment(g, q, level, SEG_CH_OPEN); break;
+                case 1: fin = gen_values(g, q, vl, d); break;
+                case 2: fin = gen_segment(g, q, level, SEG_MID); break;
+                case 3: fin = gen_values(g, q, vr, d); break;
+                case 4: fin = gen_segment(g, q, level, SEG_CH_CLOSE); break;
+                default: fin = gen_int(g, q, digests + i * 32); break;
+            }
+            if (fin) { ++g.item; g.idx = 0; }
+        }
+        if (q_bytes(q) >= KECCAK_RATE) {
+            q_absorb_full(q, a);
+            keccak_f(a);
+        } else {
+            q_absorb_last(q, a);
+            keccak_f(a);
+            break;
+        }
+    }
+    int32_t c[256];
+    for (int k = 0; k < d; ++k) c[k] = 0;
+    Dec s;
+    dinit(s, c, d, weight, 1u, bpc, bpi);
+    uint32_t produced = 0;
+    while (produced < n_used && s.phase != 3) {
+        unsigned long long blk[KECCAK_RATE_LANES];
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) blk[k] = a[k];
+        const uint32_t take = n_used - produced < (uint32_t)KECCAK_RATE ? n_used - produced : (uint32_t)KECCAK_RATE;
+        for (uint32_t j = 0; j < take && s.phase != 3; ++j) dbyte(s, c, (uint32_t)(blk[j >> 3] >> (8 * (j & 7))) & 0xffu);
+        produced += take;
+        if (produced < n_used && s.phase != 3) keccak_f(a);
+    }
+    while (s.phase != 3) dfinish(s, c);
+    int32_t* o = coef_out + i * d;
+    for (int k = 0; k < d; ++k) o[k] = c[k];
+}
+
+// ---------------------------------------------------------------------------------- hash_ag
+// one thread per aggregate: text = dst "," "[" "(" VK ", " INT ", " CH ")" ", " ... "]"  (fusion.py:586-590) over the sorted
+// signers [agg_off[j], agg_off[j+1]); then (hi - lo) * n_ag bytes are squeezed and decoded signer by signer.
+__global__ void __launch_bounds__(32) hash_ag_stream_kernel(const int32_t* __restrict__ vk_l_s, const int32_t* __restrict__ vk_r_s,
+                                                              const uint8_t* __restrict__ dg_s, const int32_t* __restrict__ c_hat_s,
+                                                              const unsigned long long* __restrict__ agg_off, size_t n_aggs, int level, int d, int weight,
+                                                              int bpc, int bpi, uint32_t n_ag, int32_t* __restrict__ coef_out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_aggs) return;
+    const size_t lo = agg_off[j], hi = agg_off[j + 1];
+    unsigned long long a[25];
+#pragma unroll
+    for (int k = 0; k < 25; ++k) a[k] = 0;
+    Queue q;
+    q_reset(q);
+    Gen g;
+    g.item = 0; g.idx = 0; g.int_len = 0;
+    size_t p = lo;
+    bool more = true;
+    if (hi == lo) {  // "[]": dst "," "[" "]"
+        q_push(q, (unsigned long long)(level == 1 ? 3 : 1) | (2ULL << 8) | ((unsigned long long)',' << 16) | ((unsigned long long)'[' << 24) |
+                      ((unsigned long long)']' << 32), 0, 5);
+        more = false;
+    }
+    // per-signer program: 0 OPEN (first / next), 1 values(vk_l), 2 MID, 3 values(vk_r), 4 AFTER_VK, 5 INT, 6 BEFORE_C, 7 values(c_hat), 8 CLOSE
+    for (;;) {
+        while (q_bytes(q) < KECCAK_RATE && more) {
+            bool fin;
+            switch (g.item) {
+                case 0: fin = gen_segment(g, q, level, p == lo ? SEG_AG_OPEN_FIRST : SEG_AG_OPEN_NEXT); break;
+                case 1: fin = gen_values(g, q, vk_l_s + p * d, d); break;
+                case 2: fin = gen_segment(g, q, level, SEG_MID); break;
+                case 3: fin = gen_values(g, q, vk_r_s + p * d, d); break;
+                case 4: fin = gen_segment(g, q, level, SEG_AG_AFTER_VK); break;
+                case 5: fin = gen_int(g, q, dg_s + p * 32); break;
+                case 6: fin = gen_segment(g, q, level, SEG_AG_BEFORE_C); break;
+                case 7: fin = gen_values(g, q, c_hat_s + p * d, d); break;
+                default: fin = gen_segment(g, q, level, SEG_AG_CLOSE); break;
+            }
+            if (fin) {
+                g.idx = 0;
+                if (++g.item == 9) {
+                    g.item = 0;
+                    if (++p == hi) {
+                        q_push(q, (unsigned long long)']', 0, 1);
+                        more = false;
+                    }
+                }
+            }
+        }
+        if (q_bytes(q) >= KECCAK_RATE) {
+            q_absorb_full(q, a);
+            keccak_f(a);
+        } else {
+            q_absorb_last(q, a);
+            keccak_f(a);
+            break;
+        }
+    }
+    // squeeze + decode, one coefficient polynomial per signer, n_ag bytes each
+    int32_t c[256];
+    unsigned long long blk[KECCAK_RATE_LANES];
+#pragma unroll
+    for (int k = 0; k < KECCAK_RATE_LANES; ++k) blk[k] = a[k];
+    int bpos = 0;  // bytes consumed from the current block
+    for (size_t sp = lo; sp < hi; ++sp) {
+        for (int k = 0; k < d; ++k) c[k] = 0;
+        Dec s;
+        dinit(s, c, d, weight, 1u, bpc, bpi);
+        uint32_t used = 0;
+        while (used < n_ag) {
+            if (bpos == KECCAK_RATE) {
+                keccak_f(a);
+#pragma unroll
+                for (int k = 0; k < KECCAK_RATE_LANES; ++k) blk[k] = a[k];
+                bpos = 0;
+            }
+            const uint32_t avail = KECCAK_RATE - bpos, need = n_ag - used;
+            const uint32_t take = avail < need ? avail : need;
+            if (s.phase != 3)
+                for (uint32_t t = 0; t < take && s.phase != 3; ++t) {
+                    const int jb = bpos + (int)t;
+                    dbyte(s, c, (uint32_t)(blk[jb >> 3] >> (8 * (jb & 7))) & 0xffu);
+                }
+            bpos += (int)take;
+            used += take;
+        }
+        while (s.phase != 3) dfinish(s, c);  // the slice is exhausted: remaining draws see empty bytes (quirk Q4)
+        int32_t* o = coef_out + sp * d;
+        for (int k = 0; k < d; ++k) o[k] = c[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------- host
+static void add_seg(std::vector<uint8_t>& pool, SegTable& t, int id, const std::string& s) {
+    while (pool.size() % 16) pool.push_back(0);
+    t.off[id] = (uint32_t)pool.size();
+    t.len[id] = (uint32_t)s.size();
+    pool.insert(pool.end(), s.begin(), s.end());
+    while (pool.size() % 16) pool.push_back(0);
+}
+
+int hashstream_init_tables(fz_ctx* ctx) {
+    uint32_t magic[257];
+    magic[0] = 0; magic[1] = 0;
+    for (uint32_t m = 2; m <= 256; ++m) magic[m] = 0xFFFFFFFFu / m + 1u;
+    if (check(cudaMemcpyToSymbol(c_magic2, magic, sizeof(magic)), "decoder constants upload")) return -2;
+    SegTable tabs[2];
+    const int degs[2] = {64, 256};
+    const unsigned roots[2] = {23584283u, 3337519u}, iroots[2] = {540632852u, 1978410468u};
+    for (int L = 0; L < 2; ++L) {
+        char ph[192];
+        snprintf(ph, sizeof(ph), "PolynomialNTTRepresentation(modulus=2147465729, degree=%d, root=%u, inv_root=%u, root_order=%d, values=[", degs[L], roots[L],
+                 iroots[L], 2 * degs[L]);
+        const std::string poly_head(ph);
+        const std::string gm_head = "GeneralMatrix(elem_class=<class 'algebra.polynomials.PolynomialNTTRepresentation'>, matrix=[[";
+        const std::string vk_head = "OneTimeVerificationKey(left_vk_hat=" + gm_head + poly_head;
+        const std::string mid = "])]]), right_vk_hat=" + gm_head + poly_head;
+        const std::string dst(1, (char)(L == 1 ? 3 : 1));
+        std::vector<uint8_t> pool;
+        memset(&tabs[L], 0, sizeof(SegTable));
+        add_seg(pool, tabs[L], SEG_CH_OPEN, dst + std::string(1, (char)1) + "," + vk_head);                          // fusion.py:416-418
+        add_seg(pool, tabs[L], SEG_MID, mid);
+        add_seg(pool, tabs[L], SEG_CH_CLOSE, "])]])),");
+        add_seg(pool, tabs[L], SEG_AG_OPEN_FIRST, dst + std::string(1, (char)2) + ",[(" + vk_head);                 // fusion.py:586-590
+        add_seg(pool, tabs[L], SEG_AG_OPEN_NEXT, ", (" + vk_head);
+        add_seg(pool, tabs[L], SEG_AG_AFTER_VK, "])]])), ");
+        add_seg(pool, tabs[L], SEG_AG_BEFORE_C, ", SignatureChallenge(c_hat=" + poly_head);
+        add_seg(pool, tabs[L], SEG_AG_CLOSE, "])))");
+        if (pool.size() > 4096) { set_error("fixed-text pool overflow"); return -1; }
+        pool.resize(4096, 0);
+        if (check(cudaMemcpyToSymbol(g_text, pool.data(), 4096, (size_t)L * 4096), "fixed text upload")) return -2;
+    }
+    (void)ctx;
+    return check(cudaMemcpyToSymbol(c_seg, tabs, sizeof(tabs)), "segment table upload");
+}
+
+int launch_hash_ch_stream(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, size_t n, int32_t* coef_out,
+                          cudaStream_t st) {
+    if (n == 0) return 0;
+    hash_ch_stream_kernel<<<(int)((n + HS_THREADS - 1) / HS_THREADS), HS_THREADS, 0, st>>>(vk_l, vk_r, digests, n, ctx->secpar == 256 ? 1 : 0, ctx->d,
+                                                                                            ctx->omega_ch, ctx->bytes_coef, ctx->bytes_idx,
+                                                                                            (uint32_t)ctx->n_ch_used, coef_out);
+    return check(cudaGetLastError(), "hash_ch_stream launch");
+}
+
+int launch_hash_ag_stream(const fz_ctx* ctx, const int32_t* vk_l_s, const int32_t* vk_r_s, const uint8_t* dg_s, const int32_t* c_hat_s,
+                          const unsigned long long* agg_off, size_t n_aggs, int32_t* coef_out, cudaStream_t st) {
+    if (n_aggs == 0) return 0;
+    hash_ag_stream_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>(vk_l_s, vk_r_s, dg_s, c_hat_s, agg_off, n_aggs, ctx->secpar == 256 ? 1 : 0, ctx->d,
+                                                                     ctx->omega_ag, ctx->bytes_coef, ctx->bytes_idx, (uint32_t)ctx->n_ag, coef_out);
+    return check(cudaGetLastError(), "hash_ag_stream launch");
+}
+
+
+// ==========================================================================================
+// Warp-cooperative variant of hash_ag: ONE WARP per aggregate.
+//
+// The aggregation hash is a single serial sponge per aggregate (fusion.py:573-591), ~279 K Keccak-f for a capacity
+// aggregate at secpar 256.  With one thread per sponge a permutation takes ~14 K cycles of one warp, which bounds the
+// latency of a batch of a few thousand aggregates.  Here 25 lanes hold one 64-bit Keccak lane each and exchange
+// through warp shuffles (theta: 4 + 2, pi: 1, chi: 2 sixty-four-bit shuffles per round), the 32 lanes format 32
+// coefficients of the repr text at a time into a block-aligned shared-memory ring, and the squeezed bytes are decoded
+// cooperatively (the 60 / 35 index draws of one coefficient polynomial are independent Horner reductions).
+namespace warpag {
+
+constexpr int RING_BLOCKS = 16;
+constexpr int RING_BYTES = RING_BLOCKS * KECCAK_RATE;   // 2176, every block start is 8-byte aligned
+constexpr int XOF_BYTES = 4096;                         // >= n_ag (3968 @256, 1195 @128) rounded up
+constexpr int WARPS = 4;
+constexpr int SMEM_PER_WARP = RING_BYTES + XOF_BYTES + 1024 + 64;
+
+__constant__ int c_rot[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+
+struct Lane {  // per-lane constants of the cooperative permutation
+    int src5, src10, src15, src20;  // same column, other rows
+    int xm1, xp1, xp2;              // same row, columns x-1, x+1, x+2
+    int pi0, pi1, pi2;              // lanes whose rotated values become B[x][y], B[x+1][y], B[x+2][y] after pi
+    int rot;
+    bool active;
+};
+
+__device__ __forceinline__ Lane lane_init(int L) {
+    Lane c;
+    const int l = L < 25 ? L : 0;
+    const int x = l % 5, y = l / 5;
+    c.src5 = (l + 5) % 25; c.src10 = (l + 10) % 25; c.src15 = (l + 15) % 25; c.src20 = (l + 20) % 25;
+    c.xm1 = (x + 4) % 5 + 5 * y; c.xp1 = (x + 1) % 5 + 5 * y; c.xp2 = (x + 2) % 5 + 5 * y;
+    // pi: B[x'][y'] = rot(A[(x' + 3y') % 5][x']); chi reads B at columns x, x+1, x+2 of the same row, so the three
+    // sources are gathered straight from the rotated values (pi and chi in one shuffle level)
+    const int x1 = (x + 1) % 5, x2 = (x + 2) % 5;
+    c.pi0 = ((x + 3 * y) % 5) + 5 * x;
+    c.pi1 = ((x1 + 3 * y) % 5) + 5 * x1;
+    c.pi2 = ((x2 + 3 * y) % 5) + 5 * x2;
+    c.rot = c_rot[l];
+    c.active = L < 25;
+    return c;
+}
+
+#define FZ_SHFL(v, s) __shfl_sync(0xffffffffu, (v), (s))
+
+__device__ __forceinline__ void keccak_f_warp(uint32_t& lo, uint32_t& hi, const Lane& c, int L) {
+#pragma unroll 1
+    for (int r = 0; r < 24; ++r) {
+        // theta
+        uint32_t cl = lo ^ FZ_SHFL(lo, c.src5) ^ FZ_SHFL(lo, c.src10) ^ FZ_SHFL(lo, c.src15) ^ FZ_SHFL(lo, c.src20);
+        uint32_t ch = hi ^ FZ_SHFL(hi, c.src5) ^ FZ_SHFL(hi, c.src10) ^ FZ_SHFL(hi, c.src15) ^ FZ_SHFL(hi, c.src20);
+        const uint32_t ml = FZ_SHFL(cl, c.xm1), mh = FZ_SHFL(ch, c.xm1);
+        const uint32_t pl = FZ_SHFL(cl, c.xp1), ph = FZ_SHFL(ch, c.xp1);
+        lo ^= ml ^ __funnelshift_l(ph, pl, 1);
+        hi ^= mh ^ __funnelshift_l(pl, ph, 1);
+        // rho: rotate left by c.rot
+        {
+            const bool sw = c.rot >= 32;
+            const uint32_t a = sw ? hi : lo, b = sw ? lo : hi;   // value = (b:a) rotated by rot & 31
+            const int s = c.rot & 31;
+            lo = __funnelshift_l(b, a, s);
+            hi = __funnelshift_l(a, b, s);
+        }
+        // pi + chi
+        const uint32_t b0l = FZ_SHFL(lo, c.pi0), b0h = FZ_SHFL(hi, c.pi0);
+        const uint32_t b1l = FZ_SHFL(lo, c.pi1), b1h = FZ_SHFL(hi, c.pi1);
+        const uint32_t b2l = FZ_SHFL(lo, c.pi2), b2h = FZ_SHFL(hi, c.pi2);
+        lo = b0l ^ (~b1l & b2l);
+        hi = b0h ^ (~b1h & b2h);
+        // iota
+        if (L == 0) {
+            const unsigned long long rc = c_keccak_rc[r];
+            lo ^= (uint32_t)rc;
+            hi ^= (uint32_t)(rc >> 32);
+        }
+    }
+}
+
+struct Ring {
+    uint8_t* buf;   // RING_BYTES, block aligned
+    int wr;         // total bytes written
+    int rd;         // total bytes absorbed (multiple of 136)
+};
+
+// all lanes: append `n` (<= 16) bytes of this lane's token after the tokens of the lower lanes
+__device__ __forceinline__ void ring_put_tokens(Ring& rg, unsigned long long lo, unsigned long long hi, int n, int L) {
+    int x = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (L >= o) x += y;
+    }
+    const int total = __shfl_sync(0xffffffffu, x, 31);
+    int off = (rg.wr + x - n) % RING_BYTES;
+    for (int k = 0; k < n; ++k) {
+        rg.buf[off] = (uint8_t)((k < 8 ? lo >> (8 * k) : hi >> (8 * (k - 8))) & 0xff);
+        off = off + 1 == RING_BYTES ? 0 : off + 1;
+    }
+    rg.wr += total;
+}
+
+// absorb every complete block currently in the ring
+__device__ __forceinline__ void ring_drain(Ring& rg, uint32_t& lo, uint32_t& hi, const Lane& c, int L) {
+    __syncwarp();
+    while (rg.wr - rg.rd >= KECCAK_RATE) {
+        if (L < KECCAK_RATE_LANES) {
+            const uint2 w = *reinterpret_cast<const uint2*>(rg.buf + (rg.rd % RING_BYTES) + 8 * L);
+            lo ^= w.x;
+            hi ^= w.y;
+        }
+        keccak_f_warp(lo, hi, c, L);
+        rg.rd += KECCAK_RATE;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void ring_segment(Ring& rg, int level, int seg, uint32_t& lo, uint32_t& hi, const Lane& c, int L) {
+    const int len = (int)c_seg[level].len[seg];
+    const uint8_t* p = g_text[level] + c_seg[level].off[seg];
+    for (int base = 0; base < len; base += 32 * 16) {   // 32 lanes x 16-byte tokens per round
+        const int t = base + 16 * L;
+        int n = len - t;
+        n = n < 0 ? 0 : (n > 16 ? 16 : n);
+        unsigned long long a = 0, b = 0;
+        if (n > 0) {
+            const uint4 v = *reinterpret_cast<const uint4*>(p + t);
+            a = ((unsigned long long)v.y << 32) | v.x;
+            b = ((unsigned long long)v.w << 32) | v.z;
+        }
+        ring_put_tokens(rg, a, b, n, L);
+        ring_drain(rg, lo, hi, c, L);
+    }
+}
+
+__device__ __forceinline__ void ring_values(Ring& rg, const int32_t* __restrict__ vals, int d, uint32_t& lo, uint32_t& hi, const Lane& c, int L) {
+    for (int base = 0; base < d; base += 32) {
+        unsigned long long a, b;
+        const int n = fmt_value(vals[base + L], base + L != d - 1, a, b);
+        ring_put_tokens(rg, a, b, n, L);
+        ring_drain(rg, lo, hi, c, L);
+    }
+}
+
+__global__ void __launch_bounds__(WARPS * 32) hash_ag_warp_kernel(const int32_t* __restrict__ vk_l_s, const int32_t* __restrict__ vk_r_s,
+                                                                   const uint8_t* __restrict__ dg_s, const int32_t* __restrict__ c_hat_s,
+                                                                   const unsigned long long* __restrict__ agg_off, size_t n_aggs, int level, int d, int weight,
+                                                                   int bpc, int bpi, uint32_t n_ag, int32_t* __restrict__ coef_out) {
+    extern __shared__ __align__(16) uint8_t wsm[];
+    const int L = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t j = (size_t)blockIdx.x * WARPS + warp;
+    if (j >= n_aggs) return;
+    uint8_t* base = wsm + (size_t)warp * SMEM_PER_WARP;
+    Ring rg;
+    rg.buf = base; rg.wr = 0; rg.rd = 0;
+    uint8_t* xof = base + RING_BYTES;            // squeezed bytes of the current signer (+ carry-over)
+    int8_t* cf = reinterpret_cast<int8_t*>(base + RING_BYTES + XOF_BYTES);   // d coefficients
+    uint8_t* intbuf = base + RING_BYTES + XOF_BYTES + 512;                   // 96 bytes decimal prehash
+    int* jdraw = reinterpret_cast<int*>(base + RING_BYTES + XOF_BYTES + 640);  // up to 64 index draws
+    const Lane c = lane_init(L);
+    uint32_t lo = 0, hi = 0;
+    const size_t p0 = agg_off[j], p1 = agg_off[j + 1];
+    // ---- absorb
+    if (p1 == p0) {
+        const unsigned long long t = (unsigned long long)(level == 1 ? 3 : 1) | (2ULL << 8) | ((unsigned long long)',' << 16) |
+                                     ((unsigned long long)'[' << 24) | ((unsigned long long)']' << 32);
+        ring_put_tokens(rg, L == 0 ? t : 0ULL, 0ULL, L == 0 ? 5 : 0, L);
+    }
+    for (size_t p = p0; p < p1; ++p) {
+        ring_segment(rg, level, p == p0 ? SEG_AG_OPEN_FIRST : SEG_AG_OPEN_NEXT, lo, hi, c, L);
+        ring_values(rg, vk_l_s + p * d, d, lo, hi, c, L);
+        ring_segment(rg, level, SEG_MID, lo, hi, c, L);
+        ring_values(rg, vk_r_s + p * d, d, lo, hi, c, L);
+        ring_segment(rg, level, SEG_AG_AFTER_VK, lo, hi, c, L);
+        int ilen = 0;
+        if (L == 0) ilen = fmt_le256(dg_s + p * 32, intbuf);
+        ilen = __shfl_sync(0xffffffffu, ilen, 0);
+        __syncwarp();
+        {
+            const int t = 16 * L;
+            int n = ilen - t;
+            n = n < 0 ? 0 : (n > 16 ? 16 : n);
+            unsigned long long a = 0, b = 0;
+            if (n > 0) {
+                for (int k = 0; k < 8; ++k) a |= (unsigned long long)intbuf[t + k] << (8 * k);
+                for (int k = 0; k < 8; ++k) b |= (unsigned long long)intbuf[t + 8 + k] << (8 * k);
+            }
+            ring_put_tokens(rg, a, b, n, L);
+            ring_drain(rg, lo, hi, c, L);
+        }
+        ring_segment(rg, level, SEG_AG_BEFORE_C, lo, hi, c, L);
+        ring_values(rg, c_hat_s + p * d, d, lo, hi, c, L);
+        ring_segment(rg, level, SEG_AG_CLOSE, lo, hi, c, L);
+        if (p + 1 == p1) {
+            ring_put_tokens(rg, L == 0 ? (unsigned long long)']' : 0ULL, 0ULL, L == 0 ? 1 : 0, L);
+            ring_drain(rg, lo, hi, c, L);
+        }
+    }
+    {   // last block with padding
+        __syncwarp();
+        const int rem = rg.wr - rg.rd;   // < 136
+        if (L < KECCAK_RATE_LANES) {
+            unsigned long long w = 0;
+            const int b0 = 8 * L;
+            for (int k = 0; k < 8; ++k)
+                if (b0 + k < rem) w |= (unsigned long long)rg.buf[(rg.rd + b0 + k) % RING_BYTES] << (8 * k);
+            if (rem >= b0 && rem < b0 + 8) w ^= 0x1FULL << (8 * (rem - b0));
+            if (L == 16) w ^= 0x8000000000000000ULL;
+            lo ^= (uint32_t)w;
+            hi ^= (uint32_t)(w >> 32);
+        }
+        keccak_f_warp(lo, hi, c, L);
+    }
+    // ---- squeeze + decode, n_ag bytes per signer
+    int have = 0;      // bytes buffered in xof[] for the current signer
+    int blk_used = KECCAK_RATE;   // bytes of the current squeezed block already handed out (136 = none available)
+    bool first_block = true;
+    const int bfs = (weight + 7) / 8;
+    for (size_t sp = p0; sp < p1; ++sp) {
+        // collect n_ag bytes
+        while (have < (int)n_ag) {
+            if (blk_used == KECCAK_RATE) {
+                if (!first_block) keccak_f_warp(lo, hi, c, L);
+                first_block = false;
+                blk_used = 0;
+            }
+            // the current block lives in registers: lanes 0..16 publish the needed part
+            const int take = min(KECCAK_RATE - blk_used, (int)n_ag - have);
+            if (L < KECCAK_RATE_LANES) {
+                const unsigned long long w = ((unsigned long long)hi << 32) | lo;
+                for (int k = 0; k < 8; ++k) {
+                    const int bpos = 8 * L + k;
+                    if (bpos >= blk_used && bpos < blk_used + take) xof[have + bpos - blk_used] = (uint8_t)(w >> (8 * k));
+                }
+            }
+            have += take;
+            blk_used += take;
+        }
+        __syncwarp();
+        // decode (fusion.py:422-481) with bound = 1: signums, `weight` ignored magnitudes, then the partial Fisher-Yates
+        for (int k = L; k < d; k += 32) {
+            int v = 0;
+            if (k < weight) v = 2 * ((xof[bfs - 1 - k / 8] >> (k % 8)) & 1) - 1;
+            cf[k] = (int8_t)v;
+        }
+        const int n_swaps = weight < d ? d - 1 - weight : 0;
+        const int first = bfs + bpc * weight;
+        // index draws whose bytes exist (possibly truncated); the others see b"" -> 0 (quirk Q4)
+        const int n_full = (int)n_ag > first ? ((int)n_ag - first + bpi - 1) / bpi : 0;
+        const int n_draw = n_full < n_swaps ? n_full : n_swaps;
+        for (int t = L; t < n_draw; t += 32) {
+            const int i = d - 1 - t;
+            const uint32_t m = (uint32_t)(i + 1), mg = c_magic2[m];
+            uint32_t acc = 0;
+            const int s0 = first + t * bpi;
+            const int e0 = min(s0 + bpi, (int)n_ag);
+            for (int q = s0; q < e0; ++q) {
+                const uint32_t v = (acc << 8) | xof[q];
+                acc = v - __umulhi(v, mg) * m;
+            }
+            jdraw[t] = (int)acc;
+        }
+        __syncwarp();
+        if (L == 0) {
+            for (int t = 0; t < n_swaps; ++t) {
+                const int i = d - 1 - t;
+                const int jj = t < n_draw ? jdraw[t] : 0;
+                const int8_t tmp = cf[i]; cf[i] = cf[jj]; cf[jj] = tmp;
+            }
+        }
+        __syncwarp();
+        int32_t* o = coef_out + sp * d;
+        for (int k = L; k < d; k += 32) o[k] = (int32_t)cf[k];
+        __syncwarp();
+        have = 0;
+    }
+}
+
+}  // namespace warpag
+
+int launch_hash_ag_warp(const fz_ctx* ctx, const int32_t* vk_l_s, const int32_t* vk_r_s, const uint8_t* dg_s, const int32_t* c_hat_s,
+                        const unsigned long long* agg_off, size_t n_aggs, int32_t* coef_out, cudaStream_t st) {
+    if (n_aggs == 0) return 0;
+    const int smem = warpag::WARPS * warpag::SMEM_PER_WARP;
+    static bool attr = false;
+    if (!attr) {
+        if (check(cudaFuncSetAttribute(warpag::hash_ag_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "hash_ag_warp smem attr")) return -2;
+        attr = true;
+    }
+    warpag::hash_ag_warp_kernel<<<(int)((n_aggs + warpag::WARPS - 1) / warpag::WARPS), warpag::WARPS * 32, smem, st>>>(
+        vk_l_s, vk_r_s, dg_s, c_hat_s, agg_off, n_aggs, ctx->secpar == 256 ? 1 : 0, ctx->d, ctx->omega_ag, ctx->bytes_coef, ctx->bytes_idx,
+        (uint32_t)ctx->n_ag, coef_out);
+    return check(cudaGetLastError(), "hash_ag_warp launch");
+}
+
+}  // namespace fz

@@ -85,6 +85,10 @@ class Context:
             raise KeyError(name)
         return v
 
+    def set_option(self, name: str, value: int) -> None:
+        self.lib.fz_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
+        self._chk(self.lib.fz_set_option(self._h, name.encode(), value))
+
     # ------------------------------------------------------------------ helpers
     def _stream(self) -> C.c_void_p:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

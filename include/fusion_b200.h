@@ -39,6 +39,8 @@ const char* fz_last_error(void);
 int fz_version(void);
 /* named integer parameter of the level ("d", "ell", "capacity", "n_ch", "n_ag", ...); -1 if unknown */
 long long fz_param(const fz_ctx* ctx, const char* name);
+/* named integer option; "buffered_hash" = 1 selects the HBM-scratch hashing pipeline instead of the streaming one (same results) */
+int fz_set_option(fz_ctx* ctx, const char* name, long long value);
 
 /* algebra/polynomials.py:394-411 transform(coefficient -> NTT) == algebra/ntt.py:216-291
  * cooley_tukey_ntt, on n_polys polynomials; in may equal out.  Input: any int32. */

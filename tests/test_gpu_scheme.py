@@ -286,3 +286,42 @@ def test_aggregate_many_vs_oracle(ctxs, oracle, scheme_golden, secpar):
     parts = ctx.aggregate_sum(sig[sel.cuda().long()], perm0, alpha[:nk], part_counts)
     folded = ctx.fold_partials(parts.reshape(1, 2, ell, d), 2, 1)
     assert torch.equal(folded[0], agg[0])
+
+
+@pytest.mark.parametrize("secpar", [128, 256])
+def test_buffered_and_streaming_hash_agree(ctxs, oracle, secpar):
+    """Two implementations of hash_ch / hash_ag (text staged in HBM vs generated inside the sponge threads) give the
+    same bytes, incl. extreme text lengths and several aggregates of different sizes (also an empty-free ragged mix)."""
+    ctx = ctxs[secpar]
+    d = ctx.d
+    rng = np.random.default_rng(17)
+    counts = [1, 3, 40, 2, 65]
+    n = sum(counts)
+    vl = rng.integers(-H, H + 1, size=(n, d)).astype(np.int32)
+    vr = rng.integers(-H, H + 1, size=(n, d)).astype(np.int32)
+    vl[0] = -H; vr[0] = -H       # longest text
+    vl[1] = 0; vr[1] = 3         # shortest text
+    vl[2] = rng.integers(-1000, 1000, size=d)
+    dg = rng.integers(0, 256, size=(n, 32)).astype(np.uint8)
+    dg[3] = 0
+    dg[4, 1:] = 0
+    out = {}
+    try:
+        for mode, impl in ((1, 0), (0, 2), (0, 3)):   # HBM-staged text / streaming thread per aggregate / streaming warp per aggregate
+            ctx.set_option("buffered_hash", mode)
+            ctx.set_option("hash_ag_impl", impl)
+            c = ctx.hash_ch(dev(vl), dev(vr), dev(dg, np.uint8))
+            a = ctx.hash_ag(dev(vl), dev(vr), dev(dg, np.uint8), c, counts)
+            out[(mode, impl)] = (host(c), host(a))
+    finally:
+        ctx.set_option("buffered_hash", 0)
+        ctx.set_option("hash_ag_impl", 0)
+    ref = out[(1, 0)]
+    for k, v in out.items():
+        assert np.array_equal(v[0], ref[0]) and np.array_equal(v[1], ref[1]), k
+    out = {0: out[(0, 3)], 1: ref}
+    # and against the oracle for the first aggregates (messages are irrelevant here: digests are given)
+    for i in range(4):
+        xof = oracle.hash_vk_and_int_to_bytes(secpar, vl[i], vr[i], bytes(dg[i]), ctx.param("n_ch"))
+        want = oracle.ntt_fwd(secpar, oracle.decode_poly(secpar, xof, secpar, 1, ctx.param("omega_ch")))
+        assert np.array_equal(out[0][0][i], want)
