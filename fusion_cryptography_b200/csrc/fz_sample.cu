@@ -111,14 +111,13 @@ __global__ void seeds_to_keys_kernel(const unsigned long long* __restrict__ seed
 }
 
 // dst[b][r][:] = src[b][:] for r < rows  (quirk Q1: every row of a seeded key matrix is the same polynomial)
-__global__ void __launch_bounds__(256) replicate_rows_kernel(const int4* __restrict__ src, int4* __restrict__ dst, size_t batch, int rows, int d4,
+__global__ void __launch_bounds__(256) replicate_rows_kernel(const int4* __restrict__ src, int4* __restrict__ dst, size_t batch0, int rows, int d4,
                                                                size_t src_batch_stride4) {
-    const size_t per = (size_t)rows * d4, total = batch * per;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = idx / per;
-        const int c = (int)(idx % d4);
-        st_stream(dst + idx, __ldg(src + b * src_batch_stride4 + c));
-    }
+    const int per = rows * d4;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per) return;
+    const size_t b = batch0 + blockIdx.y;
+    st_stream(dst + b * (size_t)per + i, __ldg(src + b * src_batch_stride4 + (i & (d4 - 1))));
 }
 
 int launch_sample(const fz_ctx* ctx, int mode, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, uint32_t bound, int weight,
@@ -138,11 +137,13 @@ int launch_seeds_to_keys(const fz_ctx* ctx, const unsigned long long* seeds, siz
 int launch_replicate_rows(const fz_ctx* ctx, const int32_t* src, int32_t* dst, size_t batch, int rows, size_t src_batch_stride, cudaStream_t st) {
     if (batch == 0) return 0;
     const int d4 = ctx->d / 4;
-    size_t blocks = (batch * rows * d4 + 255) / 256;
-    const size_t cap = (size_t)ctx->sm_count * 16;
-    if (blocks > cap) blocks = cap;
-    replicate_rows_kernel<<<(int)blocks, 256, 0, st>>>((const int4*)src, (int4*)dst, batch, rows, d4, src_batch_stride / 4);
-    return check(cudaGetLastError(), "replicate_rows launch");
+    const unsigned gx = (unsigned)((rows * d4 + 255) / 256);
+    for (size_t b0 = 0; b0 < batch; b0 += 65535) {
+        const size_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
+        replicate_rows_kernel<<<dim3(gx, (unsigned)nb), 256, 0, st>>>((const int4*)src, (int4*)dst, b0, rows, d4, src_batch_stride / 4);
+        if (check(cudaGetLastError(), "replicate_rows launch")) return -2;
+    }
+    return 0;
 }
 
 }  // namespace fz

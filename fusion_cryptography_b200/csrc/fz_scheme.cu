@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) aggregate_kernel(const int4* __restrict__
     const size_t n = hi - lo, per = (n + split - 1) / split;
     size_t p0 = lo + (size_t)s * per, p1 = p0 + per;
     if (p1 > hi) p1 = hi;
-    const int ca = c % d4;
+    const int ca = c & (d4 - 1);  // d4 is a power of two
     long long acc[4] = {0, 0, 0, 0};
     size_t p = p0;
     for (; p + 4 <= p1; p += 4) {

@@ -38,8 +38,9 @@ __global__ void __launch_bounds__(256) matvec_kernel(const int4* __restrict__ A,
                                                        int4* __restrict__ out, size_t batch, int ell, int d4) {
     const size_t total = batch * (size_t)d4;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = idx / d4;
-        const int c = (int)(idx % d4);
+        const int sh = 31 - __clz(d4);  // d4 is a power of two (16 or 64)
+        const size_t b = idx >> sh;
+        const int c = (int)(idx & (size_t)(d4 - 1));
         const int4* sp = s + b * batch_stride4 + c;
         const int4* ap = A + c;
         long long acc[4] = {0, 0, 0, 0};
@@ -61,22 +62,25 @@ __global__ void __launch_bounds__(256) matvec_kernel(const int4* __restrict__ A,
 }
 
 // sig[b][r][k] = cent( sk_l[b][r][k] * c_hat[b][k] + sk_r[b][r][k] )   (fusion.py:557)
+// grid = (ceil(ell*d4 / 256), keys per launch); 32-bit index arithmetic only (a 64-bit divide per int4 would make this
+// write-bound kernel instruction-bound)
 __global__ void __launch_bounds__(256) sign_mac_kernel(const int4* __restrict__ sk_l, const int4* __restrict__ sk_r, size_t row_stride4,
-                                                         size_t batch_stride4, const int4* __restrict__ c_hat, int4* __restrict__ sig, size_t batch, int ell,
-                                                         int d4) {
-    const size_t per_key = (size_t)ell * d4, total = batch * per_key;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = idx / per_key;
-        const int c = (int)(idx % d4);
-        const size_t row = (idx % per_key) / d4;
-        const size_t si = b * batch_stride4 + row * row_stride4 + c;
-        int4 l = ld_stream(sk_l + si), r = ld_stream(sk_r + si), ch = __ldg(c_hat + b * d4 + c), o;
-        o.x = cent_i64((long long)l.x * ch.x + r.x);
-        o.y = cent_i64((long long)l.y * ch.y + r.y);
-        o.z = cent_i64((long long)l.z * ch.z + r.z);
-        o.w = cent_i64((long long)l.w * ch.w + r.w);
-        st_stream(sig + idx, o);
-    }
+                                                         size_t batch_stride4, const int4* __restrict__ c_hat, int4* __restrict__ sig, size_t batch0,
+                                                         int ell, int d4) {
+    const int per_key = ell * d4;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per_key) return;
+    const int sh = 31 - __clz(d4);
+    const int row = i >> sh, c = i & (d4 - 1);
+    const size_t b = batch0 + blockIdx.y;
+    const size_t si = b * batch_stride4 + (size_t)row * row_stride4 + c;
+    const int4 l = ld_stream(sk_l + si), r = ld_stream(sk_r + si), ch = __ldg(c_hat + b * d4 + c);
+    int4 o;
+    o.x = cent_i64((long long)l.x * ch.x + r.x);
+    o.y = cent_i64((long long)l.y * ch.y + r.y);
+    o.z = cent_i64((long long)l.z * ch.z + r.z);
+    o.w = cent_i64((long long)l.w * ch.w + r.w);
+    st_stream(sig + b * (size_t)per_key + i, o);
 }
 
 static int stream_grid(const fz_ctx* ctx, size_t items, int threads) {
@@ -99,9 +103,14 @@ int launch_sign_mac(const fz_ctx* ctx, const int32_t* sk_l, const int32_t* sk_r,
                     int32_t* sig, size_t batch, cudaStream_t st) {
     if (batch == 0) return 0;
     const int d4 = ctx->d / 4;
-    sign_mac_kernel<<<stream_grid(ctx, batch * ctx->ell * d4, 256), 256, 0, st>>>((const int4*)sk_l, (const int4*)sk_r, sk_row_stride / 4, sk_batch_stride / 4,
-                                                                                  (const int4*)c_hat, (int4*)sig, batch, ctx->ell, d4);
-    return check(cudaGetLastError(), "sign_mac launch");
+    const unsigned gx = (unsigned)((ctx->ell * d4 + 255) / 256);
+    for (size_t b0 = 0; b0 < batch; b0 += 65535) {   // gridDim.y limit
+        const size_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
+        sign_mac_kernel<<<dim3(gx, (unsigned)nb), 256, 0, st>>>((const int4*)sk_l, (const int4*)sk_r, sk_row_stride / 4, sk_batch_stride / 4, (const int4*)c_hat,
+                                                                 (int4*)sig, b0, ctx->ell, d4);
+        if (check(cudaGetLastError(), "sign_mac launch")) return -2;
+    }
+    return 0;
 }
 
 }  // namespace fz

@@ -252,11 +252,38 @@ def shake256(self, msgs, out_len: int):
     return out[:, :out_len]
 
 
-def hash_msg(self, msgs) -> torch.Tensor:
-    """fusion.py:405-409 on a list of message byte strings -> [n, 32] digests (int = little endian)."""
+class PackedMessages:
+    """messages resident on the device: one uint8 buffer + int64 offsets[n + 1]; slicing keeps absolute offsets"""
+
+    def __init__(self, buf: torch.Tensor, offs: torch.Tensor):
+        self.buf, self.offs = buf, offs
+
+    def __len__(self):
+        return self.offs.numel() - 1
+
+    def __getitem__(self, sl):
+        if not isinstance(sl, slice):
+            raise TypeError("PackedMessages supports slices only")
+        lo, hi, step = sl.indices(len(self))
+        if step != 1:
+            raise ValueError("PackedMessages slices must be contiguous")
+        return PackedMessages(self.buf, self.offs[lo:hi + 1].contiguous())
+
+
+def pack_messages(self, msgs) -> "PackedMessages":
     buf, offs = self._pack_messages(msgs)
-    out = torch.empty((len(msgs), 32), dtype=torch.uint8, device=self.device)
-    self._chk(self.lib.fz_hash_msg(self._h, _ptr(buf), _ptr(offs), C.c_size_t(len(msgs)), _ptr(out), self._stream()))
+    return PackedMessages(buf, offs)
+
+
+def hash_msg(self, msgs) -> torch.Tensor:
+    """fusion.py:405-409 on a list of message byte strings (or PackedMessages) -> [n, 32] digests (int = little endian)."""
+    if isinstance(msgs, PackedMessages):
+        buf, offs, n = msgs.buf, msgs.offs, len(msgs)
+    else:
+        buf, offs = self._pack_messages(msgs)
+        n = len(msgs)
+    out = torch.empty((n, 32), dtype=torch.uint8, device=self.device)
+    self._chk(self.lib.fz_hash_msg(self._h, _ptr(buf), _ptr(offs), C.c_size_t(n), _ptr(out), self._stream()))
     return out
 
 
@@ -437,6 +464,6 @@ def sign_mac_rows(self, sk_hat, c_hat, out=None) -> torch.Tensor:
     return out
 
 
-for _f in (_u8, _pack_messages, _ws, sha3_256, shake256, hash_msg, format_text, decode_poly, hash_ch, _agg_off, hash_ag, sort_keys, gather_sorted,
+for _f in (_u8, _pack_messages, pack_messages, _ws, sha3_256, shake256, hash_msg, format_text, decode_poly, hash_ch, _agg_off, hash_ag, sort_keys, gather_sorted,
            aggregate_sum, fold_partials, verify_check, _seed_keys, sample_coef, sample_ntt, keygen, sign_mac_rows):
     setattr(Context, _f.__name__, _f)
