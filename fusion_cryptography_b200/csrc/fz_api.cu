@@ -101,7 +101,7 @@ int fz_init(int device, int secpar, fz_ctx** out) {
     cudaDeviceProp prop;
     if (check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { delete c; return -2; }
     c->sm_count = prop.multiProcessorCount;
-    if (ntt_init_tables(c) || hash_init_tables(c) || hashstream_init_tables(c)) { delete c; return -2; }
+    if (ntt_init_tables(c) || hash_init_tables(c) || hashstream_init_tables(c) || sample_init_tables(c)) { delete c; return -2; }
     *out = c;
     return 0;
 }

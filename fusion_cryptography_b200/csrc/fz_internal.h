@@ -67,6 +67,7 @@ int launch_hash_ag_warp(const fz_ctx* ctx, const int32_t* vk_l_s, const int32_t*
                         const unsigned long long* agg_off, size_t n_aggs, int32_t* coef_out, cudaStream_t st);
 
 // fz_sample.cu
+int sample_init_tables(fz_ctx* ctx);
 int launch_sample(const fz_ctx* ctx, int mode, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, uint32_t bound, int weight,
                   int32_t* out, cudaStream_t st);
 int launch_seeds_to_keys(const fz_ctx* ctx, const unsigned long long* seeds, size_t n, uint32_t* keys, int32_t* klen, cudaStream_t st);

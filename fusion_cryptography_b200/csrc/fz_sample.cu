@@ -4,55 +4,109 @@
 // of abs(seed) (Modules/_randommodule.c), randrange(n) = top bit_length(n) bits of a 32-bit
 // output, retried while >= n (Lib/random.py _randbelow_with_getrandbits).
 //
-// One thread per polynomial; the 624-word state lives in local memory, which the hardware
-// interleaves across the threads of a warp, so every state access of the (lock-step) seeding
-// and twist loops is a coalesced 128-byte transaction.
+// One thread per polynomial.  The 624-word state of each generator lives in SHARED memory, word-interleaved
+// across the threads of the CTA (word k of thread t at k * S + t: every lock-step access is conflict-free), 90
+// generators per CTA (90 * 632 words = 222 KiB of the 227 KiB an sm_100a CTA may own).  Seeding is two serial
+// recurrences of 624 + 623 steps per generator (init_by_array); the first, seed-independent pass of CPython's
+// init_genrand(19650218) is a constant table.  Outputs are produced on demand, in place, eight at a time (the
+// regeneration is sequential in k anyway), so no word that is never drawn is ever twisted, and the rejection loops of
+// randrange run as one convergent draw loop over a two-state machine.
 #include "fz_common.cuh"
 #include "fz_internal.h"
 
 namespace fz {
 
+constexpr int MT_N = 624, MT_M = 397;
+constexpr int SMP_STREAMS = 90;             // generators per CTA
+constexpr int SMP_THREADS = 96;
+constexpr int SMP_WORDS = MT_N + 8;         // state + the (key[j] + j) table of init_by_array
+constexpr int SMP_SMEM = SMP_STREAMS * SMP_WORDS * 4;
+
+__constant__ uint32_t c_mt0[MT_N];          // init_genrand(19650218)
+
 struct Mt {
-    uint32_t mt[624];
-    int idx;
+    uint32_t* m;   // word k of this generator is m[k * SMP_STREAMS]
+    int idx;       // next state word to regenerate / output
 };
+#define MTW(s, k) (s).m[(k) * SMP_STREAMS]
 
+__device__ __forceinline__ uint32_t mt_mix(uint32_t prev) { return prev ^ (prev >> 30); }
+
+// Modules/_randommodule.c init_by_array for klen <= 8 limbs (the key loop runs max(624, klen) = 624 times)
 __device__ __forceinline__ void mt_seed(Mt& s, const uint32_t* key, int klen) {
-    s.mt[0] = 19650218u;
-    for (int i = 1; i < 624; ++i) s.mt[i] = 1812433253u * (s.mt[i - 1] ^ (s.mt[i - 1] >> 30)) + (uint32_t)i;
-    int i = 1, j = 0;
-    for (int k = klen > 624 ? klen : 624; k; --k) {
-        s.mt[i] = (s.mt[i] ^ ((s.mt[i - 1] ^ (s.mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
-        ++i; ++j;
-        if (i >= 624) { s.mt[0] = s.mt[623]; i = 1; }
-        if (j >= klen) j = 0;
+    for (int j = 0; j < 8; ++j) MTW(s, MT_N + j) = key[j] + (uint32_t)j;
+    uint32_t prev = 19650218u;
+    int j = 0;
+#pragma unroll 8
+    for (int i = 1; i < MT_N; ++i) {
+        const uint32_t v = (c_mt0[i] ^ (mt_mix(prev) * 1664525u)) + MTW(s, MT_N + j);
+        MTW(s, i) = v;
+        prev = v;
+        if (++j >= klen) j = 0;
     }
-    for (int k = 623; k; --k) {
-        s.mt[i] = (s.mt[i] ^ ((s.mt[i - 1] ^ (s.mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
-        ++i;
-        if (i >= 624) { s.mt[0] = s.mt[623]; i = 1; }
+    {   // 624th step: i wrapped to 1 with mt[0] = mt[623]
+        const uint32_t v = (MTW(s, 1) ^ (mt_mix(prev) * 1664525u)) + MTW(s, MT_N + j);
+        MTW(s, 1) = v;
+        prev = v;
     }
-    s.mt[0] = 0x80000000u;
-    s.idx = 624;
+    for (int i0 = 2; i0 < MT_N; i0 += 8) {   // 622 steps, i = 2..623, eight state words prefetched per trip
+        uint32_t cur[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cur[e] = i0 + e < MT_N ? MTW(s, i0 + e) : 0u;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (i0 + e < MT_N) {
+                const uint32_t v = (cur[e] ^ (mt_mix(prev) * 1566083941u)) - (uint32_t)(i0 + e);
+                MTW(s, i0 + e) = v;
+                prev = v;
+            }
+    }
+    MTW(s, 1) = (MTW(s, 1) ^ (mt_mix(prev) * 1566083941u)) - 1u;   // 623rd step: i wrapped to 1
+    MTW(s, 0) = 0x80000000u;
+    s.idx = 0;   // CPython leaves index = 624: the first draw regenerates; here regeneration is on demand from word 0
 }
 
-__device__ __forceinline__ void mt_twist(Mt& s) {
-    for (int kk = 0; kk < 624; ++kk) {
-        const uint32_t y = (s.mt[kk] & 0x80000000u) | (s.mt[kk == 623 ? 0 : kk + 1] & 0x7fffffffu);
-        const int k2 = kk + 397 < 624 ? kk + 397 : kk + 397 - 624;
-        s.mt[kk] = s.mt[k2] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-    }
-    s.idx = 0;
-}
-
-__device__ __forceinline__ uint32_t mt_next(Mt& s) {
-    if (s.idx >= 624) mt_twist(s);
-    uint32_t y = s.mt[s.idx++];
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     y ^= y >> 11;
     y ^= (y << 7) & 0x9d2c5680u;
     y ^= (y << 15) & 0xefc60000u;
     y ^= y >> 18;
     return y;
+}
+
+__device__ __forceinline__ uint32_t mt_regen(uint32_t a, uint32_t b, uint32_t far) {
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+// one output (scalar path: public matrix, sparse branch)
+__device__ __forceinline__ uint32_t mt_next(Mt& s) {
+    const int k = s.idx, k1 = k + 1 == MT_N ? 0 : k + 1, km = k + MT_M < MT_N ? k + MT_M : k + MT_M - MT_N;
+    const uint32_t v = mt_regen(MTW(s, k), MTW(s, k1), MTW(s, km));
+    MTW(s, k) = v;
+    s.idx = k1;
+    return mt_temper(v);
+}
+
+// eight outputs; s.idx is a multiple of 8 (624 = 78 * 8)
+__device__ __forceinline__ void mt_next8(Mt& s, uint32_t (&y)[8]) {
+    const int k = s.idx;
+    uint32_t a[9], f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = MTW(s, k + e);
+    a[8] = MTW(s, k + 8 == MT_N ? 0 : k + 8);   // word 0 was regenerated 77 blocks ago, as in the sequential twist
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int km = k + e + MT_M < MT_N ? k + e + MT_M : k + e + MT_M - MT_N;   // old word above k, new word below
+        f[e] = MTW(s, km);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const uint32_t v = mt_regen(a[e], a[e + 1], f[e]);
+        MTW(s, k + e) = v;
+        y[e] = mt_temper(v);
+    }
+    s.idx = k + 8 == MT_N ? 0 : k + 8;
 }
 
 __device__ __forceinline__ uint32_t mt_randbelow(Mt& s, uint32_t n) {
@@ -66,11 +120,13 @@ __device__ __forceinline__ uint32_t mt_randbelow(Mt& s, uint32_t n) {
 //         then the Fisher-Yates branch when weight < d (polynomials.py:449-459)
 // mode 1: public-matrix values randrange(q) - q//2 (polynomials.py:480)
 // keys: [n][key_stride] 32-bit limbs, klen[n] limbs used (>= 1)
-__global__ void __launch_bounds__(64) sample_kernel(int mode, const uint32_t* __restrict__ keys, int key_stride, const int32_t* __restrict__ klen, size_t n,
-                                                     int d, uint32_t bound, int weight, int32_t* __restrict__ out) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void __launch_bounds__(SMP_THREADS) sample_kernel(int mode, const uint32_t* __restrict__ keys, int key_stride, const int32_t* __restrict__ klen,
+                                                              size_t n, int d, uint32_t bound, int weight, int32_t* __restrict__ out) {
+    extern __shared__ __align__(16) uint32_t smp_sm[];
+    const size_t i = (size_t)blockIdx.x * SMP_STREAMS + threadIdx.x;
+    if (threadIdx.x >= SMP_STREAMS || i >= n) return;   // no block-wide barrier below
     Mt s;
+    s.m = smp_sm + threadIdx.x;
     uint32_t key[8];
     int kl = klen[i];
     if (kl > 8) kl = 8;
@@ -81,18 +137,48 @@ __global__ void __launch_bounds__(64) sample_kernel(int mode, const uint32_t* __
         for (int k = 0; k < d; ++k) o[k] = (int32_t)((long long)mt_randbelow(s, Q) - (long long)HALF);
         return;
     }
-    const int ncoef = weight < d ? (weight < 0 ? 0 : weight) : d;
+    if (weight >= d) {
+        // dense branch (omega_sk = d, the scheme's only use): a convergent draw loop.  randrange(bound) keeps the top
+        // bit_length(bound) bits of an output and retries while >= bound; randrange(2) keeps the top 2 bits.
+        const int shb = __clz(bound);   // 32 - bit_length(bound)
+        int k = 0, have_mag = 0;
+        int32_t mag = 0;
+        int32_t c4[4];
+        while (k < d) {
+            uint32_t y[8];
+            mt_next8(s, y);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (k < d) {
+                    if (!have_mag) {
+                        const uint32_t r = y[e] >> shb;
+                        if (r < bound) { mag = 1 + (int32_t)r; have_mag = 1; }
+                    } else {
+                        const uint32_t r = y[e] >> 30;
+                        if (r < 2u) {
+                            const int32_t c = r ? -mag : mag;
+                            // four coefficients per 16-byte store; the slot index is k & 3
+                            if ((k & 3) == 0) c4[0] = c; else if ((k & 3) == 1) c4[1] = c; else if ((k & 3) == 2) c4[2] = c; else c4[3] = c;
+                            if ((k & 3) == 3) *reinterpret_cast<int4*>(o + k - 3) = make_int4(c4[0], c4[1], c4[2], c4[3]);
+                            ++k;
+                            have_mag = 0;
+                        }
+                    }
+                }
+            }
+        }
+        return;
+    }
+    const int ncoef = weight < 0 ? 0 : weight;
     for (int k = 0; k < ncoef; ++k) {
         const int32_t mag = 1 + (int32_t)mt_randbelow(s, bound);
         const int32_t sg = 1 - 2 * (int32_t)mt_randbelow(s, 2u);
         o[k] = mag * sg;
     }
     for (int k = ncoef; k < d; ++k) o[k] = 0;
-    if (ncoef < d) {
-        for (int k = d - 1; k > 0; --k) {
-            const int j = (int)mt_randbelow(s, (uint32_t)(k + 1));
-            const int32_t t = o[k]; o[k] = o[j]; o[j] = t;
-        }
+    for (int k = d - 1; k > 0; --k) {
+        const int j = (int)mt_randbelow(s, (uint32_t)(k + 1));
+        const int32_t t = o[k]; o[k] = o[j]; o[j] = t;
     }
 }
 
@@ -120,10 +206,19 @@ __global__ void __launch_bounds__(256) replicate_rows_kernel(const int4* __restr
     st_stream(dst + b * (size_t)per + i, __ldg(src + b * src_batch_stride4 + (i & (d4 - 1))));
 }
 
+int sample_init_tables(fz_ctx* ctx) {
+    uint32_t mt0[MT_N];
+    mt0[0] = 19650218u;
+    for (int i = 1; i < MT_N; ++i) mt0[i] = 1812433253u * (mt0[i - 1] ^ (mt0[i - 1] >> 30)) + (uint32_t)i;   // init_genrand
+    if (check(cudaMemcpyToSymbol(c_mt0, mt0, sizeof(mt0)), "MT19937 seed table upload")) return -2;
+    (void)ctx;
+    return check(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMP_SMEM), "sample_kernel smem attr");
+}
+
 int launch_sample(const fz_ctx* ctx, int mode, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, uint32_t bound, int weight,
                   int32_t* out, cudaStream_t st) {
     if (n == 0) return 0;
-    sample_kernel<<<(int)((n + 63) / 64), 64, 0, st>>>(mode, keys, key_stride, klen, n, ctx->d, bound, weight, out);
+    sample_kernel<<<(unsigned)((n + SMP_STREAMS - 1) / SMP_STREAMS), SMP_THREADS, SMP_SMEM, st>>>(mode, keys, key_stride, klen, n, ctx->d, bound, weight, out);
     return check(cudaGetLastError(), "sample launch");
 }
 

@@ -1,0 +1,263 @@
+// keccak_lab.cu -- development microbenchmark: cycles per Keccak-f round of one SERIAL sponge chain for several
+// ways of spreading the 25 lanes over a warp (the aggregation hash of fusion.py:573-591 is one serial SHAKE256 per
+// aggregate, so chain latency -- not ALU throughput -- bounds hash_ag at capacity), and the ALU-bound
+// thread-per-sponge rate used as the roofline of hash_ch.
+//
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/keccak_lab tools/keccak_lab.cu
+//   tools/keccak_lab [perms]
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "../fusion_cryptography_b200/csrc/fz_keccak.cuh"
+
+using namespace fz;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+__constant__ int c_rot[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+
+struct Lane {
+    int src5, src10, src15, src20, xm1, xp1, pi0, pi1, pi2, rot, x;
+    unsigned colmask;
+};
+__device__ __forceinline__ Lane lane_init(int L) {
+    Lane c;
+    const int l = L < 25 ? L : 0;
+    const int x = l % 5, y = l / 5;
+    c.x = x;
+    c.src5 = (l + 5) % 25; c.src10 = (l + 10) % 25; c.src15 = (l + 15) % 25; c.src20 = (l + 20) % 25;
+    c.xm1 = (x + 4) % 5 + 5 * y; c.xp1 = (x + 1) % 5 + 5 * y;
+    const int x1 = (x + 1) % 5, x2 = (x + 2) % 5;
+    c.pi0 = ((x + 3 * y) % 5) + 5 * x;
+    c.pi1 = ((x1 + 3 * y) % 5) + 5 * x1;
+    c.pi2 = ((x2 + 3 * y) % 5) + 5 * x2;
+    c.rot = c_rot[l];
+    c.colmask = L < 25 ? (0x108421u << x) : 0xFE000000u;
+    return c;
+}
+#define SH(v, s) __shfl_sync(0xffffffffu, (v), (s))
+
+__device__ __forceinline__ void rho(uint32_t& lo, uint32_t& hi, int rot) {
+    const bool sw = rot >= 32;
+    const uint32_t a = sw ? hi : lo, b = sw ? lo : hi;
+    const int s = rot & 31;
+    lo = __funnelshift_l(b, a, s);
+    hi = __funnelshift_l(a, b, s);
+}
+__device__ __forceinline__ void iota(uint32_t& lo, uint32_t& hi, int r, int L) {
+    if (L == 0) {
+        const unsigned long long rc = c_keccak_rc[r];
+        lo ^= (uint32_t)rc;
+        hi ^= (uint32_t)(rc >> 32);
+    }
+}
+
+// V0: 18 shuffles per round (the shipped hash_ag_warp permutation)
+__device__ __forceinline__ void f_v0(uint32_t& lo, uint32_t& hi, const Lane& c, int L, uint2*, uint2*) {
+#pragma unroll 1
+    for (int r = 0; r < 24; ++r) {
+        uint32_t cl = lo ^ SH(lo, c.src5) ^ SH(lo, c.src10) ^ SH(lo, c.src15) ^ SH(lo, c.src20);
+        uint32_t ch = hi ^ SH(hi, c.src5) ^ SH(hi, c.src10) ^ SH(hi, c.src15) ^ SH(hi, c.src20);
+        const uint32_t ml = SH(cl, c.xm1), mh = SH(ch, c.xm1), pl = SH(cl, c.xp1), ph = SH(ch, c.xp1);
+        lo ^= ml ^ __funnelshift_l(ph, pl, 1);
+        hi ^= mh ^ __funnelshift_l(pl, ph, 1);
+        rho(lo, hi, c.rot);
+        const uint32_t b0l = SH(lo, c.pi0), b0h = SH(hi, c.pi0), b1l = SH(lo, c.pi1), b1h = SH(hi, c.pi1), b2l = SH(lo, c.pi2), b2h = SH(hi, c.pi2);
+        lo = b0l ^ (~b1l & b2l);
+        hi = b0h ^ (~b1h & b2h);
+        iota(lo, hi, r, L);
+    }
+}
+
+// V1: column parity with redux.sync over per-column member masks: 2 REDUX + 10 SHFL
+__device__ __forceinline__ void f_v1(uint32_t& lo, uint32_t& hi, const Lane& c, int L, uint2*, uint2*) {
+#pragma unroll 1
+    for (int r = 0; r < 24; ++r) {
+        const uint32_t cl = __reduce_xor_sync(c.colmask, lo), ch = __reduce_xor_sync(c.colmask, hi);
+        const uint32_t ml = SH(cl, c.xm1), mh = SH(ch, c.xm1), pl = SH(cl, c.xp1), ph = SH(ch, c.xp1);
+        lo ^= ml ^ __funnelshift_l(ph, pl, 1);
+        hi ^= mh ^ __funnelshift_l(pl, ph, 1);
+        rho(lo, hi, c.rot);
+        const uint32_t b0l = SH(lo, c.pi0), b0h = SH(hi, c.pi0), b1l = SH(lo, c.pi1), b1h = SH(hi, c.pi1), b2l = SH(lo, c.pi2), b2h = SH(hi, c.pi2);
+        lo = b0l ^ (~b1l & b2l);
+        hi = b0h ^ (~b1h & b2h);
+        iota(lo, hi, r, L);
+    }
+}
+
+// V2: shared memory, three stages (own column's 4 other rows -> C; C of the two neighbour columns; pi/chi gather)
+__device__ __forceinline__ void f_v2(uint32_t& lo, uint32_t& hi, const Lane& c, int L, uint2* bufA, uint2* bufB) {
+    uint2* bufC = bufB + 32;
+#pragma unroll 1
+    for (int r = 0; r < 24; ++r) {
+        bufA[L] = make_uint2(lo, hi);
+        __syncwarp();
+        const uint2 a1 = bufA[c.src5], a2 = bufA[c.src10], a3 = bufA[c.src15], a4 = bufA[c.src20];
+        const uint32_t cl = lo ^ a1.x ^ a2.x ^ a3.x ^ a4.x, ch = hi ^ a1.y ^ a2.y ^ a3.y ^ a4.y;
+        bufC[L] = make_uint2(cl, ch);
+        __syncwarp();
+        const uint2 m = bufC[c.xm1], p = bufC[c.xp1];
+        lo ^= m.x ^ __funnelshift_l(p.y, p.x, 1);
+        hi ^= m.y ^ __funnelshift_l(p.x, p.y, 1);
+        rho(lo, hi, c.rot);
+        bufB[L] = make_uint2(lo, hi);
+        __syncwarp();
+        const uint2 b0 = bufB[c.pi0], b1 = bufB[c.pi1], b2 = bufB[c.pi2];
+        lo = b0.x ^ (~b1.x & b2.x);
+        hi = b0.y ^ (~b1.y & b2.y);
+        iota(lo, hi, r, L);
+    }
+}
+
+// V3: shared memory, two stages: theta reads the ten lanes of columns x-1 and x+1 directly
+__device__ __forceinline__ void f_v3(uint32_t& lo, uint32_t& hi, const Lane& c, int L, uint2* bufA, uint2* bufB) {
+    const int cm = (c.x + 4) % 5, cp = (c.x + 1) % 5;
+#pragma unroll 1
+    for (int r = 0; r < 24; ++r) {
+        bufA[L] = make_uint2(lo, hi);
+        __syncwarp();
+        uint2 m = bufA[cm], p = bufA[cp];
+#pragma unroll
+        for (int y = 1; y < 5; ++y) {
+            const uint2 mm = bufA[cm + 5 * y], pp = bufA[cp + 5 * y];
+            m.x ^= mm.x; m.y ^= mm.y; p.x ^= pp.x; p.y ^= pp.y;
+        }
+        lo ^= m.x ^ __funnelshift_l(p.y, p.x, 1);
+        hi ^= m.y ^ __funnelshift_l(p.x, p.y, 1);
+        rho(lo, hi, c.rot);
+        bufB[L] = make_uint2(lo, hi);
+        __syncwarp();
+        const uint2 b0 = bufB[c.pi0], b1 = bufB[c.pi1], b2 = bufB[c.pi2];
+        lo = b0.x ^ (~b1.x & b2.x);
+        hi = b0.y ^ (~b1.y & b2.y);
+        iota(lo, hi, r, L);
+    }
+}
+
+// V5: REDUX parity, then shared memory for the two remaining exchanges
+__device__ __forceinline__ void f_v5(uint32_t& lo, uint32_t& hi, const Lane& c, int L, uint2* bufA, uint2* bufB) {
+#pragma unroll 1
+    for (int r = 0; r < 24; ++r) {
+        const uint32_t cl = __reduce_xor_sync(c.colmask, lo), ch = __reduce_xor_sync(c.colmask, hi);
+        bufA[L] = make_uint2(cl, ch);
+        __syncwarp();
+        const uint2 m = bufA[c.xm1], p = bufA[c.xp1];
+        lo ^= m.x ^ __funnelshift_l(p.y, p.x, 1);
+        hi ^= m.y ^ __funnelshift_l(p.x, p.y, 1);
+        rho(lo, hi, c.rot);
+        bufB[L] = make_uint2(lo, hi);
+        __syncwarp();
+        const uint2 b0 = bufB[c.pi0], b1 = bufB[c.pi1], b2 = bufB[c.pi2];
+        lo = b0.x ^ (~b1.x & b2.x);
+        hi = b0.y ^ (~b1.y & b2.y);
+        iota(lo, hi, r, L);
+    }
+}
+
+template <int V>
+__global__ void coop_kernel(int perms, unsigned long long* state_out, long long* cycles_out) {
+    extern __shared__ uint2 sm[];
+    const int L = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint2* bufA = sm + w * 96;
+    uint2* bufB = bufA + 32;
+    const Lane c = lane_init(L);
+    const int chain = blockIdx.x * (blockDim.x >> 5) + w;
+    unsigned long long v = L < 25 ? (unsigned long long)(L + 1) * 0x9E3779B97F4A7C15ULL + (unsigned long long)chain : 0ULL;
+    uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    const long long t0 = clock64();
+    for (int p = 0; p < perms; ++p) {
+        if (V == 0) f_v0(lo, hi, c, L, bufA, bufB);
+        if (V == 1) f_v1(lo, hi, c, L, bufA, bufB);
+        if (V == 2) f_v2(lo, hi, c, L, bufA, bufB);
+        if (V == 3) f_v3(lo, hi, c, L, bufA, bufB);
+        if (V == 5) f_v5(lo, hi, c, L, bufA, bufB);
+    }
+    const long long t1 = clock64();
+    if (chain == 0 && L < 25) state_out[L] = ((unsigned long long)hi << 32) | lo;
+    if (L == 0) cycles_out[chain] = t1 - t0;
+}
+
+// V4: thread per sponge
+__global__ void thread_kernel(int perms, unsigned long long* state_out, long long* cycles_out) {
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long a[25];
+#pragma unroll
+    for (int k = 0; k < 25; ++k) a[k] = (unsigned long long)(k + 1) * 0x9E3779B97F4A7C15ULL + (unsigned long long)chain;
+    const long long t0 = clock64();
+    for (int p = 0; p < perms; ++p) keccak_f(a);
+    const long long t1 = clock64();
+    if (chain == 0)
+        for (int k = 0; k < 25; ++k) state_out[k] = a[k];
+    if ((threadIdx.x & 31) == 0) cycles_out[chain >> 5] = t1 - t0;
+}
+
+int main(int argc, char** argv) {
+    const int perms = argc > 1 ? atoi(argv[1]) : 2000;
+    cudaDeviceProp pr;
+    CK(cudaGetDeviceProperties(&pr, 0));
+    const int sms = pr.multiProcessorCount;
+    printf("device %s, %d SMs, %d perms per chain\n", pr.name, sms, perms);
+    unsigned long long* d_state; long long* d_cyc;
+    CK(cudaMalloc(&d_state, 25 * 8));
+    CK(cudaMalloc(&d_cyc, 1 << 20));
+    std::vector<unsigned long long> ref(25), got(25);
+    std::vector<long long> cyc(1 << 17);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    // reference state from the thread kernel
+    thread_kernel<<<1, 32>>>(perms, d_state, d_cyc);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(ref.data(), d_state, 200, cudaMemcpyDeviceToHost));
+    auto report = [&](const char* name, int warps_per_sm, int n_chains_warps, float ms, int sponges_per_warp) {
+        CK(cudaMemcpy(cyc.data(), d_cyc, n_chains_warps * 8, cudaMemcpyDeviceToHost));
+        long long mx = 0; double avg = 0;
+        for (int i = 0; i < n_chains_warps; ++i) { mx = cyc[i] > mx ? cyc[i] : mx; avg += (double)cyc[i]; }
+        avg /= n_chains_warps;
+        CK(cudaMemcpy(got.data(), d_state, 200, cudaMemcpyDeviceToHost));
+        bool ok = true;
+        for (int k = 0; k < 25; ++k) ok = ok && got[k] == ref[k];
+        const double total_perms = (double)n_chains_warps * sponges_per_warp * perms;
+        printf("%-28s warps/SM %2d  cycles/round avg %7.1f max %7.1f  time %8.3f ms  %7.3f Gperm/s  %s\n", name, warps_per_sm, avg / perms / 24.0,
+               (double)mx / perms / 24.0, ms, total_perms / (ms * 1e-3) / 1e9, ok ? "ok" : "MISMATCH");
+    };
+    const int wps[] = {1, 2, 4, 8, 12, 16};
+#define RUN_COOP(V, NAME)                                                                     \
+    for (int wi = 0; wi < 6; ++wi) {                                                          \
+        const int w = wps[wi];                                                                \
+        const int bw = w < 4 ? w : 4, blocks = sms * (w / bw);                                \
+        coop_kernel<V><<<blocks, bw * 32, bw * 96 * 8>>>(10, d_state, d_cyc);                  \
+        CK(cudaEventRecord(e0));                                                              \
+        coop_kernel<V><<<blocks, bw * 32, bw * 96 * 8>>>(perms, d_state, d_cyc);               \
+        CK(cudaEventRecord(e1));                                                              \
+        CK(cudaDeviceSynchronize());                                                          \
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));                                      \
+        report(NAME, w, blocks * bw, ms, 1);                                                  \
+    }
+    RUN_COOP(0, "V0 shfl x18")
+    RUN_COOP(1, "V1 redux x2 + shfl x10")
+    RUN_COOP(2, "V2 smem 3-stage")
+    RUN_COOP(3, "V3 smem 2-stage")
+    RUN_COOP(5, "V5 redux + smem")
+    const int tw[] = {4, 8, 16, 24, 32};
+    for (int wi = 0; wi < 5; ++wi) {
+        const int w = tw[wi];
+        const int bw = 4, blocks = sms * (w / bw);
+        thread_kernel<<<blocks, bw * 32>>>(10, d_state, d_cyc);
+        CK(cudaEventRecord(e0));
+        thread_kernel<<<blocks, bw * 32>>>(perms / 4, d_state, d_cyc);
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        // the reference state was taken at `perms`; recompute it for perms / 4 is not needed: only report the rate
+        CK(cudaMemcpy(cyc.data(), d_cyc, blocks * bw * 8, cudaMemcpyDeviceToHost));
+        double avg = 0;
+        for (int i = 0; i < blocks * bw; ++i) avg += (double)cyc[i];
+        avg /= blocks * bw;
+        printf("%-28s warps/SM %2d  cycles/round avg %7.1f  time %8.3f ms  %7.3f Gperm/s\n", "V4 thread per sponge", w, avg / (perms / 4) / 24.0, ms,
+               (double)blocks * bw * 32 * (perms / 4) / (ms * 1e-3) / 1e9);
+    }
+    return 0;
+}
