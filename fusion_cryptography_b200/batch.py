@@ -77,56 +77,104 @@ class Engine:
         return vk_l, vk_r, (sigs if keep_sigs else None)
 
     # ------------------------------------------------------------------ aggregate / verify
+    # The aggregation hash is one serial sponge per aggregate (fusion.py:591), so a batch is hashed WINDOW BY WINDOW over
+    # the sorted signer positions: window w holds positions [w*P, (w+1)*P) of every aggregate.  All chains advance
+    # together (latency-bound chains need every aggregate in flight), memory is O(n_aggs * P) instead of O(positions),
+    # and the per-signer work of window w+1 (gather, hash_ch) runs on a second stream while window w is absorbed.
     def _sorted_hash(self, vk_l, vk_r, digests_pos, counts, sel):
-        """sort -> gather -> hash_ch -> hash_ag for a chunk of aggregates; position p uses key row sel[p] (identity if None)."""
+        """One-shot sort -> gather -> hash_ch -> hash_ag with every position resident (small batches, kernel timing)."""
         perm = self.ctx.sort_keys(vk_l, vk_r, counts, sel=sel)
         vl_s, vr_s, dg_s = self.ctx.gather_sorted(vk_l, vk_r, digests_pos, perm, sel=sel)
         c_s = self.ctx.hash_ch(vl_s, vr_s, dg_s)
         alpha = self.ctx.hash_ag(vl_s, vr_s, dg_s, c_s, counts)
         return perm, vl_s, vr_s, c_s, alpha
 
-    @staticmethod
-    def _chunks(counts: Sequence[int], max_positions: int):
-        lo, acc, start = 0, 0, 0
-        for j, c in enumerate(counts):
-            if j > lo and acc + c > max_positions:
-                yield lo, j, start, start + acc
-                lo, start, acc = j, start + acc, 0
-            acc += c
-        if len(counts) > lo:
-            yield lo, len(counts), start, start + acc
+    def _hash_windows(self, vk_l, vk_r, dg_all, counts, sel, window_positions: int, keep_c: bool):
+        import numpy as np
+
+        ctx, dev = self.ctx, self.ctx.device
+        n_aggs = len(counts)
+        cnp = np.asarray(counts, dtype=np.int64)
+        total, max_count = int(cnp.sum()), int(cnp.max()) if n_aggs else 0
+        off_np = np.zeros(n_aggs + 1, dtype=np.int64)
+        np.cumsum(cnp, out=off_np[1:])
+        agg_off = torch.from_numpy(off_np).to(dev)
+        sel_d = sel.to(dev, dtype=torch.int32).contiguous() if sel is not None else torch.arange(total, dtype=torch.int32, device=dev)
+        perm = ctx.sort_keys(vk_l, vk_r, [int(c) for c in counts], sel=sel_d)
+        P = max(1, min(max_count, window_positions // max(n_aggs, 1))) if max_count else 1
+        state = ctx.hash_ag_begin(agg_off, n_aggs)
+        main = torch.cuda.current_stream(dev)
+        prep = torch.cuda.Stream(device=dev)
+        prep.wait_stream(main)
+        wins = []
+        for w in range(0, max(max_count, 1), P):
+            cnt = np.clip(cnp - w, 0, P)
+            n_win = int(cnt.sum())
+            woff_np = np.zeros(n_aggs + 1, dtype=np.int64)
+            np.cumsum(cnt, out=woff_np[1:])
+            if len(wins) >= 2:
+                wins[-2]["absorbed"].synchronize()   # the host stays at most two windows ahead of the chain
+            with torch.cuda.stream(prep):
+                win_off = torch.from_numpy(woff_np).to(dev, non_blocking=True)
+                cnt_d = torch.from_numpy(cnt).to(dev, non_blocking=True)
+                base = agg_off[:-1] + w - win_off[:-1]
+                idx = torch.repeat_interleave(base, cnt_d, output_size=n_win) + torch.arange(n_win, dtype=torch.int64, device=dev)
+                pos = perm.index_select(0, idx)
+                vl_w, vr_w, dg_w = ctx.gather_sorted(vk_l, vk_r, dg_all, pos, sel=sel_d)
+                c_w = ctx.hash_ch(vl_w, vr_w, dg_w)
+                ready = torch.cuda.Event()
+                ready.record(prep)
+            for t in (win_off, pos, vl_w, vr_w, dg_w, c_w):
+                t.record_stream(main)                # allocated on the side stream, consumed by the chain on the main stream
+            main.wait_event(ready)
+            ctx.hash_ag_absorb(state, vl_w, vr_w, dg_w, c_w, win_off, n_aggs)
+            absorbed = torch.cuda.Event()
+            absorbed.record(main)
+            wins.append({"win_off": win_off, "n": n_win, "pos": pos, "max": int(cnt.max()), "absorbed": absorbed, "c": c_w if keep_c else None})
+        return state, wins, sel_d, prep
 
     def aggregate(self, vk_l, vk_r, msgs: Optional[Sequence[bytes]], sigs, counts: Sequence[int], sel: Optional[torch.Tensor] = None,
-                  sig_sel: Optional[torch.Tensor] = None, max_positions: int = 1 << 22, digests: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  sig_sel: Optional[torch.Tensor] = None, max_positions: int = 1 << 19, digests: Optional[torch.Tensor] = None) -> torch.Tensor:
         """counts[j] signers per aggregate; position p (0 <= p < sum(counts)) signs msgs[p] with key row sel[p] and
         signature row sig_sel[p] (both default to p).  `digests` ([positions, 32] prehashes from hash_msg) may replace msgs.
-        Returns [n_aggs, ell, d]."""
+        `max_positions` bounds the signer positions resident per window.  Returns [n_aggs, ell, d]."""
         total = int(sum(counts))
         if any(c <= 0 for c in counts):
             raise IndexError("list index out of range")  # the reference indexes sorted_signatures[0] (fusion.py:670)
         if (digests.shape[0] if digests is not None else len(msgs)) != total:
             raise ValueError("one message per position is required")
-        dev = self.ctx.device
-        out = torch.empty((len(counts), self.ell, self.d), dtype=torch.int32, device=dev)
-        dg_all = digests if digests is not None else self.ctx.hash_msg(msgs)
-        for j0, j1, p0, p1 in self._chunks(counts, max_positions):
-            cs = list(counts[j0:j1])
-            s = None if sel is None else sel[p0:p1].to(dev)
-            # without sel, position p of this chunk is key row p0 + p
-            s_eff = s if s is not None else torch.arange(p0, p1, dtype=torch.int32, device=dev)
-            perm, _, _, _, alpha = self._sorted_hash(vk_l, vk_r, dg_all[p0:p1], cs, s_eff)
-            zsel = (sig_sel[p0:p1].to(dev) if sig_sel is not None else torch.arange(p0, p1, dtype=torch.int32, device=dev))
-            # perm is relative to the chunk: map sorted position -> signature row
-            sig_rows = zsel[perm.long()].to(torch.int32).contiguous()
-            out[j0:j1] = self.ctx.aggregate_sum(sigs, sig_rows, alpha, cs)
-        return out
+        ctx, dev = self.ctx, self.ctx.device
+        n_aggs = len(counts)
+        dg_all = digests if digests is not None else ctx.hash_msg(msgs)
+        state, wins, sel_d, side = self._hash_windows(vk_l, vk_r, dg_all, counts, sel, max_positions, keep_c=False)
+        zsel = sig_sel.to(dev, dtype=torch.int32).contiguous() if sig_sel is not None else None
+        main = torch.cuda.current_stream(dev)
+        out = None
+        prev = None
+        for wd in wins:
+            alpha_w = ctx.hash_ag_squeeze(state, wd["win_off"], n_aggs, wd["n"])      # the chain, on the main stream
+            squeezed = torch.cuda.Event()
+            squeezed.record(main)
+            alpha_w.record_stream(side)
+            with torch.cuda.stream(side):                                              # the MAC of this window overlaps the next squeeze
+                side.wait_event(squeezed)
+                rows = wd["pos"] if zsel is None else zsel.index_select(0, wd["pos"].long())
+                part = ctx.aggregate_sum_off(sigs, rows.contiguous(), alpha_w, wd["win_off"], n_aggs, wd["max"])
+                out = part if out is None else ctx.pointwise_add(out, part, out=out)
+                done = torch.cuda.Event()
+                done.record(side)
+            if prev is not None:
+                prev[0].synchronize()
+            prev = (done, alpha_w, rows, part)
+        main.wait_stream(side)
+        out.record_stream(main)
+        return out.reshape(n_aggs, self.ell, self.d)
 
     def verify(self, vk_l, vk_r, msgs: Optional[Sequence[bytes]], aggs, counts: Sequence[int], sel: Optional[torch.Tensor] = None,
-               n_msgs: Optional[Sequence[int]] = None, max_positions: int = 1 << 22, digests: Optional[torch.Tensor] = None) -> torch.Tensor:
+               n_msgs: Optional[Sequence[int]] = None, max_positions: int = 1 << 19, digests: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Returns uint8 codes per aggregate (0 = (True, ""), else VERIFY_REASONS[code])."""
-        dev = self.ctx.device
-        codes = torch.zeros(len(counts), dtype=torch.uint8, device=dev)
-        cap = self.ctx.capacity
+        ctx, dev = self.ctx, self.ctx.device
+        cap = ctx.capacity
         host_codes = [1 if c > cap else (2 if (n_msgs is not None and n_msgs[j] != c) else 0) for j, c in enumerate(counts)]
         if any(host_codes):  # reasons 1 / 2 are argument checks (fusion.py:686-689); those aggregates are not hashed
             raise ValueError("verify: aggregates with too many keys or a key/message count mismatch must be filtered by the caller: "
@@ -134,11 +182,29 @@ class Engine:
         total = int(sum(counts))
         if (digests.shape[0] if digests is not None else len(msgs)) != total:
             raise ValueError("one message per position is required")
-        dg_all = digests if digests is not None else self.ctx.hash_msg(msgs)
-        for j0, j1, p0, p1 in self._chunks(counts, max_positions):
-            cs = list(counts[j0:j1])
-            s = None if sel is None else sel[p0:p1].to(dev)
-            s_eff = s if s is not None else torch.arange(p0, p1, dtype=torch.int32, device=dev)
-            _, vl_s, vr_s, c_s, alpha = self._sorted_hash(vk_l, vk_r, dg_all[p0:p1], cs, s_eff)
-            codes[j0:j1] = self.ctx.verify_check(self.A, vl_s, vr_s, c_s, alpha, aggs[j0:j1], cs)
-        return codes
+        n_aggs = len(counts)
+        if n_aggs == 0:
+            return torch.zeros(0, dtype=torch.uint8, device=dev)
+        dg_all = digests if digests is not None else ctx.hash_msg(msgs)
+        state, wins, sel_d, side = self._hash_windows(vk_l, vk_r, dg_all, counts, sel, max_positions, keep_c=True)
+        main = torch.cuda.current_stream(dev)
+        target = None
+        prev = None
+        for wd in wins:
+            alpha_w = ctx.hash_ag_squeeze(state, wd["win_off"], n_aggs, wd["n"])
+            squeezed = torch.cuda.Event()
+            squeezed.record(main)
+            alpha_w.record_stream(side)
+            with torch.cuda.stream(side):
+                side.wait_event(squeezed)
+                vl_w, vr_w, _ = ctx.gather_sorted(vk_l, vk_r, dg_all, wd["pos"], sel=sel_d)
+                part = ctx.verify_target(vl_w, vr_w, wd["c"], alpha_w, wd["win_off"], n_aggs)
+                target = part if target is None else ctx.pointwise_add(target, part, out=target)
+                done = torch.cuda.Event()
+                done.record(side)
+            if prev is not None:
+                prev[0].synchronize()
+            prev = (done, alpha_w, vl_w, vr_w, part)
+        main.wait_stream(side)
+        target.record_stream(main)
+        return ctx.verify_finish(self.A, target, aggs)

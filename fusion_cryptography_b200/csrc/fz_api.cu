@@ -301,7 +301,7 @@ int fz_hash_ch(fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint
 }
 
 size_t fz_hash_ag_workspace(const fz_ctx* ctx, size_t n_total, size_t n_aggs, size_t max_keys) {
-    if (!ctx->buffered_hash) return 256;
+    if (!ctx->buffered_hash) return r256(n_aggs * ag_state_bytes()) + 256;
     return r256(n_total * PIECE_STRIDE) + r256(n_total * 4) + r256(n_total * 8) + r256(n_aggs * msg_stride_for(max_keys)) + r256(n_aggs * 4) +
            r256(n_total * (size_t)ctx->n_ag + 16) + 2048;
 }
@@ -313,12 +313,16 @@ int fz_hash_ag(fz_ctx* ctx, const int32_t* vk_l_s, const int32_t* vk_r_s, const 
     FZ_REQUIRE(ctx && (n_total == 0 || (vk_l_s && vk_r_s && dg_s && c_hat_s && agg_off && alpha_hat_out)), "fz_hash_ag: NULL argument");
     if (n_aggs == 0 || n_total == 0) return 0;
     if (!ctx->buffered_hash) {
-        // one serial sponge per aggregate: a warp per aggregate minimises the chain latency, a thread per aggregate
-        // maximises throughput once there are enough aggregates to fill the machine
-        const bool warp = ctx->hash_ag_impl == 3 || (ctx->hash_ag_impl == 0 && n_aggs < 8192);
-        int rc = warp ? launch_hash_ag_warp(ctx, vk_l_s, vk_r_s, dg_s, c_hat_s, (const unsigned long long*)agg_off, n_aggs, alpha_hat_out, (cudaStream_t)stream)
-                      : launch_hash_ag_stream(ctx, vk_l_s, vk_r_s, dg_s, c_hat_s, (const unsigned long long*)agg_off, n_aggs, alpha_hat_out, (cudaStream_t)stream);
-        if (!rc) rc = launch_ntt(ctx, 0, alpha_hat_out, alpha_hat_out, n_total, (cudaStream_t)stream);
+        // one window covering every signer: begin -> absorb -> squeeze on a state record per aggregate carved from ws
+        FZ_REQUIRE(ws, "fz_hash_ag: workspace required (see fz_hash_ag_workspace)");
+        Carver cv(ws, ws_bytes);
+        void* state = cv.take<uint8_t>(n_aggs * ag_state_bytes());
+        FZ_REQUIRE(cv.ok, "fz_hash_ag: workspace too small (see fz_hash_ag_workspace)");
+        cudaStream_t st = (cudaStream_t)stream;
+        int rc = launch_ag_state_init(ctx, state, (const unsigned long long*)agg_off, n_aggs, st);
+        if (!rc) rc = launch_hash_ag_absorb(ctx, state, vk_l_s, vk_r_s, dg_s, c_hat_s, (const unsigned long long*)agg_off, n_aggs, st);
+        if (!rc) rc = launch_hash_ag_squeeze(ctx, state, (const unsigned long long*)agg_off, n_aggs, alpha_hat_out, st);
+        if (!rc) rc = launch_ntt(ctx, 0, alpha_hat_out, alpha_hat_out, n_total, st);
         return rc;
     }
     FZ_REQUIRE(ws, "fz_hash_ag: workspace required in buffered mode");
@@ -337,6 +341,32 @@ int fz_hash_ag(fz_ctx* ctx, const int32_t* vk_l_s, const int32_t* vk_r_s, const 
     if (!rc) rc = launch_shake_ag(ctx, msgs, mstride, mlen, (const unsigned long long*)agg_off, xof, n_aggs, st);
     if (!rc) rc = launch_decode(ctx, xof, (size_t)ctx->n_ag, (uint32_t)ctx->n_ag, n_total, ctx->omega_ag, 1u, ctx->bytes_coef, ctx->bytes_idx, alpha_hat_out, st);
     if (!rc) rc = launch_ntt(ctx, 0, alpha_hat_out, alpha_hat_out, n_total, st);
+    return rc;
+}
+
+// ---- windowed hash_ag: the same serial sponge per aggregate, consumed a window of sorted signer positions at a time.
+// state: n_aggs records of fz_hash_ag_state_bytes() bytes (device memory owned by the caller).
+size_t fz_hash_ag_state_bytes(const fz_ctx* ctx) { (void)ctx; return ag_state_bytes(); }
+
+// agg_off: n_aggs + 1 offsets; only the signer COUNTS agg_off[j+1] - agg_off[j] are recorded
+int fz_hash_ag_begin(fz_ctx* ctx, void* state, const uint64_t* agg_off, size_t n_aggs, void* stream) {
+    FZ_REQUIRE(ctx && (n_aggs == 0 || (state && agg_off)), "fz_hash_ag_begin: NULL argument");
+    return launch_ag_state_init(ctx, state, (const unsigned long long*)agg_off, n_aggs, (cudaStream_t)stream);
+}
+
+// absorbs the next win_off[j+1] - win_off[j] sorted signers of every aggregate j; the window arrays hold them contiguously.
+// The call that delivers an aggregate's last signer pads and closes its message (an aggregate without signers closes at once).
+int fz_hash_ag_absorb(fz_ctx* ctx, void* state, const int32_t* vk_l_w, const int32_t* vk_r_w, const uint8_t* dg_w, const int32_t* c_hat_w,
+                      const uint64_t* win_off, size_t n_aggs, void* stream) {
+    FZ_REQUIRE(ctx && (n_aggs == 0 || (state && win_off)), "fz_hash_ag_absorb: NULL argument");
+    return launch_hash_ag_absorb(ctx, state, vk_l_w, vk_r_w, dg_w, c_hat_w, (const unsigned long long*)win_off, n_aggs, (cudaStream_t)stream);
+}
+
+// squeezes, decodes and transforms the aggregation coefficients of the next window of signers: alpha_hat_w: [n_window][d]
+int fz_hash_ag_squeeze(fz_ctx* ctx, void* state, const uint64_t* win_off, size_t n_aggs, size_t n_window, int32_t* alpha_hat_w, void* stream) {
+    FZ_REQUIRE(ctx && (n_aggs == 0 || (state && win_off)) && (n_window == 0 || alpha_hat_w), "fz_hash_ag_squeeze: NULL argument");
+    int rc = launch_hash_ag_squeeze(ctx, state, (const unsigned long long*)win_off, n_aggs, alpha_hat_w, (cudaStream_t)stream);
+    if (!rc) rc = launch_ntt(ctx, 0, alpha_hat_w, alpha_hat_w, n_window, (cudaStream_t)stream);
     return rc;
 }
 
@@ -392,6 +422,31 @@ int fz_verify_check(fz_ctx* ctx, const int32_t* A, const int32_t* vk_l_s, const 
     cudaStream_t st = (cudaStream_t)stream;
     int rc = launch_verify_target(ctx, vk_l_s, vk_r_s, c_hat_s, alpha_s, (const unsigned long long*)agg_off, n_aggs, target, st);
     if (!rc) rc = launch_matvec(ctx, A, agg, (size_t)ctx->d, (size_t)ctx->ell * ctx->d, observed, n_aggs, st);
+    if (!rc) rc = launch_ntt(ctx, 1, agg, coef, n_aggs * ctx->ell, st);
+    if (!rc) rc = launch_verify_finalize(ctx, target, observed, coef, n_aggs, codes, st);
+    return rc;
+}
+
+// fusion.py:706-714 over one window of sorted signers: target_w[j] = sum_p (vk_l[p] * c_hat[p] + vk_r[p]) * alpha[p]   ([n_aggs][d]);
+// window partials add up with fz_pointwise_add
+int fz_verify_target(fz_ctx* ctx, const int32_t* vk_l_w, const int32_t* vk_r_w, const int32_t* c_hat_w, const int32_t* alpha_w, const uint64_t* win_off,
+                     size_t n_aggs, int32_t* target_w, void* stream) {
+    FZ_REQUIRE(ctx && (n_aggs == 0 || (win_off && target_w)), "fz_verify_target: NULL argument");
+    return launch_verify_target(ctx, vk_l_w, vk_r_w, c_hat_w, alpha_w, (const unsigned long long*)win_off, n_aggs, target_w, (cudaStream_t)stream);
+}
+
+size_t fz_verify_finish_workspace(const fz_ctx* ctx, size_t n_aggs) { return r256(n_aggs * ctx->d * 4) + r256(n_aggs * (size_t)ctx->ell * ctx->d * 4) + 512; }
+
+// fusion.py:690-692, 715-728 given the complete target: observed = A . agg, comparison, infinity norm of INTT(agg)
+int fz_verify_finish(fz_ctx* ctx, const int32_t* A, const int32_t* target, const int32_t* agg, size_t n_aggs, uint8_t* codes, void* ws, size_t ws_bytes,
+                     void* stream) {
+    FZ_REQUIRE(ctx && (n_aggs == 0 || (A && target && agg && codes && ws)), "fz_verify_finish: NULL argument");
+    Carver cv(ws, ws_bytes);
+    int32_t* observed = cv.take<int32_t>(n_aggs * ctx->d);
+    int32_t* coef = cv.take<int32_t>(n_aggs * (size_t)ctx->ell * ctx->d);
+    FZ_REQUIRE(cv.ok, "fz_verify_finish: workspace too small (see fz_verify_finish_workspace)");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_matvec(ctx, A, agg, (size_t)ctx->d, (size_t)ctx->ell * ctx->d, observed, n_aggs, st);
     if (!rc) rc = launch_ntt(ctx, 1, agg, coef, n_aggs * ctx->ell, st);
     if (!rc) rc = launch_verify_finalize(ctx, target, observed, coef, n_aggs, codes, st);
     return rc;

@@ -323,35 +323,75 @@ __global__ void __launch_bounds__(HS_THREADS) hash_ch_stream_kernel(const int32_
 }
 
 // ---------------------------------------------------------------------------------- hash_ag
-// one thread per aggregate: text = dst "," "[" "(" VK ", " INT ", " CH ")" ", " ... "]"  (fusion.py:586-590) over the sorted
-// signers [agg_off[j], agg_off[j+1]); then (hi - lo) * n_ag bytes are squeezed and decoded signer by signer.
-__global__ void __launch_bounds__(32) hash_ag_stream_kernel(const int32_t* __restrict__ vk_l_s, const int32_t* __restrict__ vk_r_s,
-                                                              const uint8_t* __restrict__ dg_s, const int32_t* __restrict__ c_hat_s,
-                                                              const unsigned long long* __restrict__ agg_off, size_t n_aggs, int level, int d, int weight,
-                                                              int bpc, int bpi, uint32_t n_ag, int32_t* __restrict__ coef_out) {
+// The aggregation hash is ONE serial SHAKE256 per aggregate (fusion.py:573-591) over
+//     dst "," "[" "(" VK ", " INT ", " CH ")" ", " ... "]"
+// followed by total * n_ag squeezed bytes, decoded signer by signer (fusion.py:594-629).  The sponge is RESUMABLE: its
+// state (25 lanes, the text bytes not yet absorbed, the squeeze position) lives in an AgState record per aggregate, so a
+// batch of aggregates can be hashed WINDOW BY WINDOW over the sorted signer positions: every call consumes the next few
+// signers of every aggregate.  All chains of the batch are then in flight at once, independent of how many signers fit
+// in HBM at a time, and the per-signer inputs of the next window (gather, hash_ch) can be computed on another stream
+// while this window is absorbed.
+struct __align__(16) AgState {
+    unsigned long long a[25];   // sponge lanes
+    unsigned long long q[26];   // absorb phase: text bytes generated but not yet absorbed (little endian, nq of them)
+    uint32_t nq;
+    uint32_t absorbed;          // signers whose text has been generated
+    uint32_t total;             // signers of this aggregate
+    uint32_t produced;          // signers whose coefficient polynomial has been squeezed
+    uint32_t bpos;              // squeeze phase: bytes of the current block (lanes 0..16 of a) already handed out
+    uint32_t phase;             // 0 absorbing, 1 squeezing
+    uint32_t pad[20];
+};
+static_assert(sizeof(AgState) == 512, "AgState layout");
+
+__global__ void ag_state_init_kernel(AgState* __restrict__ st, const unsigned long long* __restrict__ agg_off, size_t n_aggs) {
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_aggs) return;
-    const size_t lo = agg_off[j], hi = agg_off[j + 1];
+    AgState* s = st + j;
+    for (int k = 0; k < 25; ++k) s->a[k] = 0;
+    for (int k = 0; k < 26; ++k) s->q[k] = 0;
+    s->nq = 0; s->absorbed = 0; s->total = (uint32_t)(agg_off[j + 1] - agg_off[j]); s->produced = 0; s->bpos = 0; s->phase = 0;
+}
+
+// one thread per aggregate: absorbs the signers [win_off[j], win_off[j+1]) of this window (the next ones in sorted order)
+__global__ void __launch_bounds__(32) hash_ag_absorb_thread_kernel(AgState* __restrict__ st, const int32_t* __restrict__ vk_l_s,
+                                                                     const int32_t* __restrict__ vk_r_s, const uint8_t* __restrict__ dg_s,
+                                                                     const int32_t* __restrict__ c_hat_s, const unsigned long long* __restrict__ win_off,
+                                                                     size_t n_aggs, int level, int d) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_aggs) return;
+    AgState* s = st + j;
+    if (s->phase != 0) return;
+    const size_t lo = win_off[j], hi = win_off[j + 1];
+    const uint32_t total = s->total;
+    uint32_t absorbed = s->absorbed;
+    if (hi == lo && total != 0) return;
     unsigned long long a[25];
 #pragma unroll
-    for (int k = 0; k < 25; ++k) a[k] = 0;
+    for (int k = 0; k < 25; ++k) a[k] = s->a[k];
     Queue q;
-    q_reset(q);
+    {
+        const int nq = (int)s->nq;
+        q.wi = nq >> 3; q.nb = nq & 7;
+        for (int k = 0; k < q.wi; ++k) q.blk[k] = s->q[k];
+        q.cur = q.nb ? s->q[q.wi] : 0ULL;
+    }
     Gen g;
     g.item = 0; g.idx = 0; g.int_len = 0;
     size_t p = lo;
-    bool more = true;
-    if (hi == lo) {  // "[]": dst "," "[" "]"
+    bool more = hi > lo, closing = false;
+    if (total == 0) {  // "[]": dst "," "[" "]"
         q_push(q, (unsigned long long)(level == 1 ? 3 : 1) | (2ULL << 8) | ((unsigned long long)',' << 16) | ((unsigned long long)'[' << 24) |
                       ((unsigned long long)']' << 32), 0, 5);
         more = false;
+        closing = true;
     }
     // per-signer program: 0 OPEN (first / next), 1 values(vk_l), 2 MID, 3 values(vk_r), 4 AFTER_VK, 5 INT, 6 BEFORE_C, 7 values(c_hat), 8 CLOSE
     for (;;) {
         while (q_bytes(q) < KECCAK_RATE && more) {
             bool fin;
             switch (g.item) {
-                case 0: fin = gen_segment(g, q, level, p == lo ? SEG_AG_OPEN_FIRST : SEG_AG_OPEN_NEXT); break;
+                case 0: fin = gen_segment(g, q, level, absorbed == 0 ? SEG_AG_OPEN_FIRST : SEG_AG_OPEN_NEXT); break;
                 case 1: fin = gen_values(g, q, vk_l_s + p * d, d); break;
                 case 2: fin = gen_segment(g, q, level, SEG_MID); break;
                 case 3: fin = gen_values(g, q, vk_r_s + p * d, d); break;
@@ -365,9 +405,11 @@ __global__ void __launch_bounds__(32) hash_ag_stream_kernel(const int32_t* __res
                 g.idx = 0;
                 if (++g.item == 9) {
                     g.item = 0;
-                    if (++p == hi) {
+                    ++absorbed;
+                    if (++p == hi) more = false;
+                    if (absorbed == total) {
                         q_push(q, (unsigned long long)']', 0, 1);
-                        more = false;
+                        closing = true;
                     }
                 }
             }
@@ -375,22 +417,45 @@ __global__ void __launch_bounds__(32) hash_ag_stream_kernel(const int32_t* __res
         if (q_bytes(q) >= KECCAK_RATE) {
             q_absorb_full(q, a);
             keccak_f(a);
-        } else {
+        } else if (closing) {
             q_absorb_last(q, a);
             keccak_f(a);
+            q_reset(q);
+            s->phase = 1;
+            s->bpos = 0;
             break;
+        } else {
+            break;   // window exhausted: the leftover text waits in the state
         }
     }
-    // squeeze + decode, one coefficient polynomial per signer, n_ag bytes each
+#pragma unroll
+    for (int k = 0; k < 25; ++k) s->a[k] = a[k];
+    for (int k = 0; k < q.wi; ++k) s->q[k] = q.blk[k];
+    s->q[q.wi] = q.cur;
+    s->nq = (uint32_t)q_bytes(q);
+    s->absorbed = absorbed;
+}
+
+// one thread per aggregate: squeezes and decodes the coefficients of the next hi - lo signers, n_ag bytes each
+__global__ void __launch_bounds__(32) hash_ag_squeeze_thread_kernel(AgState* __restrict__ st, const unsigned long long* __restrict__ win_off, size_t n_aggs,
+                                                                      int d, int weight, int bpc, int bpi, uint32_t n_ag, int32_t* __restrict__ coef_out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_aggs) return;
+    AgState* s = st + j;
+    const size_t lo = win_off[j], hi = win_off[j + 1];
+    if (hi == lo || s->phase != 1) return;
+    unsigned long long a[25];
+#pragma unroll
+    for (int k = 0; k < 25; ++k) a[k] = s->a[k];
     int32_t c[256];
     unsigned long long blk[KECCAK_RATE_LANES];
 #pragma unroll
     for (int k = 0; k < KECCAK_RATE_LANES; ++k) blk[k] = a[k];
-    int bpos = 0;  // bytes consumed from the current block
+    int bpos = (int)s->bpos;  // bytes consumed from the current block
     for (size_t sp = lo; sp < hi; ++sp) {
         for (int k = 0; k < d; ++k) c[k] = 0;
-        Dec s;
-        dinit(s, c, d, weight, 1u, bpc, bpi);
+        Dec ds;
+        dinit(ds, c, d, weight, 1u, bpc, bpi);
         uint32_t used = 0;
         while (used < n_ag) {
             if (bpos == KECCAK_RATE) {
@@ -401,18 +466,22 @@ __global__ void __launch_bounds__(32) hash_ag_stream_kernel(const int32_t* __res
             }
             const uint32_t avail = KECCAK_RATE - bpos, need = n_ag - used;
             const uint32_t take = avail < need ? avail : need;
-            if (s.phase != 3)
-                for (uint32_t t = 0; t < take && s.phase != 3; ++t) {
+            if (ds.phase != 3)
+                for (uint32_t t = 0; t < take && ds.phase != 3; ++t) {
                     const int jb = bpos + (int)t;
-                    dbyte(s, c, (uint32_t)(blk[jb >> 3] >> (8 * (jb & 7))) & 0xffu);
+                    dbyte(ds, c, (uint32_t)(blk[jb >> 3] >> (8 * (jb & 7))) & 0xffu);
                 }
             bpos += (int)take;
             used += take;
         }
-        while (s.phase != 3) dfinish(s, c);  // the slice is exhausted: remaining draws see empty bytes (quirk Q4)
+        while (ds.phase != 3) dfinish(ds, c);  // the slice is exhausted: remaining draws see empty bytes (quirk Q4)
         int32_t* o = coef_out + sp * d;
         for (int k = 0; k < d; ++k) o[k] = c[k];
     }
+#pragma unroll
+    for (int k = 0; k < 25; ++k) s->a[k] = a[k];
+    s->bpos = (uint32_t)bpos;
+    s->produced += (uint32_t)(hi - lo);
 }
 
 // ---------------------------------------------------------------------------------- host
@@ -466,14 +535,6 @@ int launch_hash_ch_stream(const fz_ctx* ctx, const int32_t* vk_l, const int32_t*
                                                                                             ctx->omega_ch, ctx->bytes_coef, ctx->bytes_idx,
                                                                                             (uint32_t)ctx->n_ch_used, coef_out);
     return check(cudaGetLastError(), "hash_ch_stream launch");
-}
-
-int launch_hash_ag_stream(const fz_ctx* ctx, const int32_t* vk_l_s, const int32_t* vk_r_s, const uint8_t* dg_s, const int32_t* c_hat_s,
-                          const unsigned long long* agg_off, size_t n_aggs, int32_t* coef_out, cudaStream_t st) {
-    if (n_aggs == 0) return 0;
-    hash_ag_stream_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>(vk_l_s, vk_r_s, dg_s, c_hat_s, agg_off, n_aggs, ctx->secpar == 256 ? 1 : 0, ctx->d,
-                                                                     ctx->omega_ag, ctx->bytes_coef, ctx->bytes_idx, (uint32_t)ctx->n_ag, coef_out);
-    return check(cudaGetLastError(), "hash_ag_stream launch");
 }
 
 
@@ -621,32 +682,44 @@ __device__ __forceinline__ void ring_values(Ring& rg, const int32_t* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(WARPS * 32) hash_ag_warp_kernel(const int32_t* __restrict__ vk_l_s, const int32_t* __restrict__ vk_r_s,
-                                                                   const uint8_t* __restrict__ dg_s, const int32_t* __restrict__ c_hat_s,
-                                                                   const unsigned long long* __restrict__ agg_off, size_t n_aggs, int level, int d, int weight,
-                                                                   int bpc, int bpi, uint32_t n_ag, int32_t* __restrict__ coef_out) {
+// absorb the signers [win_off[j], win_off[j+1]) of this window into the sponge of aggregate j (one warp per aggregate)
+__global__ void __launch_bounds__(WARPS * 32) hash_ag_absorb_warp_kernel(AgState* __restrict__ st, const int32_t* __restrict__ vk_l_s,
+                                                                          const int32_t* __restrict__ vk_r_s, const uint8_t* __restrict__ dg_s,
+                                                                          const int32_t* __restrict__ c_hat_s, const unsigned long long* __restrict__ win_off,
+                                                                          size_t n_aggs, int level, int d) {
     extern __shared__ __align__(16) uint8_t wsm[];
     const int L = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t j = (size_t)blockIdx.x * WARPS + warp;
     if (j >= n_aggs) return;
+    AgState* s = st + j;
+    if (s->phase != 0) return;
+    const size_t p0 = win_off[j], p1 = win_off[j + 1];
+    const uint32_t total = s->total;
+    uint32_t absorbed = s->absorbed;
+    if (p1 == p0 && total != 0) return;
     uint8_t* base = wsm + (size_t)warp * SMEM_PER_WARP;
     Ring rg;
     rg.buf = base; rg.wr = 0; rg.rd = 0;
-    uint8_t* xof = base + RING_BYTES;            // squeezed bytes of the current signer (+ carry-over)
-    int8_t* cf = reinterpret_cast<int8_t*>(base + RING_BYTES + XOF_BYTES);   // d coefficients
     uint8_t* intbuf = base + RING_BYTES + XOF_BYTES + 512;                   // 96 bytes decimal prehash
-    int* jdraw = reinterpret_cast<int*>(base + RING_BYTES + XOF_BYTES + 640);  // up to 64 index draws
     const Lane c = lane_init(L);
     uint32_t lo = 0, hi = 0;
-    const size_t p0 = agg_off[j], p1 = agg_off[j + 1];
-    // ---- absorb
-    if (p1 == p0) {
+    if (L < 25) { const unsigned long long v = s->a[L]; lo = (uint32_t)v; hi = (uint32_t)(v >> 32); }
+    {   // text left over from the previous window
+        const int nq = (int)s->nq;
+        const uint8_t* qb = reinterpret_cast<const uint8_t*>(s->q);
+        for (int k = L; k < nq; k += 32) rg.buf[k] = qb[k];
+        rg.wr = nq;
+        __syncwarp();
+    }
+    bool closing = false;
+    if (total == 0) {
         const unsigned long long t = (unsigned long long)(level == 1 ? 3 : 1) | (2ULL << 8) | ((unsigned long long)',' << 16) |
                                      ((unsigned long long)'[' << 24) | ((unsigned long long)']' << 32);
         ring_put_tokens(rg, L == 0 ? t : 0ULL, 0ULL, L == 0 ? 5 : 0, L);
+        closing = true;
     }
     for (size_t p = p0; p < p1; ++p) {
-        ring_segment(rg, level, p == p0 ? SEG_AG_OPEN_FIRST : SEG_AG_OPEN_NEXT, lo, hi, c, L);
+        ring_segment(rg, level, absorbed == 0 ? SEG_AG_OPEN_FIRST : SEG_AG_OPEN_NEXT, lo, hi, c, L);
         ring_values(rg, vk_l_s + p * d, d, lo, hi, c, L);
         ring_segment(rg, level, SEG_MID, lo, hi, c, L);
         ring_values(rg, vk_r_s + p * d, d, lo, hi, c, L);
@@ -670,37 +743,64 @@ __global__ void __launch_bounds__(WARPS * 32) hash_ag_warp_kernel(const int32_t*
         ring_segment(rg, level, SEG_AG_BEFORE_C, lo, hi, c, L);
         ring_values(rg, c_hat_s + p * d, d, lo, hi, c, L);
         ring_segment(rg, level, SEG_AG_CLOSE, lo, hi, c, L);
-        if (p + 1 == p1) {
+        if (++absorbed == total) {
             ring_put_tokens(rg, L == 0 ? (unsigned long long)']' : 0ULL, 0ULL, L == 0 ? 1 : 0, L);
             ring_drain(rg, lo, hi, c, L);
+            closing = true;
         }
     }
-    {   // last block with padding
-        __syncwarp();
-        const int rem = rg.wr - rg.rd;   // < 136
+    __syncwarp();
+    const int rem = rg.wr - rg.rd;   // < 136
+    unsigned long long w = 0;        // lane L < 17: bytes [8L, 8L + 8) of the pending text
+    if (L < KECCAK_RATE_LANES) {
+        const int b0 = 8 * L;
+        for (int k = 0; k < 8; ++k)
+            if (b0 + k < rem) w |= (unsigned long long)rg.buf[(rg.rd + b0 + k) % RING_BYTES] << (8 * k);
+    }
+    if (closing) {   // last block with padding
         if (L < KECCAK_RATE_LANES) {
-            unsigned long long w = 0;
             const int b0 = 8 * L;
-            for (int k = 0; k < 8; ++k)
-                if (b0 + k < rem) w |= (unsigned long long)rg.buf[(rg.rd + b0 + k) % RING_BYTES] << (8 * k);
             if (rem >= b0 && rem < b0 + 8) w ^= 0x1FULL << (8 * (rem - b0));
             if (L == 16) w ^= 0x8000000000000000ULL;
             lo ^= (uint32_t)w;
             hi ^= (uint32_t)(w >> 32);
         }
         keccak_f_warp(lo, hi, c, L);
+        if (L == 0) { s->phase = 1; s->bpos = 0; s->nq = 0; }
+    } else {
+        if (L < KECCAK_RATE_LANES) s->q[L] = w;
+        if (L == 0) s->nq = (uint32_t)rem;
     }
-    // ---- squeeze + decode, n_ag bytes per signer
-    int have = 0;      // bytes buffered in xof[] for the current signer
-    int blk_used = KECCAK_RATE;   // bytes of the current squeezed block already handed out (136 = none available)
-    bool first_block = true;
+    if (L < 25) s->a[L] = ((unsigned long long)hi << 32) | lo;
+    if (L == 0) s->absorbed = absorbed;
+}
+
+// squeeze + decode the coefficients of the next p1 - p0 signers of aggregate j, n_ag bytes per signer
+__global__ void __launch_bounds__(WARPS * 32) hash_ag_squeeze_warp_kernel(AgState* __restrict__ st, const unsigned long long* __restrict__ win_off,
+                                                                           size_t n_aggs, int d, int weight, int bpc, int bpi, uint32_t n_ag,
+                                                                           int32_t* __restrict__ coef_out) {
+    extern __shared__ __align__(16) uint8_t wsm[];
+    const int L = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t j = (size_t)blockIdx.x * WARPS + warp;
+    if (j >= n_aggs) return;
+    AgState* s = st + j;
+    const size_t p0 = win_off[j], p1 = win_off[j + 1];
+    if (p1 == p0 || s->phase != 1) return;
+    uint8_t* base = wsm + (size_t)warp * SMEM_PER_WARP;
+    uint8_t* xof = base + RING_BYTES;            // squeezed bytes of the current signer
+    int8_t* cf = reinterpret_cast<int8_t*>(base + RING_BYTES + XOF_BYTES);   // d coefficients
+    int* jdraw = reinterpret_cast<int*>(base + RING_BYTES + XOF_BYTES + 640);  // up to 64 index draws
+    const Lane c = lane_init(L);
+    uint32_t lo = 0, hi = 0;
+    if (L < 25) { const unsigned long long v = s->a[L]; lo = (uint32_t)v; hi = (uint32_t)(v >> 32); }
+    int have = 0;                     // bytes buffered in xof[] for the current signer
+    int blk_used = (int)s->bpos;      // bytes of the current squeezed block already handed out
     const int bfs = (weight + 7) / 8;
     for (size_t sp = p0; sp < p1; ++sp) {
         // collect n_ag bytes
         while (have < (int)n_ag) {
             if (blk_used == KECCAK_RATE) {
-                if (!first_block) keccak_f_warp(lo, hi, c, L);
-                first_block = false;
+                keccak_f_warp(lo, hi, c, L);
                 blk_used = 0;
             }
             // the current block lives in registers: lanes 0..16 publish the needed part
@@ -753,23 +853,65 @@ __global__ void __launch_bounds__(WARPS * 32) hash_ag_warp_kernel(const int32_t*
         __syncwarp();
         have = 0;
     }
+    if (L < 25) s->a[L] = ((unsigned long long)hi << 32) | lo;
+    if (L == 0) { s->bpos = (uint32_t)blk_used; s->produced += (uint32_t)(p1 - p0); }
 }
 
 }  // namespace warpag
 
-int launch_hash_ag_warp(const fz_ctx* ctx, const int32_t* vk_l_s, const int32_t* vk_r_s, const uint8_t* dg_s, const int32_t* c_hat_s,
-                        const unsigned long long* agg_off, size_t n_aggs, int32_t* coef_out, cudaStream_t st) {
+size_t ag_state_bytes() { return sizeof(AgState); }
+
+int launch_ag_state_init(const fz_ctx* ctx, void* state, const unsigned long long* agg_off, size_t n_aggs, cudaStream_t st) {
     if (n_aggs == 0) return 0;
-    const int smem = warpag::WARPS * warpag::SMEM_PER_WARP;
+    (void)ctx;
+    ag_state_init_kernel<<<(int)((n_aggs + 127) / 128), 128, 0, st>>>((AgState*)state, agg_off, n_aggs);
+    return check(cudaGetLastError(), "hash_ag state init launch");
+}
+
+static int warp_smem_attr() {
     static bool attr = false;
+    const int smem = warpag::WARPS * warpag::SMEM_PER_WARP;
     if (!attr) {
-        if (check(cudaFuncSetAttribute(warpag::hash_ag_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "hash_ag_warp smem attr")) return -2;
+        if (check(cudaFuncSetAttribute(warpag::hash_ag_absorb_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "hash_ag absorb smem attr"))
+            return -2;
+        if (check(cudaFuncSetAttribute(warpag::hash_ag_squeeze_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "hash_ag squeeze smem attr"))
+            return -2;
         attr = true;
     }
-    warpag::hash_ag_warp_kernel<<<(int)((n_aggs + warpag::WARPS - 1) / warpag::WARPS), warpag::WARPS * 32, smem, st>>>(
-        vk_l_s, vk_r_s, dg_s, c_hat_s, agg_off, n_aggs, ctx->secpar == 256 ? 1 : 0, ctx->d, ctx->omega_ag, ctx->bytes_coef, ctx->bytes_idx,
-        (uint32_t)ctx->n_ag, coef_out);
-    return check(cudaGetLastError(), "hash_ag_warp launch");
+    return 0;
+}
+
+// one serial sponge per aggregate: a warp per aggregate minimises the chain latency, a thread per aggregate maximises
+// throughput once there are enough aggregates to fill the machine
+static bool use_warp(const fz_ctx* ctx, size_t n_aggs) { return ctx->hash_ag_impl == 3 || (ctx->hash_ag_impl == 0 && n_aggs < 2560); }
+
+int launch_hash_ag_absorb(const fz_ctx* ctx, void* state, const int32_t* vk_l_s, const int32_t* vk_r_s, const uint8_t* dg_s, const int32_t* c_hat_s,
+                          const unsigned long long* win_off, size_t n_aggs, cudaStream_t st) {
+    if (n_aggs == 0) return 0;
+    const int level = ctx->secpar == 256 ? 1 : 0;
+    if (use_warp(ctx, n_aggs)) {
+        if (warp_smem_attr()) return -2;
+        warpag::hash_ag_absorb_warp_kernel<<<(int)((n_aggs + warpag::WARPS - 1) / warpag::WARPS), warpag::WARPS * 32, warpag::WARPS * warpag::SMEM_PER_WARP,
+                                             st>>>((AgState*)state, vk_l_s, vk_r_s, dg_s, c_hat_s, win_off, n_aggs, level, ctx->d);
+    } else {
+        hash_ag_absorb_thread_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>((AgState*)state, vk_l_s, vk_r_s, dg_s, c_hat_s, win_off, n_aggs, level,
+                                                                                ctx->d);
+    }
+    return check(cudaGetLastError(), "hash_ag absorb launch");
+}
+
+int launch_hash_ag_squeeze(const fz_ctx* ctx, void* state, const unsigned long long* win_off, size_t n_aggs, int32_t* coef_out, cudaStream_t st) {
+    if (n_aggs == 0) return 0;
+    if (use_warp(ctx, n_aggs)) {
+        if (warp_smem_attr()) return -2;
+        warpag::hash_ag_squeeze_warp_kernel<<<(int)((n_aggs + warpag::WARPS - 1) / warpag::WARPS), warpag::WARPS * 32, warpag::WARPS * warpag::SMEM_PER_WARP,
+                                              st>>>((AgState*)state, win_off, n_aggs, ctx->d, ctx->omega_ag, ctx->bytes_coef, ctx->bytes_idx,
+                                                    (uint32_t)ctx->n_ag, coef_out);
+    } else {
+        hash_ag_squeeze_thread_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>((AgState*)state, win_off, n_aggs, ctx->d, ctx->omega_ag, ctx->bytes_coef,
+                                                                                 ctx->bytes_idx, (uint32_t)ctx->n_ag, coef_out);
+    }
+    return check(cudaGetLastError(), "hash_ag squeeze launch");
 }
 
 }  // namespace fz

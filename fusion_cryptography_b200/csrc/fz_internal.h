@@ -18,7 +18,7 @@ struct fz_ctx {
     // scratch owned by the context (grown on demand, never per call when large enough)
     void* scratch;
     size_t scratch_bytes;
-    int hash_ag_impl;   // 0 auto (warp per aggregate below 8192 aggregates, thread per aggregate above), 2 thread, 3 warp
+    int hash_ag_impl;   // 0 auto (warp per aggregate below 2560 aggregates, thread per aggregate above), 2 thread, 3 warp
     int buffered_hash;  // 1: format text into HBM scratch first (fz_hash.cu); 0 (default): streaming generator (fz_hashstream.cu)
 };
 
@@ -60,11 +60,11 @@ int launch_shake_ag(const fz_ctx* ctx, const uint8_t* msgs, size_t msg_stride, c
 int hashstream_init_tables(fz_ctx* ctx);
 int launch_hash_ch_stream(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, size_t n, int32_t* coef_out,
                           cudaStream_t st);
-int launch_hash_ag_stream(const fz_ctx* ctx, const int32_t* vk_l_s, const int32_t* vk_r_s, const uint8_t* dg_s, const int32_t* c_hat_s,
-                          const unsigned long long* agg_off, size_t n_aggs, int32_t* coef_out, cudaStream_t st);
-
-int launch_hash_ag_warp(const fz_ctx* ctx, const int32_t* vk_l_s, const int32_t* vk_r_s, const uint8_t* dg_s, const int32_t* c_hat_s,
-                        const unsigned long long* agg_off, size_t n_aggs, int32_t* coef_out, cudaStream_t st);
+size_t ag_state_bytes();
+int launch_ag_state_init(const fz_ctx* ctx, void* state, const unsigned long long* agg_off, size_t n_aggs, cudaStream_t st);
+int launch_hash_ag_absorb(const fz_ctx* ctx, void* state, const int32_t* vk_l_s, const int32_t* vk_r_s, const uint8_t* dg_s, const int32_t* c_hat_s,
+                          const unsigned long long* win_off, size_t n_aggs, cudaStream_t st);
+int launch_hash_ag_squeeze(const fz_ctx* ctx, void* state, const unsigned long long* win_off, size_t n_aggs, int32_t* coef_out, cudaStream_t st);
 
 // fz_sample.cu
 int sample_init_tables(fz_ctx* ctx);

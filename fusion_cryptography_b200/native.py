@@ -396,6 +396,54 @@ def verify_check(self, A, vk_l_s, vk_r_s, c_hat_s, alpha_s, agg, counts) -> torc
     return codes
 
 
+# ---- windowed aggregation hash + split verify (device offsets; no host synchronisation) ----------------------
+def hash_ag_begin(self, agg_off: torch.Tensor, n_aggs: int) -> torch.Tensor:
+    """One resumable sponge record per aggregate (fusion.py:591 is one serial SHAKE256 per aggregate)."""
+    self.lib.fz_hash_ag_state_bytes.restype = C.c_size_t
+    state = torch.empty(max(n_aggs, 1) * int(self.lib.fz_hash_ag_state_bytes(self._h)), dtype=torch.uint8, device=self.device)
+    self._chk(self.lib.fz_hash_ag_begin(self._h, _ptr(state), _ptr(agg_off), C.c_size_t(n_aggs), self._stream()))
+    return state
+
+
+def hash_ag_absorb(self, state, vk_l_w, vk_r_w, dg_w, c_hat_w, win_off: torch.Tensor, n_aggs: int) -> None:
+    self._chk(self.lib.fz_hash_ag_absorb(self._h, _ptr(state), _ptr(vk_l_w), _ptr(vk_r_w), _ptr(dg_w), _ptr(c_hat_w), _ptr(win_off), C.c_size_t(n_aggs),
+                                         self._stream()))
+
+
+def hash_ag_squeeze(self, state, win_off: torch.Tensor, n_aggs: int, n_window: int) -> torch.Tensor:
+    out = torch.empty((n_window, self.d), dtype=torch.int32, device=self.device)
+    self._chk(self.lib.fz_hash_ag_squeeze(self._h, _ptr(state), _ptr(win_off), C.c_size_t(n_aggs), C.c_size_t(n_window), _ptr(out), self._stream()))
+    return out
+
+
+def aggregate_sum_off(self, sigs, rows, alpha, agg_off: torch.Tensor, n_aggs: int, max_keys: int) -> torch.Tensor:
+    """fz_aggregate_sum with device offsets: out[j] = sum over p in [agg_off[j], agg_off[j+1]) of sigs[rows[p]] * alpha[p]."""
+    self.lib.fz_aggregate_sum_workspace.restype = C.c_size_t
+    ws = self._ws(self.lib.fz_aggregate_sum_workspace(self._h, C.c_size_t(n_aggs), C.c_size_t(max_keys)))
+    out = torch.empty((n_aggs, self.ell, self.d), dtype=torch.int32, device=self.device)
+    self._chk(self.lib.fz_aggregate_sum(self._h, _ptr(sigs), _ptr(rows), _ptr(alpha), _ptr(agg_off), C.c_size_t(n_aggs), C.c_size_t(max_keys), _ptr(out),
+                                        _ptr(ws), C.c_size_t(ws.numel()), self._stream()))
+    return out
+
+
+def verify_target(self, vk_l_w, vk_r_w, c_hat_w, alpha_w, win_off: torch.Tensor, n_aggs: int) -> torch.Tensor:
+    out = torch.empty((n_aggs, self.d), dtype=torch.int32, device=self.device)
+    self._chk(self.lib.fz_verify_target(self._h, _ptr(vk_l_w), _ptr(vk_r_w), _ptr(c_hat_w), _ptr(alpha_w), _ptr(win_off), C.c_size_t(n_aggs), _ptr(out),
+                                        self._stream()))
+    return out
+
+
+def verify_finish(self, A, target, agg) -> torch.Tensor:
+    A, target, agg = self._dev(A), self._dev(target), self._dev(agg)
+    n_aggs = target.numel() // self.d
+    self.lib.fz_verify_finish_workspace.restype = C.c_size_t
+    ws = self._ws(self.lib.fz_verify_finish_workspace(self._h, C.c_size_t(n_aggs)))
+    codes = torch.empty(n_aggs, dtype=torch.uint8, device=self.device)
+    self._chk(self.lib.fz_verify_finish(self._h, _ptr(A), _ptr(target), _ptr(agg), C.c_size_t(n_aggs), _ptr(codes), _ptr(ws), C.c_size_t(ws.numel()),
+                                        self._stream()))
+    return codes
+
+
 def _seed_keys(self, seeds):
     """Python ints (any sign, up to 256 bits) -> ([n, 8] uint32 limbs, [n] int32 limb counts) on the device."""
     import numpy as np
@@ -465,5 +513,6 @@ def sign_mac_rows(self, sk_hat, c_hat, out=None) -> torch.Tensor:
 
 
 for _f in (_u8, _pack_messages, pack_messages, _ws, sha3_256, shake256, hash_msg, format_text, decode_poly, hash_ch, _agg_off, hash_ag, sort_keys, gather_sorted,
-           aggregate_sum, fold_partials, verify_check, _seed_keys, sample_coef, sample_ntt, keygen, sign_mac_rows):
+           aggregate_sum, fold_partials, verify_check, hash_ag_begin, hash_ag_absorb, hash_ag_squeeze, aggregate_sum_off,
+           verify_target, verify_finish, _seed_keys, sample_coef, sample_ntt, keygen, sign_mac_rows):
     setattr(Context, _f.__name__, _f)

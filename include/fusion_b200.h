@@ -89,6 +89,16 @@ size_t fz_hash_ag_workspace(const fz_ctx* ctx, size_t n_total, size_t n_aggs, si
 int fz_hash_ag(fz_ctx* ctx, const int32_t* vk_l_s, const int32_t* vk_r_s, const uint8_t* dg_s, const int32_t* c_hat_s, const uint64_t* agg_off,
                size_t n_aggs, size_t n_total, size_t max_keys, int32_t* alpha_hat_out, void* ws, size_t ws_bytes, void* stream);
 
+/* Windowed form of the same hash (one serial SHAKE256 per aggregate, fusion.py:591): the sponge of every aggregate is a
+ * resumable record in `state` (n_aggs * fz_hash_ag_state_bytes() bytes of device memory), fed a window of the next sorted
+ * signers of every aggregate per call -- win_off[j]..win_off[j+1] index the window arrays -- so that all aggregates of a
+ * batch advance together however many signers fit in memory at once.  begin -> absorb* -> squeeze*. */
+size_t fz_hash_ag_state_bytes(const fz_ctx* ctx);
+int fz_hash_ag_begin(fz_ctx* ctx, void* state, const uint64_t* agg_off, size_t n_aggs, void* stream);
+int fz_hash_ag_absorb(fz_ctx* ctx, void* state, const int32_t* vk_l_w, const int32_t* vk_r_w, const uint8_t* dg_w, const int32_t* c_hat_w,
+                      const uint64_t* win_off, size_t n_aggs, void* stream);
+int fz_hash_ag_squeeze(fz_ctx* ctx, void* state, const uint64_t* win_off, size_t n_aggs, size_t n_window, int32_t* alpha_hat_w, void* stream);
+
 /* ---- aggregate / verify ------------------------------------------------------------------------------- */
 /* sorted(zip(...), key=lambda x: str(x[0])) at fusion.py:661-663 and :693.  sel (optional) maps a position to a row of
  * vk_l / vk_r; perm[agg_off[j] + rank] = position.  Stable. */
@@ -107,6 +117,14 @@ int fz_fold_partials(fz_ctx* ctx, const int32_t* parts, int n_parts, size_t n_ag
 size_t fz_verify_check_workspace(const fz_ctx* ctx, size_t n_aggs);
 int fz_verify_check(fz_ctx* ctx, const int32_t* A, const int32_t* vk_l_s, const int32_t* vk_r_s, const int32_t* c_hat_s, const int32_t* alpha_s,
                     const int32_t* agg, const uint64_t* agg_off, size_t n_aggs, uint8_t* codes, void* ws, size_t ws_bytes, void* stream);
+
+/* The two halves of fz_verify_check for windowed batches: the target sum of fusion.py:706-714 over one window of sorted
+ * signers (partials add with fz_pointwise_add), then fusion.py:690-692, 715-728 on the complete target. */
+int fz_verify_target(fz_ctx* ctx, const int32_t* vk_l_w, const int32_t* vk_r_w, const int32_t* c_hat_w, const int32_t* alpha_w, const uint64_t* win_off,
+                     size_t n_aggs, int32_t* target_w, void* stream);
+size_t fz_verify_finish_workspace(const fz_ctx* ctx, size_t n_aggs);
+int fz_verify_finish(fz_ctx* ctx, const int32_t* A, const int32_t* target, const int32_t* agg, size_t n_aggs, uint8_t* codes, void* ws, size_t ws_bytes,
+                     void* stream);
 
 /* ---- seeded samplers and keygen (CPython random: MT19937 + randrange; algebra/polynomials.py:436-488) ----- */
 /* keys: [n][key_stride] little-endian 32-bit limbs of abs(seed), klen[n] in 1..8 */

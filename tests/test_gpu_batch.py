@@ -66,10 +66,21 @@ def test_aggregate_verify_batch(engines, oracle, scheme_golden, secpar):
     idx = sel_t.cuda().long()
     kpos = KeyBatch(sk_hat=kb.sk_hat[idx].contiguous(), vk_l=kb.vk_l[idx].contiguous(), vk_r=kb.vk_r[idx].contiguous())
     sigs = eng.sign(kpos, msgs)
-    for max_pos in (1 << 17, 40):   # one chunk / many chunks
-        aggs = eng.aggregate(kb.vk_l, kb.vk_r, msgs, sigs, counts, sel=sel_t, max_positions=max_pos)
-        codes = host(eng.verify(kb.vk_l, kb.vk_r, msgs, aggs, counts, sel=sel_t, max_positions=max_pos))
-        assert codes.tolist() == [0] * len(counts)
+    # one window / windows of 5 and of 1 sorted positions per aggregate (the resumable sponge of hash_ag), with a warp
+    # per aggregate (impl 3) and a thread per aggregate (impl 2): all bit-identical
+    ref_aggs = None
+    try:
+        for impl in (3, 2):
+            eng.ctx.set_option("hash_ag_impl", impl)
+            for max_pos in (1 << 17, 40, 8):
+                aggs = eng.aggregate(kb.vk_l, kb.vk_r, msgs, sigs, counts, sel=sel_t, max_positions=max_pos)
+                codes = host(eng.verify(kb.vk_l, kb.vk_r, msgs, aggs, counts, sel=sel_t, max_positions=max_pos))
+                assert codes.tolist() == [0] * len(counts), (impl, max_pos)
+                if ref_aggs is None:
+                    ref_aggs = aggs.clone()
+                assert torch.equal(aggs, ref_aggs), (impl, max_pos)
+    finally:
+        eng.ctx.set_option("hash_ag_impl", 0)
     hvl, hvr, hs = host(kb.vk_l), host(kb.vk_r), host(sigs)
     oracle.set_threads(oracle.max_threads())
     off = 0

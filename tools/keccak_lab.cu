@@ -157,6 +157,112 @@ __device__ __forceinline__ void f_v5(uint32_t& lo, uint32_t& hi, const Lane& c, 
     }
 }
 
+
+// V7: two shuffle stages: after the column parity, every lane gathers -- for each of its three pi sources -- the raw
+// lane and the parities of the source's neighbour columns, and applies theta + rho for those three lanes itself.
+struct Lane7 { int s[3], cm[3], cp[3], rot[3]; };
+__device__ __forceinline__ Lane7 lane7_init(int L) {
+    Lane7 q;
+    const int l = L < 25 ? L : 0, x = l % 5, y = l / 5;
+    for (int k = 0; k < 3; ++k) {
+        const int xk = (x + k) % 5;                 // column of B read by chi
+        const int src = ((xk + 3 * y) % 5) + 5 * xk; // A lane that pi moves to B[xk][y]
+        const int sx = src % 5;
+        q.s[k] = src; q.cm[k] = (sx + 4) % 5; q.cp[k] = (sx + 1) % 5; q.rot[k] = c_rot[src];
+    }
+    return q;
+}
+__device__ __forceinline__ void f_v7(uint32_t& lo, uint32_t& hi, const Lane& c, const Lane7& q, int L) {
+#pragma unroll 1
+    for (int r = 0; r < 24; ++r) {
+        const uint32_t cl = lo ^ SH(lo, c.src5) ^ SH(lo, c.src10) ^ SH(lo, c.src15) ^ SH(lo, c.src20);
+        const uint32_t ch = hi ^ SH(hi, c.src5) ^ SH(hi, c.src10) ^ SH(hi, c.src15) ^ SH(hi, c.src20);
+        uint32_t bl[3], bh[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            uint32_t al = SH(lo, q.s[k]), ah = SH(hi, q.s[k]);
+            const uint32_t ml = SH(cl, q.cm[k]), mh = SH(ch, q.cm[k]), pl = SH(cl, q.cp[k]), ph = SH(ch, q.cp[k]);
+            al ^= ml ^ __funnelshift_l(ph, pl, 1);
+            ah ^= mh ^ __funnelshift_l(pl, ph, 1);
+            rho(al, ah, q.rot[k]);
+            bl[k] = al; bh[k] = ah;
+        }
+        lo = bl[0] ^ (~bl[1] & bl[2]);
+        hi = bh[0] ^ (~bh[1] & bh[2]);
+        iota(lo, hi, r, L);
+    }
+}
+
+// V6: V0 on two independent sponges held by the same warp (instruction-level parallelism across chains)
+__device__ __forceinline__ void f_v6(uint32_t& lo, uint32_t& hi, uint32_t& lo2, uint32_t& hi2, const Lane& c, int L) {
+#pragma unroll 1
+    for (int r = 0; r < 24; ++r) {
+        uint32_t cl = lo ^ SH(lo, c.src5) ^ SH(lo, c.src10) ^ SH(lo, c.src15) ^ SH(lo, c.src20);
+        uint32_t ch = hi ^ SH(hi, c.src5) ^ SH(hi, c.src10) ^ SH(hi, c.src15) ^ SH(hi, c.src20);
+        uint32_t cl2 = lo2 ^ SH(lo2, c.src5) ^ SH(lo2, c.src10) ^ SH(lo2, c.src15) ^ SH(lo2, c.src20);
+        uint32_t ch2 = hi2 ^ SH(hi2, c.src5) ^ SH(hi2, c.src10) ^ SH(hi2, c.src15) ^ SH(hi2, c.src20);
+        const uint32_t ml = SH(cl, c.xm1), mh = SH(ch, c.xm1), pl = SH(cl, c.xp1), ph = SH(ch, c.xp1);
+        const uint32_t ml2 = SH(cl2, c.xm1), mh2 = SH(ch2, c.xm1), pl2 = SH(cl2, c.xp1), ph2 = SH(ch2, c.xp1);
+        lo ^= ml ^ __funnelshift_l(ph, pl, 1);
+        hi ^= mh ^ __funnelshift_l(pl, ph, 1);
+        lo2 ^= ml2 ^ __funnelshift_l(ph2, pl2, 1);
+        hi2 ^= mh2 ^ __funnelshift_l(pl2, ph2, 1);
+        rho(lo, hi, c.rot);
+        rho(lo2, hi2, c.rot);
+        const uint32_t b0l = SH(lo, c.pi0), b0h = SH(hi, c.pi0), b1l = SH(lo, c.pi1), b1h = SH(hi, c.pi1), b2l = SH(lo, c.pi2), b2h = SH(hi, c.pi2);
+        const uint32_t d0l = SH(lo2, c.pi0), d0h = SH(hi2, c.pi0), d1l = SH(lo2, c.pi1), d1h = SH(hi2, c.pi1), d2l = SH(lo2, c.pi2), d2h = SH(hi2, c.pi2);
+        lo = b0l ^ (~b1l & b2l);
+        hi = b0h ^ (~b1h & b2h);
+        lo2 = d0l ^ (~d1l & d2l);
+        hi2 = d0h ^ (~d1h & d2h);
+        iota(lo, hi, r, L);
+        iota(lo2, hi2, r, L);
+    }
+}
+
+template <int V>
+__global__ void coop2_kernel(int perms, unsigned long long* state_out, long long* cycles_out) {
+    const int L = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const Lane c = lane_init(L);
+    const Lane7 q = lane7_init(L);
+    const int chain = blockIdx.x * (blockDim.x >> 5) + w;
+    unsigned long long v = L < 25 ? (unsigned long long)(L + 1) * 0x9E3779B97F4A7C15ULL + (unsigned long long)chain : 0ULL;
+    uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32), lo2 = lo ^ 0x55u, hi2 = hi;
+    const long long t0 = clock64();
+    for (int p = 0; p < perms; ++p) {
+        if (V == 6) f_v6(lo, hi, lo2, hi2, c, L);
+        if (V == 7) f_v7(lo, hi, c, q, L);
+    }
+    const long long t1 = clock64();
+    if (chain == 0 && L < 25) state_out[L] = ((unsigned long long)hi << 32) | lo;
+    if (V == 6 && lo2 == 0x12345u && hi2 == 7u) state_out[0] = 0;   // keep the second chain alive
+    if (L == 0) cycles_out[chain] = t1 - t0;
+}
+
+// SHFL characteristics: dependent chain (latency) and batches of 8 independent shuffles (issue interval)
+__global__ void shfl_kernel(int iters, int mode, long long* cycles_out, unsigned* sink) {
+    const int L = threadIdx.x & 31;
+    unsigned x = threadIdx.x * 2654435761u, y[8];
+    const int src = (L * 7 + 3) & 31;
+    for (int k = 0; k < 8; ++k) y[k] = x + k;
+    const long long t0 = clock64();
+    if (mode == 0) {
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x = SH(x, src);
+        }
+    } else {
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) y[k] = SH(y[k], src);
+        }
+    }
+    const long long t1 = clock64();
+    for (int k = 0; k < 8; ++k) x ^= y[k];
+    if (x == 0x1234567u) sink[0] = x;
+    if (threadIdx.x == 0 && blockIdx.x == 0) cycles_out[0] = t1 - t0;
+}
+
 template <int V>
 __global__ void coop_kernel(int perms, unsigned long long* state_out, long long* cycles_out) {
     extern __shared__ uint2 sm[];
@@ -241,6 +347,33 @@ int main(int argc, char** argv) {
     RUN_COOP(2, "V2 smem 3-stage")
     RUN_COOP(3, "V3 smem 2-stage")
     RUN_COOP(5, "V5 redux + smem")
+
+#define RUN_COOP2(V, NAME)                                                                    \
+    for (int wi = 0; wi < 6; ++wi) {                                                          \
+        const int w = wps[wi];                                                                \
+        const int bw = w < 4 ? w : 4, blocks = sms * (w / bw);                                \
+        coop2_kernel<V><<<blocks, bw * 32>>>(10, d_state, d_cyc);                              \
+        CK(cudaEventRecord(e0));                                                              \
+        coop2_kernel<V><<<blocks, bw * 32>>>(perms, d_state, d_cyc);                           \
+        CK(cudaEventRecord(e1));                                                              \
+        CK(cudaDeviceSynchronize());                                                          \
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));                                      \
+        report(NAME, w, blocks * bw, ms, V == 6 ? 2 : 1);                                     \
+    }
+    RUN_COOP2(6, "V6 shfl x18, 2 chains/warp")
+    RUN_COOP2(7, "V7 shfl x26, 2 stages")
+    {
+        unsigned* d_sink; CK(cudaMalloc(&d_sink, 4));
+        const int it = 10000;
+        for (int mode = 0; mode < 2; ++mode)
+            for (int w = 1; w <= 16; w *= 2) {
+                const int bw = w < 4 ? w : 4, blocks = sms * (w / bw);
+                shfl_kernel<<<blocks, bw * 32>>>(it, mode, d_cyc, d_sink);
+                CK(cudaDeviceSynchronize());
+                long long cy; CK(cudaMemcpy(&cy, d_cyc, 8, cudaMemcpyDeviceToHost));
+                printf("SHFL %s warps/SM %2d: %.2f cycles per shuffle (one warp's view)\n", mode ? "8 independent" : "dependent chain", w, (double)cy / it / 8.0);
+            }
+    }
     const int tw[] = {4, 8, 16, 24, 32};
     for (int wi = 0; wi < 5; ++wi) {
         const int w = tw[wi];
