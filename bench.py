@@ -212,8 +212,9 @@ def scheme_extras(args, ctx, rank, world, dist):
     t_ks, (vk_l, vk_r, sigs) = timed(lambda: eng.keygen_sign(seeds, pm, chunk=16384))
     t_ks = allmax(t_ks)
     kb = eng.keygen(seeds)
-    c_hat = eng.challenges(kb.vk_l, kb.vk_r, msgs)
-    t_hash, _ = timed(lambda: eng.challenges(kb.vk_l, kb.vk_r, msgs))
+    dg = ctx.hash_msg(pm)
+    c_hat = ctx.hash_ch(kb.vk_l, kb.vk_r, dg)
+    t_hash, _ = timed(lambda: ctx.hash_ch(kb.vk_l, kb.vk_r, dg), reps=3)
     t_mac, _ = timed(lambda: ctx.sign_mac_rows(kb.sk_hat, c_hat, out=sigs), reps=5)
     # general (ell distinct rows) sign MAC, the roofline kernel of SURVEY 8d: reads 2 * ell KiB, writes ell KiB per key
     nkg = min(nk, 4096)

@@ -90,6 +90,8 @@ class Engine:
         return perm, vl_s, vr_s, c_s, alpha
 
     def _hash_windows(self, vk_l, vk_r, dg_all, counts, sel, window_positions: int, keep_c: bool):
+        """Absorb phase.  Side stream: gather -> hash_ch -> message text of window w into the per-aggregate rings; main stream:
+        the sponge chains over the rings.  Returns the sponge states and the per-window index arrays for the squeeze phase."""
         import numpy as np
 
         ctx, dev = self.ctx, self.ctx.device
@@ -103,6 +105,8 @@ class Engine:
         perm = ctx.sort_keys(vk_l, vk_r, [int(c) for c in counts], sel=sel_d)
         P = max(1, min(max_count, window_positions // max(n_aggs, 1))) if max_count else 1
         state = ctx.hash_ag_begin(agg_off, n_aggs)
+        ring, ring_cap, text_pos = ctx.hash_ag_ring(n_aggs, P)
+        agg_ids = torch.arange(n_aggs, dtype=torch.int32, device=dev)
         main = torch.cuda.current_stream(dev)
         prep = torch.cuda.Stream(device=dev)
         prep.wait_stream(main)
@@ -113,28 +117,60 @@ class Engine:
             woff_np = np.zeros(n_aggs + 1, dtype=np.int64)
             np.cumsum(cnt, out=woff_np[1:])
             if len(wins) >= 2:
-                wins[-2]["absorbed"].synchronize()   # the host stays at most two windows ahead of the chain
+                prep.wait_event(wins[-2]["absorbed"])    # ring space of window w - 2 is free once its chain step is done
+                wins[-2]["absorbed"].synchronize()       # and the host stays at most two windows ahead
             with torch.cuda.stream(prep):
                 win_off = torch.from_numpy(woff_np).to(dev, non_blocking=True)
                 cnt_d = torch.from_numpy(cnt).to(dev, non_blocking=True)
                 base = agg_off[:-1] + w - win_off[:-1]
                 idx = torch.repeat_interleave(base, cnt_d, output_size=n_win) + torch.arange(n_win, dtype=torch.int64, device=dev)
+                agg_of = torch.repeat_interleave(agg_ids, cnt_d, output_size=n_win)
                 pos = perm.index_select(0, idx)
                 vl_w, vr_w, dg_w = ctx.gather_sorted(vk_l, vk_r, dg_all, pos, sel=sel_d)
                 c_w = ctx.hash_ch(vl_w, vr_w, dg_w)
+                wend = ctx.hash_ag_text(vl_w, vr_w, dg_w, c_w, win_off, agg_of, agg_off, n_aggs, n_win, w, text_pos, ring, ring_cap)
                 ready = torch.cuda.Event()
                 ready.record(prep)
-            for t in (win_off, pos, vl_w, vr_w, dg_w, c_w):
-                t.record_stream(main)                # allocated on the side stream, consumed by the chain on the main stream
+            for t in (win_off, wend, pos, agg_of, c_w):
+                t.record_stream(main)                    # allocated on the side stream, read on the main stream
             main.wait_event(ready)
-            ctx.hash_ag_absorb(state, vl_w, vr_w, dg_w, c_w, win_off, n_aggs)
+            ctx.hash_ag_absorb_ring(state, ring, ring_cap, wend, win_off, n_aggs)
             absorbed = torch.cuda.Event()
             absorbed.record(main)
-            wins.append({"win_off": win_off, "n": n_win, "pos": pos, "max": int(cnt.max()), "absorbed": absorbed, "c": c_w if keep_c else None})
-        return state, wins, sel_d, prep
+            wins.append({"win_off": win_off, "n": n_win, "pos": pos, "agg_of": agg_of, "max": int(cnt.max()), "absorbed": absorbed,
+                         "c": c_w if keep_c else None})
+        for t in (ring, text_pos, agg_ids, agg_off, perm, sel_d):
+            t.record_stream(prep)
+        return state, wins, sel_d, prep, P
+
+    def _squeeze_windows(self, state, wins, n_aggs, P, side, consume):
+        """Squeeze phase.  Main stream: the chains write squeezed blocks of window w; side stream: decode + NTT + consume(wd, alpha_w)."""
+        ctx, dev = self.ctx, self.ctx.device
+        main = torch.cuda.current_stream(dev)
+        bufs = [ctx.hash_ag_xof_buffer(n_aggs, P) for _ in range(2)]
+        done = [None, None]
+        for k, wd in enumerate(wins):
+            xof, xof_cap = bufs[k & 1]
+            if done[k & 1] is not None:
+                main.wait_event(done[k & 1])             # the buffer's previous window has been decoded
+                done[k & 1].synchronize()
+            bpos = ctx.hash_ag_squeeze_xof(state, wd["win_off"], n_aggs, xof, xof_cap)
+            squeezed = torch.cuda.Event()
+            squeezed.record(main)
+            bpos.record_stream(side)
+            with torch.cuda.stream(side):
+                side.wait_event(squeezed)
+                alpha_w = ctx.hash_ag_decode(xof, xof_cap, bpos, wd["win_off"], wd["agg_of"], wd["n"])
+                consume(wd, alpha_w)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            done[k & 1] = ev
+        for xof, _ in bufs:
+            xof.record_stream(side)
+        main.wait_stream(side)
 
     def aggregate(self, vk_l, vk_r, msgs: Optional[Sequence[bytes]], sigs, counts: Sequence[int], sel: Optional[torch.Tensor] = None,
-                  sig_sel: Optional[torch.Tensor] = None, max_positions: int = 1 << 19, digests: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  sig_sel: Optional[torch.Tensor] = None, max_positions: int = 1 << 18, digests: Optional[torch.Tensor] = None) -> torch.Tensor:
         """counts[j] signers per aggregate; position p (0 <= p < sum(counts)) signs msgs[p] with key row sel[p] and
         signature row sig_sel[p] (both default to p).  `digests` ([positions, 32] prehashes from hash_msg) may replace msgs.
         `max_positions` bounds the signer positions resident per window.  Returns [n_aggs, ell, d]."""
@@ -146,32 +182,22 @@ class Engine:
         ctx, dev = self.ctx, self.ctx.device
         n_aggs = len(counts)
         dg_all = digests if digests is not None else ctx.hash_msg(msgs)
-        state, wins, sel_d, side = self._hash_windows(vk_l, vk_r, dg_all, counts, sel, max_positions, keep_c=False)
+        state, wins, sel_d, side, P = self._hash_windows(vk_l, vk_r, dg_all, counts, sel, max_positions, keep_c=False)
         zsel = sig_sel.to(dev, dtype=torch.int32).contiguous() if sig_sel is not None else None
-        main = torch.cuda.current_stream(dev)
-        out = None
-        prev = None
-        for wd in wins:
-            alpha_w = ctx.hash_ag_squeeze(state, wd["win_off"], n_aggs, wd["n"])      # the chain, on the main stream
-            squeezed = torch.cuda.Event()
-            squeezed.record(main)
-            alpha_w.record_stream(side)
-            with torch.cuda.stream(side):                                              # the MAC of this window overlaps the next squeeze
-                side.wait_event(squeezed)
-                rows = wd["pos"] if zsel is None else zsel.index_select(0, wd["pos"].long())
-                part = ctx.aggregate_sum_off(sigs, rows.contiguous(), alpha_w, wd["win_off"], n_aggs, wd["max"])
-                out = part if out is None else ctx.pointwise_add(out, part, out=out)
-                done = torch.cuda.Event()
-                done.record(side)
-            if prev is not None:
-                prev[0].synchronize()
-            prev = (done, alpha_w, rows, part)
-        main.wait_stream(side)
-        out.record_stream(main)
+        acc = {"out": None}
+
+        def consume(wd, alpha_w):     # fusion.py:670-677 over this window's signers, added to the running sums
+            rows = wd["pos"] if zsel is None else zsel.index_select(0, wd["pos"].long())
+            part = ctx.aggregate_sum_off(sigs, rows.contiguous(), alpha_w, wd["win_off"], n_aggs, wd["max"])
+            acc["out"] = part if acc["out"] is None else ctx.pointwise_add(acc["out"], part, out=acc["out"])
+
+        self._squeeze_windows(state, wins, n_aggs, P, side, consume)
+        out = acc["out"]
+        out.record_stream(torch.cuda.current_stream(dev))
         return out.reshape(n_aggs, self.ell, self.d)
 
     def verify(self, vk_l, vk_r, msgs: Optional[Sequence[bytes]], aggs, counts: Sequence[int], sel: Optional[torch.Tensor] = None,
-               n_msgs: Optional[Sequence[int]] = None, max_positions: int = 1 << 19, digests: Optional[torch.Tensor] = None) -> torch.Tensor:
+               n_msgs: Optional[Sequence[int]] = None, max_positions: int = 1 << 18, digests: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Returns uint8 codes per aggregate (0 = (True, ""), else VERIFY_REASONS[code])."""
         ctx, dev = self.ctx, self.ctx.device
         cap = ctx.capacity
@@ -186,25 +212,15 @@ class Engine:
         if n_aggs == 0:
             return torch.zeros(0, dtype=torch.uint8, device=dev)
         dg_all = digests if digests is not None else ctx.hash_msg(msgs)
-        state, wins, sel_d, side = self._hash_windows(vk_l, vk_r, dg_all, counts, sel, max_positions, keep_c=True)
-        main = torch.cuda.current_stream(dev)
-        target = None
-        prev = None
-        for wd in wins:
-            alpha_w = ctx.hash_ag_squeeze(state, wd["win_off"], n_aggs, wd["n"])
-            squeezed = torch.cuda.Event()
-            squeezed.record(main)
-            alpha_w.record_stream(side)
-            with torch.cuda.stream(side):
-                side.wait_event(squeezed)
-                vl_w, vr_w, _ = ctx.gather_sorted(vk_l, vk_r, dg_all, wd["pos"], sel=sel_d)
-                part = ctx.verify_target(vl_w, vr_w, wd["c"], alpha_w, wd["win_off"], n_aggs)
-                target = part if target is None else ctx.pointwise_add(target, part, out=target)
-                done = torch.cuda.Event()
-                done.record(side)
-            if prev is not None:
-                prev[0].synchronize()
-            prev = (done, alpha_w, vl_w, vr_w, part)
-        main.wait_stream(side)
-        target.record_stream(main)
+        state, wins, sel_d, side, P = self._hash_windows(vk_l, vk_r, dg_all, counts, sel, max_positions, keep_c=True)
+        acc = {"target": None}
+
+        def consume(wd, alpha_w):     # fusion.py:706-714 over this window's signers
+            vl_w, vr_w, _ = ctx.gather_sorted(vk_l, vk_r, dg_all, wd["pos"], sel=sel_d)
+            part = ctx.verify_target(vl_w, vr_w, wd["c"], alpha_w, wd["win_off"], n_aggs)
+            acc["target"] = part if acc["target"] is None else ctx.pointwise_add(acc["target"], part, out=acc["target"])
+
+        self._squeeze_windows(state, wins, n_aggs, P, side, consume)
+        target = acc["target"]
+        target.record_stream(torch.cuda.current_stream(dev))
         return ctx.verify_finish(self.A, target, aggs)

@@ -370,6 +370,54 @@ int fz_hash_ag_squeeze(fz_ctx* ctx, void* state, const uint64_t* win_off, size_t
     return rc;
 }
 
+// ---- windowed hash_ag with the text generated off the chain: fz_hash_ag_text writes the bytes a window adds to every
+// aggregate's message into per-aggregate byte rings (parallel work, any stream), fz_hash_ag_absorb_ring advances the sponges
+// over them (the serial chain), fz_hash_ag_squeeze_xof writes whole squeezed blocks per aggregate and fz_hash_ag_decode turns
+// them into coefficients (parallel work again).  Windows are uniform: window w0 holds sorted positions w0 .. w0 + P - 1.
+size_t fz_hash_ag_ring_bytes(const fz_ctx* ctx, size_t max_window) {   // per aggregate; holds two windows of text in flight
+    (void)ctx;
+    const size_t need = 2 * max_window * agw_max_piece() + 2 * 272;
+    return (need + 271) / 272 * 272;
+}
+size_t fz_hash_ag_xof_bytes(const fz_ctx* ctx, size_t max_window) { return ((max_window * (size_t)ctx->n_ag + 2 * 136 + 32) + 15) & ~(size_t)15; }
+size_t fz_hash_ag_text_workspace(const fz_ctx* ctx, size_t n_window) { (void)ctx; return r256(n_window * 4) + r256(n_window * 8) + 256; }
+
+int fz_hash_ag_text(fz_ctx* ctx, const int32_t* vk_l_w, const int32_t* vk_r_w, const uint8_t* dg_w, const int32_t* c_hat_w, const uint64_t* win_off,
+                    const uint32_t* agg_of, const uint64_t* agg_off, size_t n_aggs, size_t n_window, uint32_t w0, uint64_t* text_pos, uint8_t* ring,
+                    size_t ring_cap, uint64_t* wend_out, void* ws, size_t ws_bytes, void* stream) {
+    FZ_REQUIRE(ctx && (n_aggs == 0 || (win_off && agg_off && text_pos && ring && wend_out)), "fz_hash_ag_text: NULL argument");
+    FZ_REQUIRE(n_window == 0 || (vk_l_w && vk_r_w && dg_w && c_hat_w && agg_of && ws), "fz_hash_ag_text: NULL window argument");
+    FZ_REQUIRE(ring_cap % 272 == 0 && ring_cap >= 544, "fz_hash_ag_text: ring_cap must be a multiple of 272 (see fz_hash_ag_ring_bytes)");
+    Carver cv(ws, ws_bytes);
+    uint32_t* piece_len = cv.take<uint32_t>(n_window);
+    unsigned long long* piece_off = cv.take<unsigned long long>(n_window);
+    FZ_REQUIRE(cv.ok, "fz_hash_ag_text: workspace too small (see fz_hash_ag_text_workspace)");
+    return launch_agw_text(ctx, vk_l_w, vk_r_w, dg_w, c_hat_w, (const unsigned long long*)win_off, agg_of, (const unsigned long long*)agg_off, n_aggs,
+                           n_window, w0, (unsigned long long*)text_pos, piece_len, piece_off, (unsigned long long*)wend_out, ring, ring_cap,
+                           (cudaStream_t)stream);
+}
+
+int fz_hash_ag_absorb_ring(fz_ctx* ctx, void* state, const uint8_t* ring, size_t ring_cap, const uint64_t* wend, const uint64_t* win_off, size_t n_aggs,
+                           void* stream) {
+    FZ_REQUIRE(ctx && (n_aggs == 0 || (state && ring && wend && win_off)), "fz_hash_ag_absorb_ring: NULL argument");
+    return launch_agw_absorb(ctx, state, ring, ring_cap, (const unsigned long long*)wend, (const unsigned long long*)win_off, n_aggs, (cudaStream_t)stream);
+}
+
+int fz_hash_ag_squeeze_xof(fz_ctx* ctx, void* state, const uint64_t* win_off, size_t n_aggs, uint8_t* xof, size_t xof_cap, uint32_t* bpos_out,
+                           void* stream) {
+    FZ_REQUIRE(ctx && (n_aggs == 0 || (state && win_off && xof && bpos_out)), "fz_hash_ag_squeeze_xof: NULL argument");
+    FZ_REQUIRE(xof_cap % 16 == 0, "fz_hash_ag_squeeze_xof: xof_cap must be a multiple of 16 (see fz_hash_ag_xof_bytes)");
+    return launch_agw_squeeze(ctx, state, (const unsigned long long*)win_off, n_aggs, xof, xof_cap, bpos_out, (cudaStream_t)stream);
+}
+
+int fz_hash_ag_decode(fz_ctx* ctx, const uint8_t* xof, size_t xof_cap, const uint32_t* bpos, const uint64_t* win_off, const uint32_t* agg_of,
+                      size_t n_window, int32_t* alpha_hat_w, void* stream) {
+    FZ_REQUIRE(ctx && (n_window == 0 || (xof && bpos && win_off && agg_of && alpha_hat_w)), "fz_hash_ag_decode: NULL argument");
+    int rc = launch_agw_decode(ctx, xof, xof_cap, bpos, (const unsigned long long*)win_off, agg_of, n_window, alpha_hat_w, (cudaStream_t)stream);
+    if (!rc) rc = launch_ntt(ctx, 0, alpha_hat_w, alpha_hat_w, n_window, (cudaStream_t)stream);
+    return rc;
+}
+
 // sorted(..., key=str(vk)) (fusion.py:661-663, 693): perm[agg_off[j] + rank] = original position; sel (optional) maps positions to key rows
 int fz_sort_keys(fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint32_t* sel, const uint64_t* agg_off, size_t n_aggs, size_t max_keys,
                  uint32_t* perm, void* stream) {

@@ -525,6 +525,202 @@ __global__ void __launch_bounds__(32) shake_ag_kernel(const uint8_t* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Windowed aggregation hash, text side (the sponge side is in fz_hashstream.cu).  The text a window of sorted signers adds
+// to each aggregate's message is generated in parallel, a warp per signer, straight into a per-aggregate byte RING in HBM,
+// so the serial sponge chain only loads 17 lanes per block.  The message of aggregate j is
+//     dst 2 "," "[" piece_0 ", " piece_1 ... "]",    piece = "(" VK ", " INT ", " "SignatureChallenge(c_hat=" POLY ")" ")"
+// and the bytes signer r contributes are [opener] piece [closer]: opener = dst 2 ",[" for r = 0 else ", "; closer = "]" for
+// the aggregate's last signer.  Three passes: lengths -> per-aggregate scan of stream offsets -> format + write.
+constexpr int AGW_SMEM_PER_WARP = FMT_SMEM_PER_WARP + 64;   // piece + opener / closer + 16 bytes of alignment slack
+
+__device__ __forceinline__ int values_len(const int32_t* __restrict__ vals, int d, int lane) {
+    int my = 0;
+    for (int k = lane; k < d; k += 32) my += dec_len(vals[k]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) my += __shfl_xor_sync(0xffffffffu, my, o);
+    return my + 2 * (d - 1);
+}
+
+__global__ void __launch_bounds__(128) agw_len_kernel(int level, int d, const int32_t* __restrict__ vk_l, const int32_t* __restrict__ vk_r,
+                                                       const uint8_t* __restrict__ digests, const int32_t* __restrict__ c_hat,
+                                                       const unsigned long long* __restrict__ win_off, const uint32_t* __restrict__ agg_of,
+                                                       const unsigned long long* __restrict__ agg_off, size_t n_win, uint32_t w0,
+                                                       uint32_t* __restrict__ piece_len) {
+    const int lane = threadIdx.x & 31;
+    const size_t i = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (i >= n_win) return;
+    const FmtConst& fc = c_fmt[level];
+    const uint32_t j = agg_of[i];
+    const unsigned long long rank = w0 + (i - win_off[j]), total = agg_off[j + 1] - agg_off[j];
+    const int poly_fixed = fc.poly_head_len + 2;                 // head ... "])"
+    const int gm_fixed = fc.gm_head_len + poly_fixed + 3;        // head POLY "]])"
+    int len = 1 + 35 + gm_fixed + 15 + gm_fixed + 1 + 2 + 27 + poly_fixed + 2;
+    len += values_len(vk_l + i * d, d, lane) + values_len(vk_r + i * d, d, lane) + values_len(c_hat + i * d, d, lane);
+    int li = 0;
+    if (lane == 0) {
+        uint8_t tmp[96];
+        li = format_le256(tmp, digests + i * 32);
+    }
+    li = __shfl_sync(0xffffffffu, li, 0);
+    len += li + (rank == 0 ? 4 : 2) + (rank + 1 == total ? 1 : 0);
+    if (lane == 0) piece_len[i] = (uint32_t)len;
+}
+
+// one warp per aggregate: stream offsets of this window's pieces, new end of the generated text
+__global__ void __launch_bounds__(128) agw_layout_kernel(const uint32_t* __restrict__ piece_len, const unsigned long long* __restrict__ win_off,
+                                                          const unsigned long long* __restrict__ agg_off, size_t n_aggs, uint8_t dst0,
+                                                          unsigned long long* __restrict__ text_pos, unsigned long long* __restrict__ piece_off,
+                                                          unsigned long long* __restrict__ wend, uint8_t* __restrict__ ring, size_t ring_cap) {
+    const int lane = threadIdx.x & 31;
+    const size_t j = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (j >= n_aggs) return;
+    unsigned long long pos = text_pos[j];
+    if (agg_off[j + 1] == agg_off[j] && pos == 0) {   // "[]"
+        if (lane == 0) { uint8_t* r = ring + j * ring_cap; r[0] = dst0; r[1] = 2; r[2] = ','; r[3] = '['; r[4] = ']'; }
+        pos = 5;
+    }
+    const size_t lo = win_off[j], hi = win_off[j + 1];
+    for (size_t base = lo; base < hi; base += 32) {
+        const size_t p = base + lane;
+        const unsigned long long v = p < hi ? piece_len[p] : 0;
+        unsigned long long x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (p < hi) piece_off[p] = pos + x - v;
+        pos += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane == 0) { text_pos[j] = pos; wend[j] = pos; }
+}
+
+// dst and src are congruent mod 16; bytes outside [dst, dst + len) are never written (neighbouring pieces are written concurrently)
+__device__ __forceinline__ void copy_congruent(uint8_t* __restrict__ dst, const uint8_t* src, int len, int lane) {
+    int head = (int)((16 - ((size_t)dst & 15)) & 15);
+    if (head > len) head = len;
+    if (lane < head) dst[lane] = src[lane];
+    const int n16 = (len - head) >> 4;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+    uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+    for (int k = lane; k < n16; k += 32) d4[k] = s4[k];
+    const int done = head + 16 * n16;
+    if (lane < len - done) dst[done + lane] = src[done + lane];
+}
+
+__global__ void __launch_bounds__(FMT_WARPS * 32) agw_format_kernel(int level, int d, uint8_t dst0, const int32_t* __restrict__ vk_l,
+                                                                     const int32_t* __restrict__ vk_r, const uint8_t* __restrict__ digests,
+                                                                     const int32_t* __restrict__ c_hat, const unsigned long long* __restrict__ win_off,
+                                                                     const uint32_t* __restrict__ agg_of, const unsigned long long* __restrict__ agg_off,
+                                                                     size_t n_win, uint32_t w0, const unsigned long long* __restrict__ piece_off,
+                                                                     const uint32_t* __restrict__ piece_len, uint8_t* __restrict__ ring, size_t ring_cap) {
+    extern __shared__ __align__(16) uint8_t fsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const FmtConst& fc = c_fmt[level];
+    for (size_t i = (size_t)blockIdx.x * FMT_WARPS + warp; i < n_win; i += (size_t)gridDim.x * FMT_WARPS) {
+        const uint32_t j = agg_of[i];
+        const unsigned long long rank = w0 + (i - win_off[j]), total = agg_off[j + 1] - agg_off[j];
+        const unsigned long long off = piece_off[i];
+        uint8_t* buf = fsm + (size_t)warp * AGW_SMEM_PER_WARP + (off & 15);   // congruent to the ring position mod 16
+        int o = 0;
+        if (rank == 0) {
+            if (lane == 0) { buf[0] = dst0; buf[1] = 2; buf[2] = ','; buf[3] = '['; buf[4] = '('; }
+            o = 5;
+        } else {
+            if (lane == 0) { buf[0] = ','; buf[1] = ' '; buf[2] = '('; }
+            o = 3;
+        }
+        const char h1[] = "OneTimeVerificationKey(left_vk_hat=";
+        const char h2[] = ", right_vk_hat=";
+        o += put_str(buf + o, h1, 35, lane);
+        o += warp_format_gm1(buf + o, fc, vk_l + i * d, d, lane);
+        o += put_str(buf + o, h2, 15, lane);
+        o += warp_format_gm1(buf + o, fc, vk_r + i * d, d, lane);
+        if (lane == 0) { buf[o] = ')'; buf[o + 1] = ','; buf[o + 2] = ' '; }
+        o += 3;
+        __syncwarp();
+        int li = 0;
+        if (lane == 0) li = format_le256(buf + o, digests + i * 32);
+        li = __shfl_sync(0xffffffffu, li, 0);
+        o += li;
+        const char h3[] = ", SignatureChallenge(c_hat=";
+        o += put_str(buf + o, h3, 27, lane);
+        o += warp_format_poly(buf + o, fc, c_hat + i * d, d, lane);
+        if (lane == 0) { buf[o] = ')'; buf[o + 1] = ')'; buf[o + 2] = ']'; }
+        o += 2 + (rank + 1 == total ? 1 : 0);
+        __syncwarp();
+        // o == piece_len[i] by construction (checked in debug builds through the tests' parity with the streaming sponge)
+        uint8_t* rj = ring + (size_t)j * ring_cap;
+        const size_t start = (size_t)(off % ring_cap);
+        const int seg1 = (size_t)o <= ring_cap - start ? o : (int)(ring_cap - start);
+        copy_congruent(rj + start, buf, seg1, lane);
+        if (o > seg1) copy_congruent(rj, buf + seg1, o - seg1, lane);   // ring_cap is a multiple of 16: still congruent
+        (void)piece_len;
+        __syncwarp();
+    }
+}
+
+// decode_bytes_to_agg_coefs (fusion.py:594-629) for a window: one warp per signer, n_ag squeezed bytes each, taken from the
+// per-aggregate XOF buffer the sponge chain wrote (signer r of the window starts bpos[j] + r * n_ag bytes into it)
+__global__ void __launch_bounds__(128) agw_decode_kernel(const uint8_t* __restrict__ xof, size_t xof_cap, const uint32_t* __restrict__ bpos,
+                                                          const unsigned long long* __restrict__ win_off, const uint32_t* __restrict__ agg_of, size_t n_win,
+                                                          int d, int weight, int bpc, int bpi, uint32_t n_ag, int32_t* __restrict__ coef_out) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    const int L = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t i = (size_t)blockIdx.x * 4 + warp;
+    if (i >= n_win) return;
+    const int per_warp = (((int)n_ag + 32 + 15) & ~15) + 256 + 256;
+    uint8_t* xs = dsm + (size_t)warp * per_warp;
+    int8_t* cf = reinterpret_cast<int8_t*>(xs + (((int)n_ag + 32 + 15) & ~15));
+    int* jdraw = reinterpret_cast<int*>(cf + 256);
+    const uint32_t j = agg_of[i];
+    const uint8_t* src = xof + (size_t)j * xof_cap + bpos[j] + (size_t)(i - win_off[j]) * n_ag;
+    const int shift = (int)((size_t)src & 15);
+    {   // aligned 16-byte loads covering [src, src + n_ag)
+        const uint4* s4 = reinterpret_cast<const uint4*>(src - shift);
+        const int n16 = (shift + (int)n_ag + 15) >> 4;
+        uint4* x4 = reinterpret_cast<uint4*>(xs);
+        for (int k = L; k < n16; k += 32) x4[k] = __ldg(s4 + k);
+    }
+    __syncwarp();
+    const uint8_t* x = xs + shift;
+    const int bfs = (weight + 7) / 8;
+    for (int k = L; k < d; k += 32) {
+        int v = 0;
+        if (k < weight) v = 2 * ((x[bfs - 1 - k / 8] >> (k % 8)) & 1) - 1;
+        cf[k] = (int8_t)v;
+    }
+    const int n_swaps = weight < d ? d - 1 - weight : 0;
+    const int first = bfs + bpc * weight;
+    // index draws whose bytes exist (possibly truncated); the others see b"" -> 0 (quirk Q4)
+    const int n_full = (int)n_ag > first ? ((int)n_ag - first + bpi - 1) / bpi : 0;
+    const int n_draw = n_full < n_swaps ? n_full : n_swaps;
+    for (int t = L; t < n_draw; t += 32) {
+        const int idx = d - 1 - t;
+        const uint32_t m = (uint32_t)(idx + 1), mg = c_magic[m];
+        uint32_t acc = 0;
+        const int s0 = first + t * bpi;
+        const int e0 = min(s0 + bpi, (int)n_ag);
+        for (int q = s0; q < e0; ++q) {
+            const uint32_t v = (acc << 8) | x[q];
+            acc = v - __umulhi(v, mg) * m;
+        }
+        jdraw[t] = (int)acc;
+    }
+    __syncwarp();
+    if (L == 0) {
+        for (int t = 0; t < n_swaps; ++t) {
+            const int idx = d - 1 - t;
+            const int jj = t < n_draw ? jdraw[t] : 0;
+            const int8_t tmp = cf[idx]; cf[idx] = cf[jj]; cf[jj] = tmp;
+        }
+    }
+    __syncwarp();
+    int32_t* o = coef_out + i * d;
+    for (int k = L; k < d; k += 32) o[k] = (int32_t)cf[k];
+}
+
 // ------------------------------------------------------------------------------------------ host
 int hash_init_tables(fz_ctx* ctx) {
     FmtConst h[2];
@@ -602,6 +798,47 @@ int launch_shake_ag(const fz_ctx* ctx, const uint8_t* msgs, size_t msg_stride, c
     if (n_aggs == 0) return 0;
     shake_ag_kernel<<<grid_for(n_aggs, 32), 32, 0, st>>>(msgs, msg_stride, msg_len, agg_off, (uint32_t)ctx->n_ag, xof, n_aggs);
     return check(cudaGetLastError(), "shake_ag launch");
+}
+
+size_t agw_max_piece() { return (size_t)FMT_SMEM_PER_WARP + 8; }
+
+int launch_agw_text(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, const int32_t* c_hat, const unsigned long long* win_off,
+                    const uint32_t* agg_of, const unsigned long long* agg_off, size_t n_aggs, size_t n_win, uint32_t w0, unsigned long long* text_pos,
+                    uint32_t* piece_len, unsigned long long* piece_off, unsigned long long* wend, uint8_t* ring, size_t ring_cap, cudaStream_t st) {
+    if (n_aggs == 0) return 0;
+    const int level = ctx->secpar == 256 ? 1 : 0;
+    const uint8_t dst0 = (uint8_t)(ctx->secpar == 256 ? 3 : 1);
+    if (n_win) {
+        agw_len_kernel<<<(unsigned)((n_win + 3) / 4), 128, 0, st>>>(level, ctx->d, vk_l, vk_r, digests, c_hat, win_off, agg_of, agg_off, n_win, w0, piece_len);
+        if (check(cudaGetLastError(), "agw_len launch")) return -2;
+    }
+    agw_layout_kernel<<<(unsigned)((n_aggs + 3) / 4), 128, 0, st>>>(piece_len, win_off, agg_off, n_aggs, dst0, text_pos, piece_off, wend, ring, ring_cap);
+    if (check(cudaGetLastError(), "agw_layout launch")) return -2;
+    if (n_win) {
+        static bool attr = false;
+        const int smem = FMT_WARPS * AGW_SMEM_PER_WARP;
+        if (!attr) {
+            if (check(cudaFuncSetAttribute(agw_format_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "agw_format smem attr")) return -2;
+            attr = true;
+        }
+        size_t blocks = (n_win + FMT_WARPS - 1) / FMT_WARPS;
+        const size_t cap = (size_t)ctx->sm_count * 16;
+        if (blocks > cap) blocks = cap;
+        agw_format_kernel<<<(unsigned)blocks, FMT_WARPS * 32, smem, st>>>(level, ctx->d, dst0, vk_l, vk_r, digests, c_hat, win_off, agg_of, agg_off, n_win, w0,
+                                                                          piece_off, piece_len, ring, ring_cap);
+        if (check(cudaGetLastError(), "agw_format launch")) return -2;
+    }
+    return 0;
+}
+
+int launch_agw_decode(const fz_ctx* ctx, const uint8_t* xof, size_t xof_cap, const uint32_t* bpos, const unsigned long long* win_off, const uint32_t* agg_of,
+                      size_t n_win, int32_t* coef_out, cudaStream_t st) {
+    if (n_win == 0) return 0;
+    const int per_warp = ((ctx->n_ag + 32 + 15) & ~15) + 256 + 256;
+    const int smem = 4 * per_warp;   // <= 18 KiB at either level: below the default dynamic shared memory limit
+    agw_decode_kernel<<<(unsigned)((n_win + 3) / 4), 128, smem, st>>>(xof, xof_cap, bpos, win_off, agg_of, n_win, ctx->d, ctx->omega_ag, ctx->bytes_coef,
+                                                                      ctx->bytes_idx, (uint32_t)ctx->n_ag, coef_out);
+    return check(cudaGetLastError(), "agw_decode launch");
 }
 
 }  // namespace fz

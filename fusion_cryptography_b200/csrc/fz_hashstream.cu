@@ -340,7 +340,8 @@ struct __align__(16) AgState {
     uint32_t produced;          // signers whose coefficient polynomial has been squeezed
     uint32_t bpos;              // squeeze phase: bytes of the current block (lanes 0..16 of a) already handed out
     uint32_t phase;             // 0 absorbing, 1 squeezing
-    uint32_t pad[20];
+    unsigned long long rpos;    // ring-fed absorb (fz_hash.cu agw_*): message bytes absorbed so far (a multiple of 136 until closing)
+    uint32_t pad[18];
 };
 static_assert(sizeof(AgState) == 512, "AgState layout");
 
@@ -351,6 +352,7 @@ __global__ void ag_state_init_kernel(AgState* __restrict__ st, const unsigned lo
     for (int k = 0; k < 25; ++k) s->a[k] = 0;
     for (int k = 0; k < 26; ++k) s->q[k] = 0;
     s->nq = 0; s->absorbed = 0; s->total = (uint32_t)(agg_off[j + 1] - agg_off[j]); s->produced = 0; s->bpos = 0; s->phase = 0;
+    s->rpos = 0;
 }
 
 // one thread per aggregate: absorbs the signers [win_off[j], win_off[j+1]) of this window (the next ones in sorted order)
@@ -482,6 +484,102 @@ __global__ void __launch_bounds__(32) hash_ag_squeeze_thread_kernel(AgState* __r
     for (int k = 0; k < 25; ++k) s->a[k] = a[k];
     s->bpos = (uint32_t)bpos;
     s->produced += (uint32_t)(hi - lo);
+}
+
+// ---------------------------------------------------------------------------------- ring-fed chain (thread per aggregate)
+// The text of the window is already in the aggregate's byte ring (fz_hash.cu agw_format_kernel): the chain only loads the
+// 17 lanes of each block (the next block's loads are issued before the permutation of the current one) and permutes.
+__global__ void __launch_bounds__(32) agw_absorb_thread_kernel(AgState* __restrict__ st, const uint8_t* __restrict__ ring, size_t ring_cap,
+                                                                const unsigned long long* __restrict__ wend, const unsigned long long* __restrict__ win_off,
+                                                                size_t n_aggs) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_aggs) return;
+    AgState* s = st + j;
+    if (s->phase != 0) return;
+    const uint32_t absorbed = s->absorbed + (uint32_t)(win_off[j + 1] - win_off[j]);
+    const bool closing = absorbed == s->total;
+    unsigned long long rpos = s->rpos;
+    const unsigned long long end = wend[j];
+    s->absorbed = absorbed;
+    if (rpos + KECCAK_RATE > end && !closing) return;
+    unsigned long long a[25];
+#pragma unroll
+    for (int k = 0; k < 25; ++k) a[k] = s->a[k];
+    const unsigned long long* base = reinterpret_cast<const unsigned long long*>(ring + j * ring_cap);
+    unsigned long long nxt[KECCAK_RATE_LANES];
+    bool have = rpos + KECCAK_RATE <= end;
+    if (have) {
+        const unsigned long long* b = base + (rpos % ring_cap) / 8;
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) nxt[k] = __ldcs(b + k);
+    }
+    while (have) {
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) a[k] ^= nxt[k];
+        rpos += KECCAK_RATE;
+        have = rpos + KECCAK_RATE <= end;
+        if (have) {
+            const unsigned long long* b = base + (rpos % ring_cap) / 8;
+#pragma unroll
+            for (int k = 0; k < KECCAK_RATE_LANES; ++k) nxt[k] = __ldcs(b + k);
+        }
+        keccak_f(a);
+    }
+    if (closing) {   // last (partial) block with SHAKE padding; rem < 136
+        const uint32_t rem = (uint32_t)(end - rpos);
+        const unsigned long long* b = base + (rpos % ring_cap) / 8;
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) {
+            unsigned long long w = 0;
+            if ((uint32_t)(8 * k) < rem) {
+                w = b[k];
+                const uint32_t valid = rem - 8 * k;
+                if (valid < 8) w &= (1ULL << (8 * valid)) - 1ULL;
+            }
+            if ((rem >> 3) == (uint32_t)k) w ^= 0x1FULL << (8 * (rem & 7));
+            if (k == 16) w ^= 0x8000000000000000ULL;
+            a[k] ^= w;
+        }
+        keccak_f(a);
+        rpos = end;
+        s->phase = 1;
+        s->bpos = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < 25; ++k) s->a[k] = a[k];
+    s->rpos = rpos;
+}
+
+// squeezes whole blocks into the aggregate's XOF buffer: offset 0 is the start of the sponge's current block, the window's
+// bytes begin bpos_out[j] bytes into it (signer r of the window at bpos_out[j] + r * n_ag)
+__global__ void __launch_bounds__(32) agw_squeeze_thread_kernel(AgState* __restrict__ st, const unsigned long long* __restrict__ win_off, size_t n_aggs,
+                                                                 uint32_t n_ag, uint8_t* __restrict__ xof, size_t xof_cap, uint32_t* __restrict__ bpos_out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_aggs) return;
+    AgState* s = st + j;
+    const unsigned long long cnt = win_off[j + 1] - win_off[j];
+    if (cnt == 0 || s->phase != 1) return;
+    unsigned long long a[25];
+#pragma unroll
+    for (int k = 0; k < 25; ++k) a[k] = s->a[k];
+    const uint32_t bpos = s->bpos;
+    bpos_out[j] = bpos;
+    unsigned long long* out = reinterpret_cast<unsigned long long*>(xof + j * xof_cap);
+    const unsigned long long need = bpos + cnt * n_ag;   // bytes counted from the start of the current block
+    unsigned long long o = 0;
+#pragma unroll
+    for (int k = 0; k < KECCAK_RATE_LANES; ++k) __stcs(out + k, a[k]);
+    while (o + KECCAK_RATE < need) {
+        keccak_f(a);
+        o += KECCAK_RATE;
+        unsigned long long* ob = out + o / 8;
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) __stcs(ob + k, a[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 25; ++k) s->a[k] = a[k];
+    s->bpos = (uint32_t)(need - o);
+    s->produced += (uint32_t)cnt;
 }
 
 // ---------------------------------------------------------------------------------- host
@@ -857,6 +955,88 @@ __global__ void __launch_bounds__(WARPS * 32) hash_ag_squeeze_warp_kernel(AgStat
     if (L == 0) { s->bpos = (uint32_t)blk_used; s->produced += (uint32_t)(p1 - p0); }
 }
 
+// ring-fed chain, one warp per aggregate: lanes 0..16 load the block (prefetched one block ahead)
+__global__ void __launch_bounds__(32) agw_absorb_warp_kernel(AgState* __restrict__ st, const uint8_t* __restrict__ ring, size_t ring_cap,
+                                                                      const unsigned long long* __restrict__ wend,
+                                                                      const unsigned long long* __restrict__ win_off, size_t n_aggs) {
+    const int L = threadIdx.x & 31;
+    const size_t j = blockIdx.x;   // one warp per CTA: the chains spread evenly over the SMs
+    if (j >= n_aggs) return;
+    AgState* s = st + j;
+    if (s->phase != 0) return;
+    const uint32_t absorbed = s->absorbed + (uint32_t)(win_off[j + 1] - win_off[j]);
+    const bool closing = absorbed == s->total;
+    unsigned long long rpos = s->rpos;
+    const unsigned long long end = wend[j];
+    __syncwarp();
+    if (L == 0) s->absorbed = absorbed;
+    if (rpos + KECCAK_RATE > end && !closing) return;
+    const Lane c = lane_init(L);
+    uint32_t lo = 0, hi = 0;
+    if (L < 25) { const unsigned long long v = s->a[L]; lo = (uint32_t)v; hi = (uint32_t)(v >> 32); }
+    const uint8_t* rj = ring + j * ring_cap;
+    bool have = rpos + KECCAK_RATE <= end;
+    uint2 nxt = make_uint2(0u, 0u);
+    if (have && L < KECCAK_RATE_LANES) nxt = __ldcs(reinterpret_cast<const uint2*>(rj + (rpos % ring_cap)) + L);
+    while (have) {
+        lo ^= nxt.x;
+        hi ^= nxt.y;
+        rpos += KECCAK_RATE;
+        have = rpos + KECCAK_RATE <= end;
+        nxt = make_uint2(0u, 0u);
+        if (have && L < KECCAK_RATE_LANES) nxt = __ldcs(reinterpret_cast<const uint2*>(rj + (rpos % ring_cap)) + L);
+        keccak_f_warp(lo, hi, c, L);
+    }
+    if (closing) {
+        const uint32_t rem = (uint32_t)(end - rpos);
+        if (L < KECCAK_RATE_LANES) {
+            unsigned long long w = 0;
+            if ((uint32_t)(8 * L) < rem) {
+                w = *(reinterpret_cast<const unsigned long long*>(rj + (rpos % ring_cap)) + L);
+                const uint32_t valid = rem - 8 * L;
+                if (valid < 8) w &= (1ULL << (8 * valid)) - 1ULL;
+            }
+            if ((rem >> 3) == (uint32_t)L) w ^= 0x1FULL << (8 * (rem & 7));
+            if (L == 16) w ^= 0x8000000000000000ULL;
+            lo ^= (uint32_t)w;
+            hi ^= (uint32_t)(w >> 32);
+        }
+        keccak_f_warp(lo, hi, c, L);
+        rpos = end;
+        if (L == 0) { s->phase = 1; s->bpos = 0; }
+    }
+    if (L < 25) s->a[L] = ((unsigned long long)hi << 32) | lo;
+    if (L == 0) s->rpos = rpos;
+}
+
+__global__ void __launch_bounds__(32) agw_squeeze_warp_kernel(AgState* __restrict__ st, const unsigned long long* __restrict__ win_off, size_t n_aggs,
+                                                                       uint32_t n_ag, uint8_t* __restrict__ xof, size_t xof_cap,
+                                                                       uint32_t* __restrict__ bpos_out) {
+    const int L = threadIdx.x & 31;
+    const size_t j = blockIdx.x;
+    if (j >= n_aggs) return;
+    AgState* s = st + j;
+    const unsigned long long cnt = win_off[j + 1] - win_off[j];
+    if (cnt == 0 || s->phase != 1) return;
+    const Lane c = lane_init(L);
+    uint32_t lo = 0, hi = 0;
+    if (L < 25) { const unsigned long long v = s->a[L]; lo = (uint32_t)v; hi = (uint32_t)(v >> 32); }
+    const uint32_t bpos = s->bpos;
+    __syncwarp();
+    if (L == 0) bpos_out[j] = bpos;
+    uint2* out = reinterpret_cast<uint2*>(xof + j * xof_cap);
+    const unsigned long long need = bpos + cnt * n_ag;
+    unsigned long long o = 0;
+    if (L < KECCAK_RATE_LANES) __stcs(out + L, make_uint2(lo, hi));
+    while (o + KECCAK_RATE < need) {
+        keccak_f_warp(lo, hi, c, L);
+        o += KECCAK_RATE;
+        if (L < KECCAK_RATE_LANES) __stcs(out + o / 8 + L, make_uint2(lo, hi));
+    }
+    if (L < 25) s->a[L] = ((unsigned long long)hi << 32) | lo;
+    if (L == 0) { s->bpos = (uint32_t)(need - o); s->produced += (uint32_t)cnt; }
+}
+
 }  // namespace warpag
 
 size_t ag_state_bytes() { return sizeof(AgState); }
@@ -912,6 +1092,26 @@ int launch_hash_ag_squeeze(const fz_ctx* ctx, void* state, const unsigned long l
                                                                                  ctx->bytes_idx, (uint32_t)ctx->n_ag, coef_out);
     }
     return check(cudaGetLastError(), "hash_ag squeeze launch");
+}
+
+int launch_agw_absorb(const fz_ctx* ctx, void* state, const uint8_t* ring, size_t ring_cap, const unsigned long long* wend,
+                      const unsigned long long* win_off, size_t n_aggs, cudaStream_t st) {
+    if (n_aggs == 0) return 0;
+    if (use_warp(ctx, n_aggs))
+        warpag::agw_absorb_warp_kernel<<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
+    else
+        agw_absorb_thread_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
+    return check(cudaGetLastError(), "agw_absorb launch");
+}
+
+int launch_agw_squeeze(const fz_ctx* ctx, void* state, const unsigned long long* win_off, size_t n_aggs, uint8_t* xof, size_t xof_cap, uint32_t* bpos_out,
+                       cudaStream_t st) {
+    if (n_aggs == 0) return 0;
+    if (use_warp(ctx, n_aggs))
+        warpag::agw_squeeze_warp_kernel<<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
+    else
+        agw_squeeze_thread_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
+    return check(cudaGetLastError(), "agw_squeeze launch");
 }
 
 }  // namespace fz

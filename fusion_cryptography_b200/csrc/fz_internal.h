@@ -66,6 +66,18 @@ int launch_hash_ag_absorb(const fz_ctx* ctx, void* state, const int32_t* vk_l_s,
                           const unsigned long long* win_off, size_t n_aggs, cudaStream_t st);
 int launch_hash_ag_squeeze(const fz_ctx* ctx, void* state, const unsigned long long* win_off, size_t n_aggs, int32_t* coef_out, cudaStream_t st);
 
+int launch_agw_absorb(const fz_ctx* ctx, void* state, const uint8_t* ring, size_t ring_cap, const unsigned long long* wend,
+                      const unsigned long long* win_off, size_t n_aggs, cudaStream_t st);
+int launch_agw_squeeze(const fz_ctx* ctx, void* state, const unsigned long long* win_off, size_t n_aggs, uint8_t* xof, size_t xof_cap, uint32_t* bpos_out,
+                       cudaStream_t st);
+// fz_hash.cu (windowed text / decode)
+size_t agw_max_piece();
+int launch_agw_text(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, const int32_t* c_hat, const unsigned long long* win_off,
+                    const uint32_t* agg_of, const unsigned long long* agg_off, size_t n_aggs, size_t n_win, uint32_t w0, unsigned long long* text_pos,
+                    uint32_t* piece_len, unsigned long long* piece_off, unsigned long long* wend, uint8_t* ring, size_t ring_cap, cudaStream_t st);
+int launch_agw_decode(const fz_ctx* ctx, const uint8_t* xof, size_t xof_cap, const uint32_t* bpos, const unsigned long long* win_off, const uint32_t* agg_of,
+                      size_t n_win, int32_t* coef_out, cudaStream_t st);
+
 // fz_sample.cu
 int sample_init_tables(fz_ctx* ctx);
 int launch_sample(const fz_ctx* ctx, int mode, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, uint32_t bound, int weight,

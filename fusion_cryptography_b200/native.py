@@ -444,6 +444,51 @@ def verify_finish(self, A, target, agg) -> torch.Tensor:
     return codes
 
 
+# ---- ring-fed windowed aggregation hash: text generation and decoding off the serial chain --------------------
+def hash_ag_ring(self, n_aggs: int, max_window: int):
+    """(ring, ring_cap, text_pos): per-aggregate byte rings for windows of <= max_window signers per aggregate."""
+    self.lib.fz_hash_ag_ring_bytes.restype = C.c_size_t
+    cap = int(self.lib.fz_hash_ag_ring_bytes(self._h, C.c_size_t(max_window)))
+    ring = torch.empty(max(n_aggs, 1) * cap, dtype=torch.uint8, device=self.device)
+    return ring, cap, torch.zeros(max(n_aggs, 1), dtype=torch.int64, device=self.device)
+
+
+def hash_ag_xof_buffer(self, n_aggs: int, max_window: int):
+    self.lib.fz_hash_ag_xof_bytes.restype = C.c_size_t
+    cap = int(self.lib.fz_hash_ag_xof_bytes(self._h, C.c_size_t(max_window)))
+    return torch.empty(max(n_aggs, 1) * cap, dtype=torch.uint8, device=self.device), cap
+
+
+def hash_ag_text(self, vk_l_w, vk_r_w, dg_w, c_hat_w, win_off, agg_of, agg_off, n_aggs: int, n_window: int, w0: int, text_pos, ring, ring_cap: int):
+    """Writes the text window w0 adds to every aggregate's message into the rings; returns the message lengths after it."""
+    self.lib.fz_hash_ag_text_workspace.restype = C.c_size_t
+    ws = self._ws(self.lib.fz_hash_ag_text_workspace(self._h, C.c_size_t(n_window)))
+    wend = torch.empty(max(n_aggs, 1), dtype=torch.int64, device=self.device)
+    self._chk(self.lib.fz_hash_ag_text(self._h, _ptr(vk_l_w), _ptr(vk_r_w), _ptr(dg_w), _ptr(c_hat_w), _ptr(win_off), _ptr(agg_of), _ptr(agg_off),
+                                       C.c_size_t(n_aggs), C.c_size_t(n_window), C.c_uint32(w0), _ptr(text_pos), _ptr(ring), C.c_size_t(ring_cap), _ptr(wend),
+                                       _ptr(ws), C.c_size_t(ws.numel()), self._stream()))
+    return wend
+
+
+def hash_ag_absorb_ring(self, state, ring, ring_cap: int, wend, win_off, n_aggs: int) -> None:
+    self._chk(self.lib.fz_hash_ag_absorb_ring(self._h, _ptr(state), _ptr(ring), C.c_size_t(ring_cap), _ptr(wend), _ptr(win_off), C.c_size_t(n_aggs),
+                                              self._stream()))
+
+
+def hash_ag_squeeze_xof(self, state, win_off, n_aggs: int, xof, xof_cap: int) -> torch.Tensor:
+    bpos = torch.empty(max(n_aggs, 1), dtype=torch.int32, device=self.device)
+    self._chk(self.lib.fz_hash_ag_squeeze_xof(self._h, _ptr(state), _ptr(win_off), C.c_size_t(n_aggs), _ptr(xof), C.c_size_t(xof_cap), _ptr(bpos),
+                                              self._stream()))
+    return bpos
+
+
+def hash_ag_decode(self, xof, xof_cap: int, bpos, win_off, agg_of, n_window: int) -> torch.Tensor:
+    out = torch.empty((n_window, self.d), dtype=torch.int32, device=self.device)
+    self._chk(self.lib.fz_hash_ag_decode(self._h, _ptr(xof), C.c_size_t(xof_cap), _ptr(bpos), _ptr(win_off), _ptr(agg_of), C.c_size_t(n_window), _ptr(out),
+                                         self._stream()))
+    return out
+
+
 def _seed_keys(self, seeds):
     """Python ints (any sign, up to 256 bits) -> ([n, 8] uint32 limbs, [n] int32 limb counts) on the device."""
     import numpy as np
@@ -514,5 +559,6 @@ def sign_mac_rows(self, sk_hat, c_hat, out=None) -> torch.Tensor:
 
 for _f in (_u8, _pack_messages, pack_messages, _ws, sha3_256, shake256, hash_msg, format_text, decode_poly, hash_ch, _agg_off, hash_ag, sort_keys, gather_sorted,
            aggregate_sum, fold_partials, verify_check, hash_ag_begin, hash_ag_absorb, hash_ag_squeeze, aggregate_sum_off,
-           verify_target, verify_finish, _seed_keys, sample_coef, sample_ntt, keygen, sign_mac_rows):
+           verify_target, verify_finish, hash_ag_ring, hash_ag_xof_buffer, hash_ag_text, hash_ag_absorb_ring, hash_ag_squeeze_xof,
+           hash_ag_decode, _seed_keys, sample_coef, sample_ntt, keygen, sign_mac_rows):
     setattr(Context, _f.__name__, _f)

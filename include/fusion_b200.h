@@ -98,6 +98,25 @@ int fz_hash_ag_begin(fz_ctx* ctx, void* state, const uint64_t* agg_off, size_t n
 int fz_hash_ag_absorb(fz_ctx* ctx, void* state, const int32_t* vk_l_w, const int32_t* vk_r_w, const uint8_t* dg_w, const int32_t* c_hat_w,
                       const uint64_t* win_off, size_t n_aggs, void* stream);
 int fz_hash_ag_squeeze(fz_ctx* ctx, void* state, const uint64_t* win_off, size_t n_aggs, size_t n_window, int32_t* alpha_hat_w, void* stream);
+/* The same windowed hash with everything but the permutations taken off the serial chain: the text a window adds to each
+ * message (str() of fusion.py:586-590) is written, a warp per signer, into a byte ring per aggregate (n_aggs * ring_cap
+ * bytes, ring_cap = fz_hash_ag_ring_bytes(P) for windows of <= P signers per aggregate; text_pos: n_aggs running byte
+ * counts, zero-initialised; wend_out: n_aggs message lengths after this window); the chain absorbs ring blocks up to wend;
+ * squeezed blocks go to a per-aggregate XOF buffer (xof_cap = fz_hash_ag_xof_bytes(P)) which fz_hash_ag_decode turns into
+ * the window's coefficients (fusion.py:594-629 + NTT).  Window w0 holds the sorted positions w0.. of every aggregate;
+ * agg_of[i] is the aggregate of window entry i.  Text of window w+2 may only be written once window w has been absorbed. */
+size_t fz_hash_ag_ring_bytes(const fz_ctx* ctx, size_t max_window);
+size_t fz_hash_ag_xof_bytes(const fz_ctx* ctx, size_t max_window);
+size_t fz_hash_ag_text_workspace(const fz_ctx* ctx, size_t n_window);
+int fz_hash_ag_text(fz_ctx* ctx, const int32_t* vk_l_w, const int32_t* vk_r_w, const uint8_t* dg_w, const int32_t* c_hat_w, const uint64_t* win_off,
+                    const uint32_t* agg_of, const uint64_t* agg_off, size_t n_aggs, size_t n_window, uint32_t w0, uint64_t* text_pos, uint8_t* ring,
+                    size_t ring_cap, uint64_t* wend_out, void* ws, size_t ws_bytes, void* stream);
+int fz_hash_ag_absorb_ring(fz_ctx* ctx, void* state, const uint8_t* ring, size_t ring_cap, const uint64_t* wend, const uint64_t* win_off, size_t n_aggs,
+                           void* stream);
+int fz_hash_ag_squeeze_xof(fz_ctx* ctx, void* state, const uint64_t* win_off, size_t n_aggs, uint8_t* xof, size_t xof_cap, uint32_t* bpos_out,
+                           void* stream);
+int fz_hash_ag_decode(fz_ctx* ctx, const uint8_t* xof, size_t xof_cap, const uint32_t* bpos, const uint64_t* win_off, const uint32_t* agg_of,
+                      size_t n_window, int32_t* alpha_hat_w, void* stream);
 
 /* ---- aggregate / verify ------------------------------------------------------------------------------- */
 /* sorted(zip(...), key=lambda x: str(x[0])) at fusion.py:661-663 and :693.  sel (optional) maps a position to a row of
