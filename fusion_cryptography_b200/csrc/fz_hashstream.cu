@@ -303,23 +303,66 @@ __global__ void __launch_bounds__(HS_THREADS) hash_ch_stream_kernel(const int32_
             break;
         }
     }
-    int32_t c[256];
+    // ---- squeeze + decode (fusion.py:422-481 with bound = 1: every magnitude is 1, its bytes are skipped) ----
+    // The squeezed stream has the same layout for every signer: bfs signum bytes, weight * bpc magnitude bytes, then one
+    // bpi-byte big-endian integer per Fisher-Yates draw (i = d-1 down to weight+1), so all threads walk it in lock step.
+    // Each block is staged in shared memory ([word][thread]: conflict-free) and every draw is reduced mod (i + 1) two
+    // bytes per step: acc < 256, so acc * 2^16 + 2 bytes < 2^24 and the reciprocal multiplication is exact.
+    __shared__ uint32_t blk_sm[2 * KECCAK_RATE_LANES * HS_THREADS];
+    int8_t c[256];
     for (int k = 0; k < d; ++k) c[k] = 0;
-    Dec s;
-    dinit(s, c, d, weight, 1u, bpc, bpi);
-    uint32_t produced = 0;
-    while (produced < n_used && s.phase != 3) {
-        unsigned long long blk[KECCAK_RATE_LANES];
+    const int bfs = (weight + 7) / 8;
+    const int first = bfs + bpc * weight;                 // first byte of the index draws
+    const int n_swaps = weight < d ? d - 1 - weight : 0;
+    uint32_t* my = blk_sm + threadIdx.x;
+    const uint8_t* myb = reinterpret_cast<const uint8_t*>(my);
+    int t = 0, rem = bpi;                                 // current draw and its bytes still to come
+    uint32_t acc = 0, m = (uint32_t)d, mg = c_magic2[m <= 256 ? m : 0];
+    for (uint32_t base = 0; base < n_used; base += KECCAK_RATE) {
+        if (base) keccak_f(a);
 #pragma unroll
-        for (int k = 0; k < KECCAK_RATE_LANES; ++k) blk[k] = a[k];
-        const uint32_t take = n_used - produced < (uint32_t)KECCAK_RATE ? n_used - produced : (uint32_t)KECCAK_RATE;
-        for (uint32_t j = 0; j < take && s.phase != 3; ++j) dbyte(s, c, (uint32_t)(blk[j >> 3] >> (8 * (j & 7))) & 0xffu);
-        produced += take;
-        if (produced < n_used && s.phase != 3) keccak_f(a);
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) {
+            my[(2 * k) * HS_THREADS] = (uint32_t)a[k];
+            my[(2 * k + 1) * HS_THREADS] = (uint32_t)(a[k] >> 32);
+        }
+        // byte o of the block is at myb[(o >> 2) * 4 * HS_THREADS + (o & 3)]
+#define BLKB(o) ((uint32_t)myb[((o) >> 2) * (4 * HS_THREADS) + ((o) & 3)])
+        if (base == 0) {
+            // signums: bit i (LSB first) of the big-endian integer of the first bfs bytes (bfs <= 32 < 136)
+            for (int k = 0; k < weight && k < d; ++k) c[k] = (int8_t)(2 * (int)((BLKB(bfs - 1 - (k >> 3)) >> (k & 7)) & 1u) - 1);
+        }
+        int pos = (int)base < first ? first - (int)base : 0;   // skip signums / magnitudes
+        const int lim = (int)(n_used - base) < KECCAK_RATE ? (int)(n_used - base) : KECCAK_RATE;
+        while (pos < lim && t < n_swaps) {
+            int nb = lim - pos < rem ? lim - pos : rem;
+            rem -= nb;
+            for (; nb >= 2; nb -= 2, pos += 2) {
+                const uint32_t v = (acc << 16) | (BLKB(pos) << 8) | BLKB(pos + 1);
+                acc = v - __umulhi(v, mg) * m;
+            }
+            if (nb) {
+                const uint32_t v = (acc << 8) | BLKB(pos);
+                acc = v - __umulhi(v, mg) * m;
+                ++pos;
+            }
+            if (rem == 0) {
+                const int i2 = d - 1 - t, j2 = (int)acc;
+                const int8_t tmp = c[i2]; c[i2] = c[j2]; c[j2] = tmp;
+                ++t; rem = bpi; acc = 0;
+                m = (uint32_t)(d - t); mg = c_magic2[m];
+            }
+        }
+#undef BLKB
+        if (t >= n_swaps) break;
     }
-    while (s.phase != 3) dfinish(s, c);
+    // a stream shorter than the draws need (never for hash_ch: n_used covers them) would leave truncated / empty draws
+    for (; t < n_swaps; ++t) {
+        const int i2 = d - 1 - t, j2 = rem == bpi ? 0 : (int)acc;
+        const int8_t tmp = c[i2]; c[i2] = c[j2]; c[j2] = tmp;
+        rem = bpi; acc = 0;
+    }
     int32_t* o = coef_out + i * d;
-    for (int k = 0; k < d; ++k) o[k] = c[k];
+    for (int k = 0; k < d; k += 4) *reinterpret_cast<int4*>(o + k) = make_int4(c[k], c[k + 1], c[k + 2], c[k + 3]);
 }
 
 // ---------------------------------------------------------------------------------- hash_ag
