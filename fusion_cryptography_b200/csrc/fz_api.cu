@@ -515,7 +515,7 @@ int fz_sample_ntt(fz_ctx* ctx, const uint32_t* keys, int key_stride, const int32
     return launch_sample(ctx, 1, keys, key_stride, klen, n, 0, 0, out, (cudaStream_t)stream);
 }
 
-size_t fz_keygen_workspace(const fz_ctx* ctx, size_t n) { return r256(2 * n * 4 * 4) + r256(2 * n * 4) + r256(2 * n * ctx->d * 4) + 1024; }
+size_t fz_keygen_workspace(const fz_ctx* ctx, size_t n) { return r256(2 * n * 4 * 4) + r256(2 * n * 4) + r256(2 * n * ctx->d * 4) + r256(ctx->d * 4) + 1024; }
 
 // fusion.py:338-373 for n u64 seeds (seed_i for the left key, seed_i + 1 for the right key).
 // sk_l / sk_r ([n][ell][d]) may be NULL (keys are then not materialised); sk_hat ([n][2][d], optional) receives the
@@ -527,15 +527,17 @@ int fz_keygen(fz_ctx* ctx, const int32_t* A, const uint64_t* seeds, size_t n, in
     uint32_t* keys = cv.take<uint32_t>(2 * n * 4);
     int32_t* klen = cv.take<int32_t>(2 * n);
     int32_t* tmp = sk_hat ? sk_hat : cv.take<int32_t>(2 * n * ctx->d);
+    int32_t* asum = cv.take<int32_t>(ctx->d);
     FZ_REQUIRE(cv.ok, "fz_keygen: workspace too small (see fz_keygen_workspace)");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t d = ctx->d;
     int rc = launch_seeds_to_keys(ctx, (const unsigned long long*)seeds, n, keys, klen, st);
     if (!rc) rc = launch_sample(ctx, 0, keys, 4, klen, 2 * n, 52u, ctx->d, tmp, st);   // beta_sk = 52, omega_sk = d (fusion.py:87, 90)
     if (!rc) rc = launch_ntt(ctx, 0, tmp, tmp, 2 * n, st);
-    // vk = A . sk with every row of sk equal to the sampled polynomial (row stride 0)
-    if (!rc) rc = launch_matvec(ctx, A, tmp, 0, 2 * d, vk_l, n, st);
-    if (!rc) rc = launch_matvec(ctx, A, tmp + d, 0, 2 * d, vk_r, n, st);
+    // vk = A . sk with every row of sk equal to the sampled polynomial: (sum of the rows of A) o sk   (quirk Q1; the general
+    // ell-row product is fz_matvec)
+    if (!rc) rc = launch_matvec_rows(ctx, A, asum, tmp, 2 * d, vk_l, n, st);
+    if (!rc) rc = launch_matvec_rows(ctx, A, asum, tmp + d, 2 * d, vk_r, n, st);
     if (!rc && sk_l) rc = launch_replicate_rows(ctx, tmp, sk_l, n, ctx->ell, 2 * d, st);
     if (!rc && sk_r) rc = launch_replicate_rows(ctx, tmp + d, sk_r, n, ctx->ell, 2 * d, st);
     return rc;
@@ -544,8 +546,7 @@ int fz_keygen(fz_ctx* ctx, const int32_t* A, const uint64_t* seeds, size_t n, in
 // fusion.py:557 with broadcast rows: sig[b][r] = sk_hat[b][0] * c_hat[b] + sk_hat[b][1] for every r (keys from fz_keygen's sk_hat)
 int fz_sign_mac_rows(fz_ctx* ctx, const int32_t* sk_hat, const int32_t* c_hat, int32_t* sig, size_t batch, void* stream) {
     FZ_REQUIRE(ctx && (batch == 0 || (sk_hat && c_hat && sig)), "fz_sign_mac_rows: NULL argument");
-    const size_t d = ctx->d;
-    return launch_sign_mac(ctx, sk_hat, sk_hat + d, 0, 2 * d, c_hat, sig, batch, (cudaStream_t)stream);
+    return launch_sign_rows(ctx, sk_hat, c_hat, sig, batch, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -40,6 +40,9 @@ int launch_matvec(const fz_ctx* ctx, const int32_t* A, const int32_t* s, size_t 
 int launch_sign_mac(const fz_ctx* ctx, const int32_t* sk_l, const int32_t* sk_r, size_t sk_row_stride, size_t sk_batch_stride, const int32_t* c_hat,
                     int32_t* sig, size_t batch, cudaStream_t st);
 
+int launch_sign_rows(const fz_ctx* ctx, const int32_t* sk_hat, const int32_t* c_hat, int32_t* sig, size_t batch, cudaStream_t st);
+int launch_matvec_rows(const fz_ctx* ctx, const int32_t* A, int32_t* asum, const int32_t* s, size_t s_batch_stride, int32_t* out, size_t batch,
+                       cudaStream_t st);
 
 // fz_hash.cu
 int hash_init_tables(fz_ctx* ctx);

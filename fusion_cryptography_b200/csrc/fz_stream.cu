@@ -83,6 +83,56 @@ __global__ void __launch_bounds__(256) sign_mac_kernel(const int4* __restrict__ 
     st_stream(sig + b * (size_t)per_key + i, o);
 }
 
+// Keys generated from a seed have ell IDENTICAL rows on each side (fusion.py:159-168: every entry is sampled with the same
+// seed), so their signature has ell identical rows too: one multiply-add per coefficient, ell streamed
+// stores.  sk_hat: [batch][2][d] (the one distinct row of sk_l and of sk_r), sig: [batch][ell][d].  Write-bound.
+__global__ void __launch_bounds__(256) sign_rows_kernel(const int4* __restrict__ sk_hat, const int4* __restrict__ c_hat, int4* __restrict__ sig,
+                                                          size_t batch, int ell, int d4) {
+    const size_t total = batch * (size_t)d4;
+    const int sh = 31 - __clz(d4);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = idx >> sh;
+        const int c = (int)(idx & (size_t)(d4 - 1));
+        const int4 l = __ldg(sk_hat + b * 2 * d4 + c), r = __ldg(sk_hat + b * 2 * d4 + d4 + c), ch = __ldg(c_hat + idx);
+        int4 o;
+        o.x = cent_i64((long long)l.x * ch.x + r.x);
+        o.y = cent_i64((long long)l.y * ch.y + r.y);
+        o.z = cent_i64((long long)l.z * ch.z + r.z);
+        o.w = cent_i64((long long)l.w * ch.w + r.w);
+        int4* dst = sig + b * (size_t)ell * d4 + c;
+#pragma unroll 4
+        for (int row = 0; row < ell; ++row) st_stream(dst + (size_t)row * d4, o);
+    }
+}
+
+// asum[k] = cent( sum_r A[r][k] ): with identical rows s, A . s = asum o s   (matrices.py:121-131 for a broadcast column)
+__global__ void __launch_bounds__(64) asum_kernel(const int4* __restrict__ A, int4* __restrict__ asum, int ell, int d4) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d4) return;
+    long long acc[4] = {0, 0, 0, 0};
+    for (int r = 0; r < ell; ++r) {
+        const int4 a = __ldg(A + (size_t)r * d4 + c);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    }
+    asum[c] = cent4(acc);
+}
+
+// out[b][k] = cent( asum[k] * s[b * batch_stride + k] )
+__global__ void __launch_bounds__(256) mul_bcast_kernel(const int4* __restrict__ asum, const int4* __restrict__ s, size_t batch_stride4,
+                                                          int4* __restrict__ out, size_t batch, int d4) {
+    const size_t total = batch * (size_t)d4;
+    const int sh = 31 - __clz(d4);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = idx >> sh;
+        const int c = (int)(idx & (size_t)(d4 - 1));
+        const int4 a = __ldg(asum + c), v = ld_stream(s + b * batch_stride4 + c);
+        int4 o;
+        o.x = cent_i64((long long)a.x * v.x); o.y = cent_i64((long long)a.y * v.y);
+        o.z = cent_i64((long long)a.z * v.z); o.w = cent_i64((long long)a.w * v.w);
+        out[idx] = o;
+    }
+}
+
 static int stream_grid(const fz_ctx* ctx, size_t items, int threads) {
     size_t blocks = (items + threads - 1) / threads;
     const size_t cap = (size_t)ctx->sm_count * 16;
@@ -111,6 +161,24 @@ int launch_sign_mac(const fz_ctx* ctx, const int32_t* sk_l, const int32_t* sk_r,
         if (check(cudaGetLastError(), "sign_mac launch")) return -2;
     }
     return 0;
+}
+
+int launch_sign_rows(const fz_ctx* ctx, const int32_t* sk_hat, const int32_t* c_hat, int32_t* sig, size_t batch, cudaStream_t st) {
+    if (batch == 0) return 0;
+    const int d4 = ctx->d / 4;
+    sign_rows_kernel<<<stream_grid(ctx, batch * d4, 256), 256, 0, st>>>((const int4*)sk_hat, (const int4*)c_hat, (int4*)sig, batch, ctx->ell, d4);
+    return check(cudaGetLastError(), "sign_rows launch");
+}
+
+// vk[b] = A . s[b] for s with ell identical rows: asum (d int32 of scratch) = column sums of A, then one pointwise product
+int launch_matvec_rows(const fz_ctx* ctx, const int32_t* A, int32_t* asum, const int32_t* s, size_t s_batch_stride, int32_t* out, size_t batch,
+                       cudaStream_t st) {
+    if (batch == 0) return 0;
+    const int d4 = ctx->d / 4;
+    asum_kernel<<<(d4 + 63) / 64, 64, 0, st>>>((const int4*)A, (int4*)asum, ctx->ell, d4);
+    if (check(cudaGetLastError(), "asum launch")) return -2;
+    mul_bcast_kernel<<<stream_grid(ctx, batch * d4, 256), 256, 0, st>>>((const int4*)asum, (const int4*)s, s_batch_stride / 4, (int4*)out, batch, d4);
+    return check(cudaGetLastError(), "mul_bcast launch");
 }
 
 }  // namespace fz

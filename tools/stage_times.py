@@ -7,8 +7,9 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 eng = Engine(256, seed=42); ctx = eng.ctx
 seeds = (10**6 + 2 * np.arange(n)).astype(np.uint64)
 msgs = ctx.pack_messages([f"msg-{i:07d}".encode() for i in range(n)])
-def t(fn, reps=3):
-    fn(); torch.cuda.synchronize()
+def t(fn, reps=5):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(reps): r = fn()
@@ -25,3 +26,6 @@ ms, c = t(lambda: ctx.hash_ch(kb.vk_l, kb.vk_r, dg)); print(f"hash_ch           
 sig = torch.empty((n, eng.ell, eng.d), dtype=torch.int32, device="cuda")
 ms, x = t(lambda: ctx.sign_mac_rows(kb.sk_hat, c, out=sig)); print(f"sign_mac_rows       {ms:8.3f} ms")
 ms, x = t(lambda: eng.keygen_sign(seeds, msgs, chunk=16384)); print(f"keygen_sign total   {ms:8.3f} ms  -> {n/ms*1e3/1e6:.2f} M sign/s")
+
+big = torch.empty(1 << 30, dtype=torch.int32, device="cuda")
+ms, _ = t(lambda: big.zero_()); print(f"memset 4 GiB        {ms:8.3f} ms  -> {4 * 1.073741824 / ms * 1e3:.0f} GB/s write-only")
