@@ -59,21 +59,23 @@ class Engine:
             return self.ctx.sign_mac(keys.sk_l, keys.sk_r, c_hat, out=out)   # general: ell distinct rows
         return self.ctx.sign_mac_rows(keys.sk_hat, c_hat, out=out)
 
-    def keygen_sign(self, seeds, msgs: Sequence[bytes], chunk: int = 16384, keep_sigs: bool = True):
+    def keygen_sign(self, seeds, msgs: Sequence[bytes], chunk: int = 65536, keep_sigs: bool = True):
         """BASELINE config[2]: keygen + sign of many one-time keys; secret keys never reach HBM as ell rows.
         Returns (vk_l, vk_r, sigs or None); with keep_sigs=False signatures of each chunk overwrite one buffer."""
         import numpy as np
 
         seeds = np.asarray(seeds, dtype=np.uint64)
         n = len(seeds)
-        vk_l = torch.empty((n, self.d), dtype=torch.int32, device=self.ctx.device)
-        vk_r = torch.empty((n, self.d), dtype=torch.int32, device=self.ctx.device)
-        sigs = torch.empty((n if keep_sigs else min(chunk, n), self.ell, self.d), dtype=torch.int32, device=self.ctx.device)
+        dev = self.ctx.device
+        if not isinstance(msgs, native.PackedMessages):
+            msgs = self.ctx.pack_messages(list(msgs))
+        seeds_d = torch.from_numpy(seeds.view(np.int64)).to(dev)
+        vk_l = torch.empty((n, self.d), dtype=torch.int32, device=dev)
+        vk_r = torch.empty((n, self.d), dtype=torch.int32, device=dev)
+        sigs = torch.empty((n if keep_sigs else min(chunk, n), self.ell, self.d), dtype=torch.int32, device=dev)
         for lo in range(0, n, chunk):
             hi = min(n, lo + chunk)
-            kb = self.keygen(seeds[lo:hi])
-            vk_l[lo:hi], vk_r[lo:hi] = kb.vk_l, kb.vk_r
-            self.sign(kb, msgs[lo:hi], out=sigs[lo:hi] if keep_sigs else sigs[: hi - lo])
+            self.ctx.keygen_sign(self.A, seeds_d[lo:hi], msgs[lo:hi], vk_l[lo:hi], vk_r[lo:hi], sigs[lo:hi] if keep_sigs else sigs[: hi - lo])
         return vk_l, vk_r, (sigs if keep_sigs else None)
 
     # ------------------------------------------------------------------ aggregate / verify

@@ -543,6 +543,31 @@ int fz_keygen(fz_ctx* ctx, const int32_t* A, const uint64_t* seeds, size_t n, in
     return rc;
 }
 
+// fusion.py:338-373 + 534-557 in one call: n one-time keys from u64 seeds, each signing message i (msgs[offs[i]..offs[i+1]) on
+// the device).  The secret keys never leave the workspace; vk_l / vk_r: [n][d], sig: [n][ell][d].
+size_t fz_keygen_sign_workspace(const fz_ctx* ctx, size_t n) {
+    return r256(fz_keygen_workspace(ctx, n)) + r256(fz_hash_ch_workspace(ctx, n)) + r256(2 * n * ctx->d * 4) + r256(n * 32) + r256(n * ctx->d * 4) + 1024;
+}
+
+int fz_keygen_sign(fz_ctx* ctx, const int32_t* A, const uint64_t* seeds, const uint8_t* msgs, const uint64_t* offs, size_t n, int32_t* vk_l, int32_t* vk_r,
+                   int32_t* sig, void* ws, size_t ws_bytes, void* stream) {
+    FZ_REQUIRE(ctx && (n == 0 || (A && seeds && msgs && offs && vk_l && vk_r && sig && ws)), "fz_keygen_sign: NULL argument");
+    if (n == 0) return 0;
+    Carver cv(ws, ws_bytes);
+    int32_t* sk_hat = cv.take<int32_t>(2 * n * ctx->d);
+    uint8_t* digests = cv.take<uint8_t>(n * 32);
+    int32_t* c_hat = cv.take<int32_t>(n * ctx->d);
+    const size_t kws = fz_keygen_workspace(ctx, n), hws = fz_hash_ch_workspace(ctx, n);
+    void* kbuf = cv.take<uint8_t>(kws);
+    void* hbuf = cv.take<uint8_t>(hws);
+    FZ_REQUIRE(cv.ok, "fz_keygen_sign: workspace too small (see fz_keygen_sign_workspace)");
+    int rc = fz_keygen(ctx, A, seeds, n, nullptr, nullptr, sk_hat, vk_l, vk_r, kbuf, kws, stream);
+    if (!rc) rc = fz_hash_msg(ctx, msgs, offs, n, digests, stream);
+    if (!rc) rc = fz_hash_ch(ctx, vk_l, vk_r, digests, n, c_hat, hbuf, hws, stream);
+    if (!rc) rc = launch_sign_rows(ctx, sk_hat, c_hat, sig, n, (cudaStream_t)stream);
+    return rc;
+}
+
 // fusion.py:557 with broadcast rows: sig[b][r] = sk_hat[b][0] * c_hat[b] + sk_hat[b][1] for every r (keys from fz_keygen's sk_hat)
 int fz_sign_mac_rows(fz_ctx* ctx, const int32_t* sk_hat, const int32_t* c_hat, int32_t* sig, size_t batch, void* stream) {
     FZ_REQUIRE(ctx && (batch == 0 || (sk_hat && c_hat && sig)), "fz_sign_mac_rows: NULL argument");

@@ -549,6 +549,15 @@ def keygen(self, A, seeds, want_sk: bool = True):
     return sk_l, sk_r, sk_hat, vk_l, vk_r
 
 
+def keygen_sign(self, A, seeds: torch.Tensor, msgs: "PackedMessages", vk_l, vk_r, sig) -> None:
+    """fz_keygen_sign: seeds (int64 view of u64, device), packed messages on the device; writes vk_l / vk_r [n, d] and sig [n, ell, d]."""
+    n = seeds.numel()
+    self.lib.fz_keygen_sign_workspace.restype = C.c_size_t
+    ws = self._ws(self.lib.fz_keygen_sign_workspace(self._h, C.c_size_t(n)))
+    self._chk(self.lib.fz_keygen_sign(self._h, _ptr(A), _ptr(seeds), _ptr(msgs.buf), _ptr(msgs.offs), C.c_size_t(n), _ptr(vk_l), _ptr(vk_r), _ptr(sig),
+                                      _ptr(ws), C.c_size_t(ws.numel()), self._stream()))
+
+
 def sign_mac_rows(self, sk_hat, c_hat, out=None) -> torch.Tensor:
     sk_hat, c_hat = self._dev(sk_hat), self._dev(c_hat)
     n = c_hat.numel() // self.d
@@ -560,5 +569,5 @@ def sign_mac_rows(self, sk_hat, c_hat, out=None) -> torch.Tensor:
 for _f in (_u8, _pack_messages, pack_messages, _ws, sha3_256, shake256, hash_msg, format_text, decode_poly, hash_ch, _agg_off, hash_ag, sort_keys, gather_sorted,
            aggregate_sum, fold_partials, verify_check, hash_ag_begin, hash_ag_absorb, hash_ag_squeeze, aggregate_sum_off,
            verify_target, verify_finish, hash_ag_ring, hash_ag_xof_buffer, hash_ag_text, hash_ag_absorb_ring, hash_ag_squeeze_xof,
-           hash_ag_decode, _seed_keys, sample_coef, sample_ntt, keygen, sign_mac_rows):
+           hash_ag_decode, _seed_keys, sample_coef, sample_ntt, keygen, keygen_sign, sign_mac_rows):
     setattr(Context, _f.__name__, _f)

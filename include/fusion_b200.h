@@ -154,6 +154,11 @@ int fz_sample_ntt(fz_ctx* ctx, const uint32_t* keys, int key_stride, const int32
 size_t fz_keygen_workspace(const fz_ctx* ctx, size_t n);
 int fz_keygen(fz_ctx* ctx, const int32_t* A, const uint64_t* seeds, size_t n, int32_t* sk_l, int32_t* sk_r, int32_t* sk_hat, int32_t* vk_l, int32_t* vk_r,
               void* ws, size_t ws_bytes, void* stream);
+/* keygen (fusion.py:338-373) + sign (fusion.py:534-557) of n one-time keys in one call: key i comes from seeds[i] and signs
+ * the message bytes msgs[offs[i]..offs[i+1]) (device memory).  vk_l / vk_r: [n][d], sig: [n][ell][d]. */
+size_t fz_keygen_sign_workspace(const fz_ctx* ctx, size_t n);
+int fz_keygen_sign(fz_ctx* ctx, const int32_t* A, const uint64_t* seeds, const uint8_t* msgs, const uint64_t* offs, size_t n, int32_t* vk_l, int32_t* vk_r,
+                   int32_t* sig, void* ws, size_t ws_bytes, void* stream);
 /* fusion.py:557 for keys kept as their one distinct row (sk_hat from fz_keygen): sig: [batch][ell][d] */
 int fz_sign_mac_rows(fz_ctx* ctx, const int32_t* sk_hat, const int32_t* c_hat, int32_t* sig, size_t batch, void* stream);
 
