@@ -288,6 +288,55 @@ def scheme_extras(args, ctx, rank, world, dist):
     }
 
 
+def verify_128(args, rank, world, dist, device_index):
+    """BASELINE configs[4], secpar 128 half: capacity-sized (1796 signers) aggregates, aggregate + verify sigs/s per GPU share."""
+    import numpy as np
+    import torch
+
+    from fusion_cryptography_b200 import native
+    from fusion_cryptography_b200.batch import Engine
+
+    ctx = native.get_context(128, device_index)
+    eng = Engine(128, seed=42, device=device_index)
+    dev, cap = ctx.device, ctx.capacity
+    nk = min(args.extra_keys, 32768)
+    seeds = (10**6 + 2 * (rank * nk + np.arange(nk))).astype(np.uint64)
+    msgs = [f"msg-{rank * nk + i:07d}".encode() for i in range(nk)]
+    vk_l, vk_r, sigs = eng.keygen_sign(seeds, ctx.pack_messages(msgs))
+    na = args.extra_aggs
+    counts = [cap] * na
+    base = (np.arange(na)[:, None] * 97 + np.arange(cap)[None, :]) % nk
+    sel = torch.from_numpy(base.reshape(-1).astype(np.int32)).to(dev)
+    dg_pos = ctx.hash_msg(msgs)[sel.long()].contiguous()
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / 1000.0, out
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    eng.aggregate(vk_l, vk_r, None, sigs, counts, sel=sel, sig_sel=sel, digests=dg_pos)
+    t_agg, aggs = timed(lambda: eng.aggregate(vk_l, vk_r, None, sigs, counts, sel=sel, sig_sel=sel, digests=dg_pos))
+    eng.verify(vk_l, vk_r, None, aggs, counts, sel=sel, digests=dg_pos)
+    t_ver, codes = timed(lambda: eng.verify(vk_l, vk_r, None, aggs, counts, sel=sel, digests=dg_pos))
+    ok = bool((codes == 0).all().item())
+    t_agg, t_ver = allmax(t_agg), allmax(t_ver)
+    tot = na * cap
+    return {"secpar": 128, "aggregates_per_gpu": na, "signers_per_aggregate": cap,
+            "aggregate": {"value": tot * world / t_agg, "unit": "sigs/s", "seconds": t_agg},
+            "verify": {"value": tot * world / t_ver, "unit": "sigs/s", "seconds": t_ver, "all_accept": ok}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -409,6 +458,9 @@ def main():
     same = bool(torch.equal(hout.to(dev), c))
 
     extra = scheme_extras(args, ctx, rank, world, dist if world > 1 else None) if not args.no_extras else None
+    if extra is not None:
+        torch.cuda.empty_cache()
+        extra["secpar_128"] = verify_128(args, rank, world, dist if world > 1 else None, local_rank)
     if rank == 0:
         peak, peak_src = peaks()
         value = n * world * args.steps / (elapsed_ms / 1000.0)
