@@ -37,7 +37,7 @@ WORKLOAD = "configs[1]: fwd NTT + pointwise mul + inv NTT over 2^20 secpar-256 p
 # algorithmic HBM bytes per polynomial: NTT/INTT 1 KiB in + 1 KiB out, pointwise 3 KiB
 BYTES = {"ntt_fwd": 2048, "pointwise_mul": 3072, "ntt_inv": 2048}
 # measured on B200 with tools/keccak_lab.cu: Keccak-f[1600] per second with one sponge per thread and the ALU pipe (LOP3/SHF) saturated
-KECCAK_PEAK = 4.0e9
+KECCAK_PEAK = 4.28e9
 
 
 def peaks():
@@ -258,7 +258,7 @@ def scheme_extras(args, ctx, rank, world, dist):
                 "aggregate": {"value": nf * cap / t_fa, "unit": "sigs/s", "seconds": t_fa},
                 "verify": {"value": nf * cap / t_fv, "unit": "sigs/s", "seconds": t_fv, "all_accept": bool((codef == 0).all().item())},
                 "keccak_f_per_sec": nf * cap * 224.0 / t_fv,
-                "note": "hash_ch 125 + hash_ag ~99 Keccak-f per signer (SURVEY 8d); measured ALU-pipe peak 4.0e9 Keccak-f/s (profiles/r01_keccak_lab_v1.txt)"}
+                "note": "hash_ch 125 + hash_ag ~99 Keccak-f per signer (SURVEY 8d); measured ALU-pipe peak 4.28e9 Keccak-f/s (profiles/r01_keccak_lab_v2.txt)"}
         del aggf, codef, self_, dgf
     # the streaming aggregation sum alone (alpha precomputed): 86,016 B per signer
     perm, vl_s, vr_s, c_s, alpha = eng._sorted_hash(kb.vk_l, kb.vk_r, dg_pos, counts, sel)
@@ -279,7 +279,7 @@ def scheme_extras(args, ctx, rank, world, dist):
         "kernels": {
             "hash_ch": {"value": nk / t_hash, "unit": "challenges/s/GPU", "bound": "alu (LOP3/SHF)", "keccak_f_per_sec": 125.0 * nk / t_hash,
                         "alu_peak_keccak_f_per_sec": KECCAK_PEAK, "frac_of_alu_peak": 125.0 * nk / t_hash / KECCAK_PEAK,
-                        "peak_source": "tools/keccak_lab.cu thread-per-sponge rate on B200 (profiles/r01_keccak_lab_v1.txt)"},
+                        "peak_source": "tools/keccak_lab.cu thread-per-sponge rate on B200 (profiles/r01_keccak_lab_v2.txt)"},
             "sign_mac_rows": {"GB/s": nk * ell * d * 4 / t_mac / 1e9, "ms": 1000 * t_mac, "bytes": "ell KiB written per key (keys as one row)"},
             "sign_mac": {"GB/s": nkg * 3 * ell * d * 4 / t_macg / 1e9, "ms": 1000 * t_macg, "bytes": "3 * ell KiB per key (SURVEY 8d: 257,024 B)"},
             "aggregate_sum": {"GB/s": tot * (ell + 1) * d * 4 / t_sum / 1e9, "ms": 1000 * t_sum, "bytes": "(ell + 1) KiB per signer (SURVEY 8d: 86,016 B)",

@@ -47,33 +47,44 @@ __device__ __forceinline__ void keccak_round(unsigned long long (&a)[25], unsign
     unsigned long long c2 = xor5(a[2], a[7], a[12], a[17], a[22]);
     unsigned long long c3 = xor5(a[3], a[8], a[13], a[18], a[23]);
     unsigned long long c4 = xor5(a[4], a[9], a[14], a[19], a[24]);
-    unsigned long long d0 = c4 ^ rol64<1>(c1), d1 = c0 ^ rol64<1>(c2), d2 = c1 ^ rol64<1>(c3), d3 = c2 ^ rol64<1>(c4), d4 = c3 ^ rol64<1>(c0);
+    // theta folded into the rho inputs: a ^ D[x] = a ^ C[x-1] ^ rol(C[x+1], 1) is ONE three-input LOP3 per half, so D is never formed
+    const unsigned long long r0 = rol64<1>(c0), r1 = rol64<1>(c1), r2 = rol64<1>(c2), r3 = rol64<1>(c3), r4 = rol64<1>(c4);
+#define TH0(v) ((v) ^ c4 ^ r1)
+#define TH1(v) ((v) ^ c0 ^ r2)
+#define TH2(v) ((v) ^ c1 ^ r3)
+#define TH3(v) ((v) ^ c2 ^ r4)
+#define TH4(v) ((v) ^ c3 ^ r0)
     // theta + rho + pi:  b[y + 5*((2x + 3y) % 5)] = rol(a[x + 5y] ^ d[x], r[x + 5y])
-    unsigned long long b0 = a[0] ^ d0;
-    unsigned long long b10 = rol64<1>(a[1] ^ d1);
-    unsigned long long b20 = rol64<62>(a[2] ^ d2);
-    unsigned long long b5 = rol64<28>(a[3] ^ d3);
-    unsigned long long b15 = rol64<27>(a[4] ^ d4);
-    unsigned long long b16 = rol64<36>(a[5] ^ d0);
-    unsigned long long b1 = rol64<44>(a[6] ^ d1);
-    unsigned long long b11 = rol64<6>(a[7] ^ d2);
-    unsigned long long b21 = rol64<55>(a[8] ^ d3);
-    unsigned long long b6 = rol64<20>(a[9] ^ d4);
-    unsigned long long b7 = rol64<3>(a[10] ^ d0);
-    unsigned long long b17 = rol64<10>(a[11] ^ d1);
-    unsigned long long b2 = rol64<43>(a[12] ^ d2);
-    unsigned long long b12 = rol64<25>(a[13] ^ d3);
-    unsigned long long b22 = rol64<39>(a[14] ^ d4);
-    unsigned long long b23 = rol64<41>(a[15] ^ d0);
-    unsigned long long b8 = rol64<45>(a[16] ^ d1);
-    unsigned long long b18 = rol64<15>(a[17] ^ d2);
-    unsigned long long b3 = rol64<21>(a[18] ^ d3);
-    unsigned long long b13 = rol64<8>(a[19] ^ d4);
-    unsigned long long b14 = rol64<18>(a[20] ^ d0);
-    unsigned long long b24 = rol64<2>(a[21] ^ d1);
-    unsigned long long b9 = rol64<61>(a[22] ^ d2);
-    unsigned long long b19 = rol64<56>(a[23] ^ d3);
-    unsigned long long b4 = rol64<14>(a[24] ^ d4);
+    unsigned long long b0 = TH0(a[0]);
+    unsigned long long b10 = rol64<1>(TH1(a[1]));
+    unsigned long long b20 = rol64<62>(TH2(a[2]));
+    unsigned long long b5 = rol64<28>(TH3(a[3]));
+    unsigned long long b15 = rol64<27>(TH4(a[4]));
+    unsigned long long b16 = rol64<36>(TH0(a[5]));
+    unsigned long long b1 = rol64<44>(TH1(a[6]));
+    unsigned long long b11 = rol64<6>(TH2(a[7]));
+    unsigned long long b21 = rol64<55>(TH3(a[8]));
+    unsigned long long b6 = rol64<20>(TH4(a[9]));
+    unsigned long long b7 = rol64<3>(TH0(a[10]));
+    unsigned long long b17 = rol64<10>(TH1(a[11]));
+    unsigned long long b2 = rol64<43>(TH2(a[12]));
+    unsigned long long b12 = rol64<25>(TH3(a[13]));
+    unsigned long long b22 = rol64<39>(TH4(a[14]));
+    unsigned long long b23 = rol64<41>(TH0(a[15]));
+    unsigned long long b8 = rol64<45>(TH1(a[16]));
+    unsigned long long b18 = rol64<15>(TH2(a[17]));
+    unsigned long long b3 = rol64<21>(TH3(a[18]));
+    unsigned long long b13 = rol64<8>(TH4(a[19]));
+    unsigned long long b14 = rol64<18>(TH0(a[20]));
+    unsigned long long b24 = rol64<2>(TH1(a[21]));
+    unsigned long long b9 = rol64<61>(TH2(a[22]));
+    unsigned long long b19 = rol64<56>(TH3(a[23]));
+    unsigned long long b4 = rol64<14>(TH4(a[24]));
+#undef TH0
+#undef TH1
+#undef TH2
+#undef TH3
+#undef TH4
     // chi + iota
     a[0] = chi(b0, b1, b2) ^ rc; a[1] = chi(b1, b2, b3); a[2] = chi(b2, b3, b4); a[3] = chi(b3, b4, b0); a[4] = chi(b4, b0, b1);
     a[5] = chi(b5, b6, b7); a[6] = chi(b6, b7, b8); a[7] = chi(b7, b8, b9); a[8] = chi(b8, b9, b5); a[9] = chi(b9, b5, b6);
