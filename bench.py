@@ -346,7 +346,7 @@ def main():
     ap.add_argument("--polys", type=int, default=N_POLYS, help="polynomials per GPU (default: the BASELINE size 2^20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the keygen+sign / aggregate / verify throughput section")
-    ap.add_argument("--extra-keys", type=int, default=65536, help="one-time keys per GPU for the sign leg")
+    ap.add_argument("--extra-keys", type=int, default=262144, help="one-time keys per GPU for the sign leg")
     ap.add_argument("--extra-aggs", type=int, default=1250, help="capacity-sized aggregates per GPU for the aggregate/verify leg (10^4 / 8 GPUs)")
     ap.add_argument("--full-batch-aggs", type=int, default=10000, help="N = 1 only: also run the whole C5 batch of capacity aggregates on one GPU (0 = skip)")
     args = ap.parse_args()
