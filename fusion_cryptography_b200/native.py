@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfusion_b200.so")
+LIB_PATH = os.environ.get("FUSION_B200_LIB", os.path.join(_HERE, "libfusion_b200.so"))
 _lib = None
 
 Q = 2147465729
