@@ -1,6 +1,7 @@
 // fz_api.cu -- the extern "C" surface declared in include/fusion_b200.h.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -181,7 +182,9 @@ static int host_pipeline(fz_ctx* ctx, int mode, const int32_t* host_in, const in
     if (n_polys == 0) return 0;
     if (check(cudaSetDevice(ctx->device), "cudaSetDevice")) return -2;
     const size_t poly_bytes = (size_t)ctx->d * sizeof(int32_t);
-    const size_t chunk = ((size_t)32 << 20) / poly_bytes;  // 32 MiB per chunk
+    size_t chunk_mb = 32;   // MiB per chunk; FZ_HOST_CHUNK_MB overrides (tuning knob of the host pipeline)
+    if (const char* e = getenv("FZ_HOST_CHUNK_MB")) { const long v = atol(e); if (v >= 1 && v <= 1024) chunk_mb = (size_t)v; }
+    const size_t chunk = (chunk_mb << 20) / poly_bytes;
     const int NBUF = 4;
     const size_t need = NBUF * chunk * poly_bytes;
     if (ctx->scratch_bytes < need) {
