@@ -233,9 +233,22 @@ def scheme_extras(args, ctx, rank, world, dist):
     dg_pos = ctx.hash_msg(msgs)[sel.long()].contiguous()
     # first call: buffers come from cudaMalloc; the timed call reuses them (a verifier service runs warm)
     eng.aggregate(kb.vk_l, kb.vk_r, None, sigs, counts, sel=sel, sig_sel=sel, digests=dg_pos)
+    # these two legs are bound by the latency of the serial sponge chains, i.e. proportional to the SM clock: record it
+    cs = ClockSampler(ctx.device_index)
+    cs.start()
+    w0 = time.time()
     t_agg, aggs = timed(lambda: eng.aggregate(kb.vk_l, kb.vk_r, None, sigs, counts, sel=sel, sig_sel=sel, digests=dg_pos))
+    w1 = time.time()
+    cs.mark(w0, w1)
+    clk_agg = cs.stop()
     eng.verify(kb.vk_l, kb.vk_r, None, aggs, counts, sel=sel, digests=dg_pos)
+    cs = ClockSampler(ctx.device_index)
+    cs.start()
+    w0 = time.time()
     t_ver, codes = timed(lambda: eng.verify(kb.vk_l, kb.vk_r, None, aggs, counts, sel=sel, digests=dg_pos))
+    w1 = time.time()
+    cs.mark(w0, w1)
+    clk_ver = cs.stop()
     ok = bool((codes == 0).all().item())
     # 1 % tampered aggregates must be rejected with the reference's reason code
     bad = aggs.clone()
@@ -272,9 +285,10 @@ def scheme_extras(args, ctx, rank, world, dist):
         "secpar": SECPAR, "n_gpus": world,
         "keygen_sign": {"keys_per_gpu": nk, "value": nk * world / t_ks, "unit": "sign/s", "seconds": t_ks,
                         "note": "seeds -> MT19937 sampler -> NTT -> A.sk -> SHA3/SHAKE challenge -> decode -> NTT -> sk_l*c+sk_r, sk never materialised as ell rows"},
-        "aggregate": {"aggregates_per_gpu": na, "signers_per_aggregate": cap, "value": tot * world / t_agg, "unit": "sigs/s", "seconds": t_agg},
+        "aggregate": {"aggregates_per_gpu": na, "signers_per_aggregate": cap, "value": tot * world / t_agg, "unit": "sigs/s", "seconds": t_agg,
+                      "clocks_rank0": clk_agg},
         "verify": {"aggregates_per_gpu": na, "signers_per_aggregate": cap, "value": tot * world / t_ver, "unit": "sigs/s", "seconds": t_ver, "all_accept": ok,
-                   "tampered_1pct_rejected": tamper_ok},
+                   "tampered_1pct_rejected": tamper_ok, "clocks_rank0": clk_ver},
         "full_batch_one_gpu": full,
         "kernels": {
             "hash_ch": {"value": nk / t_hash, "unit": "challenges/s/GPU", "bound": "alu (LOP3/SHF)", "keccak_f_per_sec": 125.0 * nk / t_hash,
@@ -332,7 +346,26 @@ def verify_128(args, rank, world, dist, device_index):
     ok = bool((codes == 0).all().item())
     t_agg, t_ver = allmax(t_agg), allmax(t_ver)
     tot = na * cap
-    return {"secpar": 128, "aggregates_per_gpu": na, "signers_per_aggregate": cap,
+    # d = 64 transforms: 2^22 polynomials (1 GiB), 512 B of HBM traffic per polynomial and direction
+    npoly = 1 << 22
+    hq = (native.Q - 1) // 2
+    x = torch.randint(-hq, hq + 1, (npoly, 64), dtype=torch.int32, device=dev)
+    y = torch.empty_like(x)
+    ntt = {}
+    for name, fn in (("ntt_fwd", ctx.ntt_fwd), ("ntt_inv", ctx.ntt_inv)):
+        for _ in range(3):
+            fn(x, out=y)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            fn(x, out=y)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        ntt[name] = {"ms": ms, "GB/s": 2 * npoly * 256 / (ms / 1000.0) / 1e9, "polys": npoly}
+    del x, y
+    return {"secpar": 128, "aggregates_per_gpu": na, "signers_per_aggregate": cap, "ntt_d64": ntt,
             "aggregate": {"value": tot * world / t_agg, "unit": "sigs/s", "seconds": t_agg},
             "verify": {"value": tot * world / t_ver, "unit": "sigs/s", "seconds": t_ver, "all_accept": ok}}
 

@@ -83,6 +83,11 @@ class Engine:
     # the sorted signer positions: window w holds positions [w*P, (w+1)*P) of every aggregate.  All chains advance
     # together (latency-bound chains need every aggregate in flight), memory is O(n_aggs * P) instead of O(positions),
     # and the per-signer work of window w+1 (gather, hash_ch) runs on a second stream while window w is absorbed.
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.ctx.device)
+        return self._side
+
     def _sorted_hash(self, vk_l, vk_r, digests_pos, counts, sel):
         """One-shot sort -> gather -> hash_ch -> hash_ag with every position resident (small batches, kernel timing)."""
         perm = self.ctx.sort_keys(vk_l, vk_r, counts, sel=sel)
@@ -110,7 +115,7 @@ class Engine:
         ring, ring_cap, text_pos = ctx.hash_ag_ring(n_aggs, P)
         agg_ids = torch.arange(n_aggs, dtype=torch.int32, device=dev)
         main = torch.cuda.current_stream(dev)
-        prep = torch.cuda.Stream(device=dev)
+        prep = self._side_stream()      # one side stream per engine: the caching allocator pools blocks per stream
         prep.wait_stream(main)
         wins = []
         for w in range(0, max(max_count, 1), P):

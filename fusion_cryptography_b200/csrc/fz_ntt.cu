@@ -182,9 +182,12 @@ __device__ __forceinline__ void xchg_c2s(uint32_t* tile, int tau, const uint32_t
 }
 
 constexpr int NTT_THREADS = 128;
+#ifndef NTT_MIN_BLOCKS
+#define NTT_MIN_BLOCKS 1
+#endif
 
 template <int LOGD>
-__global__ void __launch_bounds__(NTT_THREADS) ntt_fwd_kernel(const int32_t* in, int32_t* out, size_t n_polys) {
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_fwd_kernel(const int32_t* in, int32_t* out, size_t n_polys) {
     using C = Cfg<LOGD>;
     __shared__ __align__(16) uint32_t smem[(NTT_THREADS / 32) * C::WARP_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_fwd_kernel(const int32_t* in,
 }
 
 template <int LOGD>
-__global__ void __launch_bounds__(NTT_THREADS) ntt_inv_kernel(const int32_t* in, int32_t* out, size_t n_polys) {
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_inv_kernel(const int32_t* in, int32_t* out, size_t n_polys) {
     using C = Cfg<LOGD>;
     __shared__ __align__(16) uint32_t smem[(NTT_THREADS / 32) * C::WARP_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
