@@ -15,7 +15,7 @@ sel = torch.from_numpy(base.reshape(-1).astype(np.int32)).to(dev)
 dg = ctx.hash_msg(msgs)[sel.long()].contiguous()
 counts = [cap] * na
 aggs = eng.aggregate(vk_l, vk_r, None, sigs, counts, sel=sel, sig_sel=sel, digests=dg)
-for it in range(5):
+for it in range(3):
     st0 = torch.cuda.memory_stats()
     torch.cuda.synchronize(); t0 = time.perf_counter()
     codes = eng.verify(vk_l, vk_r, None, aggs, counts, sel=sel, digests=dg)
