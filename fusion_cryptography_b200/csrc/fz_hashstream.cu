@@ -1137,9 +1137,25 @@ int launch_hash_ag_squeeze(const fz_ctx* ctx, void* state, const unsigned long l
     return check(cudaGetLastError(), "hash_ag squeeze launch");
 }
 
+// The chain kernels use no shared memory, so by default their CTAs run on SMs configured with the smallest shared-memory
+// carve-out -- and an SM cannot change its carve-out while CTAs are resident: every kernel of the side stream that needs shared
+// memory (torch's scans, hash_ch, the text formatter) then waits until a whole SM has drained, i.e. almost to the end of the
+// chain kernel (44 of 52 ms, found with tools/agg_host_probe.py).  Asking for the largest carve-out keeps the SMs hospitable.
+static int chain_carveout() {
+    static bool done = false;
+    if (done) return 0;
+    const void* ks[] = {(const void*)agw_absorb_thread_kernel, (const void*)agw_squeeze_thread_kernel, (const void*)warpag::agw_absorb_warp_kernel,
+                        (const void*)warpag::agw_squeeze_warp_kernel};
+    for (const void* k : ks)
+        if (check(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "chain kernel carve-out")) return -2;
+    done = true;
+    return 0;
+}
+
 int launch_agw_absorb(const fz_ctx* ctx, void* state, const uint8_t* ring, size_t ring_cap, const unsigned long long* wend,
                       const unsigned long long* win_off, size_t n_aggs, cudaStream_t st) {
     if (n_aggs == 0) return 0;
+    if (chain_carveout()) return -2;
     if (use_warp(ctx, n_aggs))
         warpag::agw_absorb_warp_kernel<<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
     else
@@ -1150,6 +1166,7 @@ int launch_agw_absorb(const fz_ctx* ctx, void* state, const uint8_t* ring, size_
 int launch_agw_squeeze(const fz_ctx* ctx, void* state, const unsigned long long* win_off, size_t n_aggs, uint8_t* xof, size_t xof_cap, uint32_t* bpos_out,
                        cudaStream_t st) {
     if (n_aggs == 0) return 0;
+    if (chain_carveout()) return -2;
     if (use_warp(ctx, n_aggs))
         warpag::agw_squeeze_warp_kernel<<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
     else
