@@ -13,8 +13,29 @@ except ImportError:  # drop-in layout
     from algebra.polynomials import PolynomialCoefficientRepresentation, PolynomialNTTRepresentation, _eq_zero
 
 
+_ALGEBRA_DUNDERS = ("__eq__", "__add__", "__neg__", "__sub__", "__mul__")
+
+
 def is_algebraic_class(cls):
-    return all(hasattr(cls, m) for m in ("__eq__", "__add__", "__neg__", "__sub__", "__mul__"))
+    return all(hasattr(cls, m) for m in _ALGEBRA_DUNDERS)
+
+
+def _validated_elem_class(matrix):
+    """The reference's constructor checks (algebra/matrices.py:15-36), in the reference's order and with its messages."""
+    problems = (
+        (lambda: not isinstance(matrix, list), "Matrix must be a list"),
+        (lambda: not matrix, "Matrix must not be empty."),
+        (lambda: any(not isinstance(row, list) for row in matrix), "Matrix must be a list of lists"),
+        (lambda: any(not row for row in matrix), "Matrix must not contain empty lists"),
+        (lambda: any(len(row) != len(matrix[0]) for row in matrix), "All rows must have the same length"),
+        (lambda: not is_algebraic_class(cls=type(matrix[0][0])), "Matrix must contain only instances of the same algebraic class"),
+        (lambda: any(not isinstance(item, type(matrix[0][0])) for row in matrix for item in row),
+         "Matrix must contain only instances of the same algebraic class"),
+    )
+    for failed, message in problems:
+        if failed():
+            raise ValueError(message)
+    return type(matrix[0][0])
 
 
 class GeneralMatrix:
@@ -22,23 +43,20 @@ class GeneralMatrix:
     matrix: List[List[object]]
 
     def __init__(self, matrix: List[list]):
-        if not isinstance(matrix, list):
-            raise ValueError("Matrix must be a list")
-        elif not matrix:
-            raise ValueError("Matrix must not be empty.")
-        elif any(not isinstance(x, list) for x in matrix):
-            raise ValueError("Matrix must be a list of lists")
-        elif any(not x for x in matrix):
-            raise ValueError("Matrix must not contain empty lists")
-        elif not all(len(row) == len(matrix[0]) for row in matrix):
-            raise ValueError("All rows must have the same length")
-        elif not is_algebraic_class(cls=matrix[0][0].__class__):
-            raise ValueError("Matrix must contain only instances of the same algebraic class")
-        elif not all(all(isinstance(item, matrix[0][0].__class__) for item in row) for row in matrix):
-            raise ValueError("Matrix must contain only instances of the same algebraic class")
-        self.elem_class = matrix[0][0].__class__
+        self.elem_class = _validated_elem_class(matrix)
         self.matrix = matrix
         self._base = None  # device tensor [rows, cols, d] the elements are views of (set by the kernels' wrappers)
+
+    @property
+    def _shape(self):
+        return len(self.matrix), len(self.matrix[0])
+
+    def _map(self, fn):
+        return GeneralMatrix(matrix=[[fn(item) for item in row] for row in self.matrix])
+
+    def _is_zero_operand(self, other) -> bool:
+        """`other == 0` in the reference's sense: an all-zero matrix or a zero scalar / polynomial (matrices.py:62-63, 75-76)."""
+        return other._all_zero() if isinstance(other, GeneralMatrix) else _eq_zero(other)
 
     # ------------------------------------------------------------------ device plumbing
     @classmethod
@@ -106,36 +124,32 @@ class GeneralMatrix:
         self.matrix[key] = 0
 
     def __eq__(self, other):
-        if (isinstance(other, GeneralMatrix) and other._all_zero()) or (not isinstance(other, GeneralMatrix) and _eq_zero(other)):
+        if self._is_zero_operand(other):
             return self._all_zero()
-        elif not isinstance(other, GeneralMatrix) or self.elem_class != other.elem_class:
-            return False
-        elif len(self.matrix) != len(other.matrix) or len(self.matrix[0]) != len(other.matrix[0]):
+        if not isinstance(other, GeneralMatrix) or self.elem_class != other.elem_class or self._shape != other._shape:
             return False
         return self.matrix == other.matrix
 
     __hash__ = None
 
     def __add__(self, other):
-        if (isinstance(other, GeneralMatrix) and other._all_zero()) or (not isinstance(other, GeneralMatrix) and _eq_zero(other)):
+        if self._is_zero_operand(other):
             return self
-        elif not isinstance(other, GeneralMatrix) or self.elem_class != other.elem_class:
+        if not isinstance(other, GeneralMatrix) or self.elem_class != other.elem_class:
             raise NotImplementedError("Can only add GeneralMatrix objects of the same algebraic class")
-        elif len(self.matrix) != len(other.matrix) or len(self.matrix[0]) != len(other.matrix[0]):
+        if self._shape != other._shape:
             raise ValueError("Matrix dimensions must match")
-        if self.elem_class in (PolynomialNTTRepresentation, PolynomialCoefficientRepresentation) and self._same_ring() and other._same_ring() \
-                and self._ring() == other._ring():
+        on_device = self.elem_class in (PolynomialNTTRepresentation, PolynomialCoefficientRepresentation)
+        if on_device and self._same_ring() and other._same_ring() and self._ring() == other._ring():
             ctx = self.matrix[0][0]._ctx()
             return GeneralMatrix._from_tensor(self._ring(), self.elem_class, ctx.pointwise_add(self._tensor(), other._tensor()))
-        return GeneralMatrix(matrix=[[self.matrix[i][j] + other.matrix[i][j] for j in range(len(self.matrix[0]))] for i in range(len(self.matrix))])
+        return GeneralMatrix(matrix=[[x + y for x, y in zip(ra, rb)] for ra, rb in zip(self.matrix, other.matrix)])
 
     def __radd__(self, other):
-        if other == 0:
-            return self
-        return self + other
+        return self if other == 0 else self + other
 
     def __neg__(self):
-        return GeneralMatrix(matrix=[[-self.matrix[i][j] for j in range(len(self.matrix[0]))] for i in range(len(self.matrix))])
+        return self._map(lambda item: -item)
 
     def __sub__(self, other):
         return self + (-other)
@@ -148,47 +162,53 @@ class GeneralMatrix:
                 t = self._tensor()
                 out = ctx.pointwise_mul(t, other._tensor().expand_as(t).contiguous())
                 return GeneralMatrix._from_tensor(self._ring(), self.elem_class, out)
-            return GeneralMatrix(matrix=[[self.matrix[i][j] * other for j in range(len(self.matrix[0]))] for i in range(len(self.matrix))])
-        elif not isinstance(other, GeneralMatrix) or self.elem_class != other.elem_class:
+            return self._map(lambda item: item * other)
+        if not isinstance(other, GeneralMatrix) or self.elem_class != other.elem_class:
             raise TypeError("Can only multiply matrices of the same algebraic class")
-        elif len(self.matrix[0]) != len(other.matrix):
+        (rows, inner), (inner_b, cols) = self._shape, other._shape
+        if inner != inner_b:
             raise ValueError("Matrix dimension mismatch")
-        rows, inner, cols = len(self.matrix), len(self.matrix[0]), len(other.matrix[0])
         if self._is_scheme_ntt() and self._same_ring() and other._same_ring() and self._ring() == other._ring():
             ctx = self.matrix[0][0]._ctx()
             if rows == 1 and cols == 1 and inner == ctx.ell:
                 # (1 x ell) . (ell x 1): the scheme's A.s / A.z (reference :121-131) as one fused MAC kernel
                 out = ctx.matvec(self._tensor().reshape(inner, ctx.d), other._tensor().reshape(1, inner, ctx.d))
                 return GeneralMatrix._from_tensor(self._ring(), self.elem_class, out.reshape(1, 1, ctx.d))
+        # general shapes: left-to-right accumulation through the elements' own operators (every + and * re-centres, so the
+        # value equals the reference's for any order; the order is kept anyway)
+        def cell(i, j):
+            acc = self.matrix[i][0] * other.matrix[0][j]
+            for k in range(1, inner):
+                acc += self.matrix[i][k] * other.matrix[k][j]
+            return acc
+
         result = GeneralMatrix.__new__(GeneralMatrix)
-        result.elem_class = self.elem_class
-        result._base = None
-        result.matrix = [[0 for _ in range(cols)] for _ in range(rows)]
-        for i in range(rows):
-            for j in range(cols):
-                acc = self.matrix[i][0] * other.matrix[0][j]
-                for k in range(1, inner):
-                    acc += self.matrix[i][k] * other.matrix[k][j]
-                result.matrix[i][j] = acc
+        result.elem_class, result._base = self.elem_class, None
+        result.matrix = [[cell(i, j) for j in range(cols)] for i in range(rows)]
         return result
 
     def __mod__(self, other):
         if not isinstance(other, int):
             raise TypeError("Can only take the remainder of a matrix with an integer")
-        elif other <= 1:
+        if other <= 1:
             raise ValueError("Modulus must be greater than 1")
-        return GeneralMatrix(matrix=[[self.matrix[i][j] % other for j in range(len(self.matrix[0]))] for i in range(len(self.matrix))])
+        return self._map(lambda item: item % other)
+
+    def _entries(self):
+        return [item for row in self.matrix for item in row]
 
     def norm(self, p: Union[int, str]):
-        if not all(hasattr(z, "norm") for y in self.matrix for z in y):
+        entries = self._entries()
+        if any(not hasattr(item, "norm") for item in entries):
             raise NotImplementedError("Matrix elements must have a norm method")
-        elif p == "infty":
-            return max(max(z.norm(p=p) for z in y) for y in self.matrix)
+        if p == "infty":
+            return max(item.norm(p=p) for item in entries)
 
     def weight(self):
-        if not all(hasattr(z, "weight") for y in self.matrix for z in y):
+        entries = self._entries()
+        if any(not hasattr(item, "weight") for item in entries):
             raise NotImplementedError("Matrix elements must have a weight method")
-        return max(max(z.weight() for z in y) for y in self.matrix)
+        return max(item.weight() for item in entries)
 
 
 GeneralMatrix.__module__ = "algebra.matrices"
