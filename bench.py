@@ -256,6 +256,16 @@ def scheme_extras(args, ctx, rank, world, dist):
     codes_bad = eng.verify(kb.vk_l, kb.vk_r, None, bad, counts, sel=sel, digests=dg_pos)
     tamper_ok = bool((codes_bad[::100] == 3).all().item()) and int((codes_bad != 0).sum().item()) == len(range(0, na, 100))
     del bad
+    # C4: ONE capacity aggregate end to end (sort, 2818 challenges, the serial aggregation hash, the weighted sum) and its verification:
+    # the latency of one SHAKE256 chain of 279 K permutations
+    one = slice(0, cap)
+    eng.aggregate(kb.vk_l, kb.vk_r, None, sigs, [cap], sel=sel[one], sig_sel=sel[one], digests=dg_pos[one])
+    t_one_a, agg1 = timed(lambda: eng.aggregate(kb.vk_l, kb.vk_r, None, sigs, [cap], sel=sel[one], sig_sel=sel[one], digests=dg_pos[one]))
+    eng.verify(kb.vk_l, kb.vk_r, None, agg1, [cap], sel=sel[one], digests=dg_pos[one])
+    t_one_v, code1 = timed(lambda: eng.verify(kb.vk_l, kb.vk_r, None, agg1, [cap], sel=sel[one], digests=dg_pos[one]))
+    single = {"signers": cap, "aggregate_seconds": t_one_a, "verify_seconds": t_one_v, "accepted": bool((code1 == 0).all().item()),
+              "equals_batched_result": bool(torch.equal(agg1[0], aggs[0])),
+              "note": "one serial SHAKE256 chain (197 K absorb + 82 K squeeze permutations) on one warp: latency-bound by construction"}
     # the whole C5 batch (10^4 capacity aggregates) on ONE GPU: with every sponge chain of the batch in flight the hash
     # kernels are bound by the integer ALU pipe instead of by the latency of a single chain
     full = None
@@ -292,6 +302,7 @@ def scheme_extras(args, ctx, rank, world, dist):
                       "clocks_rank0": clk_agg},
         "verify": {"aggregates_per_gpu": na, "signers_per_aggregate": cap, "value": tot * world / t_ver, "unit": "sigs/s", "seconds": t_ver, "all_accept": ok,
                    "tampered_1pct_rejected": tamper_ok, "clocks_rank0": clk_ver},
+        "single_capacity_aggregate": single,
         "full_batch_one_gpu": full,
         "kernels": {
             "hash_ch": {"value": nk / t_hash, "unit": "challenges/s/GPU", "bound": "alu (LOP3/SHF)", "keccak_f_per_sec": 125.0 * nk / t_hash,
