@@ -758,6 +758,39 @@ __device__ __forceinline__ void keccak_f_warp(uint32_t& lo, uint32_t& hi, const 
     }
 }
 
+// The same permutation with the round loop unrolled UNROLL times, round constants as immediates under a lane-0 mask (no
+// predicated constant load).  Measured in tools/keccak_lab.cu: with one chain per SM sub-partition or fewer, UNROLL = 8 runs a
+// round in 177 cycles against 200 (fully unrolled the 23 KB of straight-line code miss the instruction cache: 198); at 8 and 12
+// chains per SM, where the shuffle pipe is the limit, full unrolling wins: 219 / 263 cycles against 257 / 287.
+template <int UNROLL>
+__device__ __forceinline__ void keccak_f_warp_u(uint32_t& lo, uint32_t& hi, const Lane& c, int L) {
+    constexpr unsigned long long RC[24] = {
+        0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, 0x0000000080000001ULL,
+        0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+        0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL,
+        0x000000000000800aULL, 0x800000008000000aULL, 0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+    const uint32_t is0 = L == 0 ? 0xffffffffu : 0u;
+#pragma unroll UNROLL
+    for (int r = 0; r < 24; ++r) {
+        const uint32_t cl = lo ^ FZ_SHFL(lo, c.src5) ^ FZ_SHFL(lo, c.src10) ^ FZ_SHFL(lo, c.src15) ^ FZ_SHFL(lo, c.src20);
+        const uint32_t ch = hi ^ FZ_SHFL(hi, c.src5) ^ FZ_SHFL(hi, c.src10) ^ FZ_SHFL(hi, c.src15) ^ FZ_SHFL(hi, c.src20);
+        const uint32_t ml = FZ_SHFL(cl, c.xm1), mh = FZ_SHFL(ch, c.xm1), pl = FZ_SHFL(cl, c.xp1), ph = FZ_SHFL(ch, c.xp1);
+        lo ^= ml ^ __funnelshift_l(ph, pl, 1);
+        hi ^= mh ^ __funnelshift_l(pl, ph, 1);
+        {
+            const bool sw = c.rot >= 32;
+            const uint32_t a = sw ? hi : lo, b = sw ? lo : hi;
+            const int s = c.rot & 31;
+            lo = __funnelshift_l(b, a, s);
+            hi = __funnelshift_l(a, b, s);
+        }
+        const uint32_t b0l = FZ_SHFL(lo, c.pi0), b0h = FZ_SHFL(hi, c.pi0), b1l = FZ_SHFL(lo, c.pi1), b1h = FZ_SHFL(hi, c.pi1);
+        const uint32_t b2l = FZ_SHFL(lo, c.pi2), b2h = FZ_SHFL(hi, c.pi2);
+        lo = b0l ^ (~b1l & b2l) ^ ((uint32_t)RC[r] & is0);
+        hi = b0h ^ (~b1h & b2h) ^ ((uint32_t)(RC[r] >> 32) & is0);
+    }
+}
+
 struct Ring {
     uint8_t* buf;   // RING_BYTES, block aligned
     int wr;         // total bytes written
@@ -999,6 +1032,7 @@ __global__ void __launch_bounds__(WARPS * 32) hash_ag_squeeze_warp_kernel(AgStat
 }
 
 // ring-fed chain, one warp per aggregate: lanes 0..16 load the block (prefetched one block ahead)
+template <int UNROLL>
 __global__ void __launch_bounds__(32) agw_absorb_warp_kernel(AgState* __restrict__ st, const uint8_t* __restrict__ ring, size_t ring_cap,
                                                                       const unsigned long long* __restrict__ wend,
                                                                       const unsigned long long* __restrict__ win_off, size_t n_aggs) {
@@ -1028,7 +1062,7 @@ __global__ void __launch_bounds__(32) agw_absorb_warp_kernel(AgState* __restrict
         have = rpos + KECCAK_RATE <= end;
         nxt = make_uint2(0u, 0u);
         if (have && L < KECCAK_RATE_LANES) nxt = __ldcs(reinterpret_cast<const uint2*>(rj + (rpos % ring_cap)) + L);
-        keccak_f_warp(lo, hi, c, L);
+        keccak_f_warp_u<UNROLL>(lo, hi, c, L);
     }
     if (closing) {
         const uint32_t rem = (uint32_t)(end - rpos);
@@ -1044,7 +1078,7 @@ __global__ void __launch_bounds__(32) agw_absorb_warp_kernel(AgState* __restrict
             lo ^= (uint32_t)w;
             hi ^= (uint32_t)(w >> 32);
         }
-        keccak_f_warp(lo, hi, c, L);
+        keccak_f_warp_u<UNROLL>(lo, hi, c, L);
         rpos = end;
         if (L == 0) { s->phase = 1; s->bpos = 0; }
     }
@@ -1052,6 +1086,7 @@ __global__ void __launch_bounds__(32) agw_absorb_warp_kernel(AgState* __restrict
     if (L == 0) s->rpos = rpos;
 }
 
+template <int UNROLL>
 __global__ void __launch_bounds__(32) agw_squeeze_warp_kernel(AgState* __restrict__ st, const unsigned long long* __restrict__ win_off, size_t n_aggs,
                                                                        uint32_t n_ag, uint8_t* __restrict__ xof, size_t xof_cap,
                                                                        uint32_t* __restrict__ bpos_out) {
@@ -1072,7 +1107,7 @@ __global__ void __launch_bounds__(32) agw_squeeze_warp_kernel(AgState* __restric
     unsigned long long o = 0;
     if (L < KECCAK_RATE_LANES) __stcs(out + L, make_uint2(lo, hi));
     while (o + KECCAK_RATE < need) {
-        keccak_f_warp(lo, hi, c, L);
+        keccak_f_warp_u<UNROLL>(lo, hi, c, L);
         o += KECCAK_RATE;
         if (L < KECCAK_RATE_LANES) __stcs(out + o / 8 + L, make_uint2(lo, hi));
     }
@@ -1144,8 +1179,9 @@ int launch_hash_ag_squeeze(const fz_ctx* ctx, void* state, const unsigned long l
 static int chain_carveout() {
     static bool done = false;
     if (done) return 0;
-    const void* ks[] = {(const void*)agw_absorb_thread_kernel, (const void*)agw_squeeze_thread_kernel, (const void*)warpag::agw_absorb_warp_kernel,
-                        (const void*)warpag::agw_squeeze_warp_kernel};
+    const void* ks[] = {(const void*)agw_absorb_thread_kernel,          (const void*)agw_squeeze_thread_kernel,
+                        (const void*)warpag::agw_absorb_warp_kernel<8>,  (const void*)warpag::agw_squeeze_warp_kernel<8>,
+                        (const void*)warpag::agw_absorb_warp_kernel<24>, (const void*)warpag::agw_squeeze_warp_kernel<24>};
     for (const void* k : ks)
         if (check(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "chain kernel carve-out")) return -2;
     done = true;
@@ -1157,7 +1193,13 @@ int launch_agw_absorb(const fz_ctx* ctx, void* state, const uint8_t* ring, size_
     if (n_aggs == 0) return 0;
     if (chain_carveout()) return -2;
     if (use_warp(ctx, n_aggs))
-        warpag::agw_absorb_warp_kernel<<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
+    {
+        // up to one chain per SM sub-partition the round loop unrolled by 8 has the lowest latency; beyond, full unrolling (see keccak_f_warp_u)
+        if (n_aggs <= (size_t)ctx->sm_count * 4)
+            warpag::agw_absorb_warp_kernel<8><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
+        else
+            warpag::agw_absorb_warp_kernel<24><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
+    }
     else
         agw_absorb_thread_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
     return check(cudaGetLastError(), "agw_absorb launch");
@@ -1168,7 +1210,12 @@ int launch_agw_squeeze(const fz_ctx* ctx, void* state, const unsigned long long*
     if (n_aggs == 0) return 0;
     if (chain_carveout()) return -2;
     if (use_warp(ctx, n_aggs))
-        warpag::agw_squeeze_warp_kernel<<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
+    {
+        if (n_aggs <= (size_t)ctx->sm_count * 4)
+            warpag::agw_squeeze_warp_kernel<8><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
+        else
+            warpag::agw_squeeze_warp_kernel<24><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
+    }
     else
         agw_squeeze_thread_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
     return check(cudaGetLastError(), "agw_squeeze launch");

@@ -158,6 +158,31 @@ __device__ __forceinline__ void f_v5(uint32_t& lo, uint32_t& hi, const Lane& c, 
 }
 
 
+
+// V8 / V9: the V0 round with the 24 rounds fully unrolled (round constants become immediates, the scheduler may overlap the tail of
+// one round with the head of the next) / unrolled by 4
+template <int UNROLL>
+__device__ __forceinline__ void f_v8(uint32_t& lo, uint32_t& hi, const Lane& c, int L) {
+    constexpr unsigned long long RC[24] = {
+        0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, 0x0000000080000001ULL,
+        0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+        0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL,
+        0x000000000000800aULL, 0x800000008000000aULL, 0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+    const uint32_t is0 = L == 0 ? 0xffffffffu : 0u;
+#pragma unroll UNROLL
+    for (int r = 0; r < 24; ++r) {
+        uint32_t cl = lo ^ SH(lo, c.src5) ^ SH(lo, c.src10) ^ SH(lo, c.src15) ^ SH(lo, c.src20);
+        uint32_t ch = hi ^ SH(hi, c.src5) ^ SH(hi, c.src10) ^ SH(hi, c.src15) ^ SH(hi, c.src20);
+        const uint32_t ml = SH(cl, c.xm1), mh = SH(ch, c.xm1), pl = SH(cl, c.xp1), ph = SH(ch, c.xp1);
+        lo ^= ml ^ __funnelshift_l(ph, pl, 1);
+        hi ^= mh ^ __funnelshift_l(pl, ph, 1);
+        rho(lo, hi, c.rot);
+        const uint32_t b0l = SH(lo, c.pi0), b0h = SH(hi, c.pi0), b1l = SH(lo, c.pi1), b1h = SH(hi, c.pi1), b2l = SH(lo, c.pi2), b2h = SH(hi, c.pi2);
+        lo = b0l ^ (~b1l & b2l) ^ ((uint32_t)RC[r] & is0);
+        hi = b0h ^ (~b1h & b2h) ^ ((uint32_t)(RC[r] >> 32) & is0);
+    }
+}
+
 // V7: two shuffle stages: after the column parity, every lane gathers -- for each of its three pi sources -- the raw
 // lane and the parities of the source's neighbour columns, and applies theta + rho for those three lanes itself.
 struct Lane7 { int s[3], cm[3], cp[3], rot[3]; };
@@ -232,6 +257,14 @@ __global__ void coop2_kernel(int perms, unsigned long long* state_out, long long
     for (int p = 0; p < perms; ++p) {
         if (V == 6) f_v6(lo, hi, lo2, hi2, c, L);
         if (V == 7) f_v7(lo, hi, c, q, L);
+        if (V == 8) f_v8<24>(lo, hi, c, L);
+        if (V == 9) f_v8<4>(lo, hi, c, L);
+        if (V == 10) f_v8<2>(lo, hi, c, L);
+        if (V == 11) f_v8<3>(lo, hi, c, L);
+        if (V == 12) f_v8<6>(lo, hi, c, L);
+        if (V == 13) f_v8<8>(lo, hi, c, L);
+        if (V == 14) f_v8<12>(lo, hi, c, L);
+        if (V == 15) f_v8<1>(lo, hi, c, L);
     }
     const long long t1 = clock64();
     if (chain == 0 && L < 25) state_out[L] = ((unsigned long long)hi << 32) | lo;
@@ -362,6 +395,14 @@ int main(int argc, char** argv) {
     }
     RUN_COOP2(6, "V6 shfl x18, 2 chains/warp")
     RUN_COOP2(7, "V7 shfl x26, 2 stages")
+    RUN_COOP2(8, "V8 = V0 unrolled x24")
+    RUN_COOP2(9, "V9 = V0 unrolled x4")
+    RUN_COOP2(15, "V15 = V0 mask-iota, x1")
+    RUN_COOP2(10, "V10 = V0 unrolled x2")
+    RUN_COOP2(11, "V11 = V0 unrolled x3")
+    RUN_COOP2(12, "V12 = V0 unrolled x6")
+    RUN_COOP2(13, "V13 = V0 unrolled x8")
+    RUN_COOP2(14, "V14 = V0 unrolled x12")
     {
         unsigned* d_sink; CK(cudaMalloc(&d_sink, 4));
         const int it = 10000;
