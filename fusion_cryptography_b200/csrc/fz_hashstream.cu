@@ -1141,7 +1141,7 @@ static int warp_smem_attr() {
 
 // one serial sponge per aggregate: a warp per aggregate minimises the chain latency, a thread per aggregate maximises
 // throughput once there are enough aggregates to fill the machine
-static bool use_warp(const fz_ctx* ctx, size_t n_aggs) { return ctx->hash_ag_impl == 3 || (ctx->hash_ag_impl == 0 && n_aggs < 2560); }
+static bool use_warp(const fz_ctx* ctx, size_t n_aggs) { return ctx->hash_ag_impl == 3 || (ctx->hash_ag_impl == 0 && n_aggs < 2816); }
 
 int launch_hash_ag_absorb(const fz_ctx* ctx, void* state, const int32_t* vk_l_s, const int32_t* vk_r_s, const uint8_t* dg_s, const int32_t* c_hat_s,
                           const unsigned long long* win_off, size_t n_aggs, cudaStream_t st) {

@@ -18,7 +18,7 @@ struct fz_ctx {
     // scratch owned by the context (grown on demand, never per call when large enough)
     void* scratch;
     size_t scratch_bytes;
-    int hash_ag_impl;   // 0 auto (warp per aggregate below 2560 aggregates, thread per aggregate above), 2 thread, 3 warp
+    int hash_ag_impl;   // 0 auto (warp per aggregate below 2816 aggregates, thread per aggregate above), 2 thread, 3 warp
     int buffered_hash;  // 1: format text into HBM scratch first (fz_hash.cu); 0 (default): streaming generator (fz_hashstream.cu)
 };
 
