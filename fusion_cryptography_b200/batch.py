@@ -130,28 +130,17 @@ class Engine:
             n_win = int(cnt.sum())
             woff_np = np.zeros(n_aggs + 1, dtype=np.int64)
             np.cumsum(cnt, out=woff_np[1:])
-            _t = [__import__("time").perf_counter()] if os.environ.get("FZ_TRACE") else None
             if len(wins) >= 2:
                 if overlap:
                     prep.wait_event(wins[-2]["absorbed"])    # ring space of window w - 2 is free once its chain step is done
                 wins[-2]["absorbed"].synchronize()           # and the host stays at most two windows ahead
-            if _t is not None: _t.append(__import__("time").perf_counter())
             with torch.cuda.stream(prep):
-                if _t is not None:
-                    _e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-                    _e[0].record()
                 win_off = torch.from_numpy(woff_np).to(dev, non_blocking=True)
                 cnt_d = torch.from_numpy(cnt).to(dev, non_blocking=True)
-                if _t is not None: _e[1].record()
                 base = agg_off[:-1] + w - win_off[:-1]
                 idx = torch.repeat_interleave(base, cnt_d, output_size=n_win) + torch.arange(n_win, dtype=torch.int64, device=dev)
-                if _t is not None: _e[2].record()
                 agg_of = torch.repeat_interleave(agg_ids, cnt_d, output_size=n_win)
-                if _t is not None: _e[3].record()
                 pos = perm.index_select(0, idx)
-                if _t is not None:
-                    _e[4].record()
-                    self._trace_events = getattr(self, "_trace_events", []) + [_e]
                 vl_w, vr_w, dg_w = ctx.gather_sorted(vk_l, vk_r, dg_all, pos, sel=sel_d)
                 c_w = ctx.hash_ch(vl_w, vr_w, dg_w)
                 wend = ctx.hash_ag_text(vl_w, vr_w, dg_w, c_w, win_off, agg_of, agg_off, n_aggs, n_win, w, text_pos, ring, ring_cap)
@@ -164,9 +153,6 @@ class Engine:
             ctx.hash_ag_absorb_ring(state, ring, ring_cap, wend, win_off, n_aggs)
             absorbed = torch.cuda.Event()
             absorbed.record(main)
-            if _t is not None:
-                _t.append(__import__("time").perf_counter())
-                print(f"window {len(wins)}: host waited {1e3 * (_t[1] - _t[0]):.1f} ms, enqueued in {1e3 * (_t[2] - _t[1]):.1f} ms, t = {1e3 * _t[2]:.1f}")
             wins.append({"win_off": win_off, "n": n_win, "pos": pos, "agg_of": agg_of, "max": int(cnt.max()), "absorbed": absorbed,
                          "c": c_w if keep_c else None})
         if overlap:

@@ -82,6 +82,3 @@ rows_.sort()
 for a, b, t in rows_[:26]:
     print(f"  {a:8.1f} -> {b:8.1f}  {t}")
 
-if os.environ.get("FZ_TRACE"):
-    for _e in eng._trace_events[-14:-10]:
-        print("  prep torch ops (ms since call start):", " ".join(f"{base_ev.elapsed_time(x):.1f}" for x in _e))
