@@ -467,7 +467,7 @@ def _device_hash_pipeline(params: Params, keys: List[OneTimeVerificationKey], me
     perm = ctx.sort_keys(vl, vr, [n]) if sort else torch.arange(n, dtype=torch.int32, device=ctx.device)
     vl_s, vr_s, dg_s = ctx.gather_sorted(vl, vr, dg, perm)
     c_s = ctx.hash_ch(vl_s, vr_s, dg_s)
-    alpha = ctx.hash_ag(vl_s, vr_s, dg_s, c_s, [n])
+    alpha = ctx.hash_ag_fast(vl_s, vr_s, dg_s, c_s, [n])
     return perm, vl_s, vr_s, c_s, alpha
 
 

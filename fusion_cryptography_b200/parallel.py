@@ -80,7 +80,7 @@ def aggregate_one_sharded(engine, vk_l: torch.Tensor, vk_r: torch.Tensor, msgs: 
     else:
         c_s = c_loc
     # (3) serial aggregation hash, redundantly on every rank
-    alpha = ctx.hash_ag(vl_s, vr_s, dg_s, c_s, [n])
+    alpha = ctx.hash_ag_fast(vl_s, vr_s, dg_s, c_s, [n])
     # (4) partial sum over the signers whose signatures live here (original index in [lo, hi))
     lo, hi = shard_bounds(n, rank, world)
     mine = (perm >= lo) & (perm < hi)

@@ -316,6 +316,15 @@ def test_buffered_and_streaming_hash_agree(ctxs, oracle, secpar):
     finally:
         ctx.set_option("buffered_hash", 0)
         ctx.set_option("hash_ag_impl", 0)
+    # fourth implementation: the ring-fed kernels (text by a warp per signer, chains that only permute, parallel decode), with a warp
+    # and with a thread per aggregate
+    try:
+        for impl in (3, 2):
+            ctx.set_option("hash_ag_impl", impl)
+            c = ctx.hash_ch(dev(vl), dev(vr), dev(dg, np.uint8))
+            out[("ring", impl)] = (host(c), host(ctx.hash_ag_fast(dev(vl), dev(vr), dev(dg, np.uint8), c, counts)))
+    finally:
+        ctx.set_option("hash_ag_impl", 0)
     ref = out[(1, 0)]
     for k, v in out.items():
         assert np.array_equal(v[0], ref[0]) and np.array_equal(v[1], ref[1]), k
