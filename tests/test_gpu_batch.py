@@ -118,7 +118,7 @@ def test_single_aggregate_sharded_world1(engines, oracle):
     assert np.array_equal(host(agg[0]), want)
 
 
-def test_capacity_aggregate_properties():
+def test_capacity_aggregate_properties(oracle):
     """BASELINE config[3] at full size (N = 2818 @256): aggregate and verify one capacity-sized aggregate; properties:
     verify accepts, a tampered copy is rejected, and aggregation is the alpha-weighted sum (linearity in the signatures)."""
     from fusion_cryptography_b200.batch import Engine
@@ -130,6 +130,11 @@ def test_capacity_aggregate_properties():
     vk_l, vk_r, sigs = eng.keygen_sign(seeds, msgs, chunk=1024)
     agg = eng.aggregate(vk_l, vk_r, msgs, sigs, [n])
     assert host(eng.verify(vk_l, vk_r, msgs, agg, [n])).tolist() == [0]
+    # bit-exact against the oracle at full capacity (one SHAKE256 over 26.8 MB of repr text, 11.2 MB squeezed), and the oracle's verify
+    oracle.set_threads(oracle.max_threads())
+    want = oracle.aggregate(256, host(vk_l), host(vk_r), msgs, host(sigs))
+    assert np.array_equal(host(agg[0]), want)
+    assert oracle.verify(256, host(eng.A), host(vk_l), host(vk_r), msgs, want) == 0
     bad = agg.clone()
     bad[0, 5, 7] += 1
     assert host(eng.verify(vk_l, vk_r, msgs, bad, [n])).tolist() == [3]
