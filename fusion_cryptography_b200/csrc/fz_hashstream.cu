@@ -758,10 +758,12 @@ __device__ __forceinline__ void keccak_f_warp(uint32_t& lo, uint32_t& hi, const 
     }
 }
 
-// The same permutation with the round loop unrolled UNROLL times, round constants as immediates under a lane-0 mask (no
-// predicated constant load).  Measured in tools/keccak_lab.cu: with one chain per SM sub-partition or fewer, UNROLL = 8 runs a
-// round in 177 cycles against 200 (fully unrolled the 23 KB of straight-line code miss the instruction cache: 198); at 8 and 12
-// chains per SM, where the shuffle pipe is the limit, full unrolling wins: 219 / 263 cycles against 257 / 287.
+// The same permutation, fully unrolled (round constants become immediates under a lane-0 mask, no predicated constant load), with
+// the shuffles written in the order that lets the scheduler run the low half ahead of the high half: the low half's stage-2 shuffles
+// are issued while the high half's stage-1 shuffles are still in flight, and the low half of the next round starts while the high
+// half finishes chi.  The schedule ptxas emits follows the source order of the shuffles closely; measured in tools/keccak_lab.cu
+// (cycles per round at 1 / 8 / 12 chains per SM): this order 168 / 197 / 240, the plain loop 200 / 257 / 287, the plain loop unrolled
+// 198 / 219 / 266, unrolled by eight 177 / 254 / 288.
 template <int UNROLL>
 __device__ __forceinline__ void keccak_f_warp_u(uint32_t& lo, uint32_t& hi, const Lane& c, int L) {
     constexpr unsigned long long RC[24] = {
@@ -772,20 +774,25 @@ __device__ __forceinline__ void keccak_f_warp_u(uint32_t& lo, uint32_t& hi, cons
     const uint32_t is0 = L == 0 ? 0xffffffffu : 0u;
 #pragma unroll UNROLL
     for (int r = 0; r < 24; ++r) {
-        const uint32_t cl = lo ^ FZ_SHFL(lo, c.src5) ^ FZ_SHFL(lo, c.src10) ^ FZ_SHFL(lo, c.src15) ^ FZ_SHFL(lo, c.src20);
-        const uint32_t ch = hi ^ FZ_SHFL(hi, c.src5) ^ FZ_SHFL(hi, c.src10) ^ FZ_SHFL(hi, c.src15) ^ FZ_SHFL(hi, c.src20);
-        const uint32_t ml = FZ_SHFL(cl, c.xm1), mh = FZ_SHFL(ch, c.xm1), pl = FZ_SHFL(cl, c.xp1), ph = FZ_SHFL(ch, c.xp1);
+        // theta: column parity of the low half, then of the high half
+        const uint32_t l1 = FZ_SHFL(lo, c.src5), l2 = FZ_SHFL(lo, c.src10), l3 = FZ_SHFL(lo, c.src15), l4 = FZ_SHFL(lo, c.src20);
+        const uint32_t h1 = FZ_SHFL(hi, c.src5), h2 = FZ_SHFL(hi, c.src10), h3 = FZ_SHFL(hi, c.src15), h4 = FZ_SHFL(hi, c.src20);
+        const uint32_t cl = lo ^ l1 ^ l2 ^ l3 ^ l4;
+        const uint32_t ml = FZ_SHFL(cl, c.xm1), pl = FZ_SHFL(cl, c.xp1);
+        const uint32_t ch = hi ^ h1 ^ h2 ^ h3 ^ h4;
+        const uint32_t mh = FZ_SHFL(ch, c.xm1), ph = FZ_SHFL(ch, c.xp1);
         lo ^= ml ^ __funnelshift_l(ph, pl, 1);
         hi ^= mh ^ __funnelshift_l(pl, ph, 1);
-        {
+        {   // rho
             const bool sw = c.rot >= 32;
             const uint32_t a = sw ? hi : lo, b = sw ? lo : hi;
             const int s = c.rot & 31;
             lo = __funnelshift_l(b, a, s);
             hi = __funnelshift_l(a, b, s);
         }
-        const uint32_t b0l = FZ_SHFL(lo, c.pi0), b0h = FZ_SHFL(hi, c.pi0), b1l = FZ_SHFL(lo, c.pi1), b1h = FZ_SHFL(hi, c.pi1);
-        const uint32_t b2l = FZ_SHFL(lo, c.pi2), b2h = FZ_SHFL(hi, c.pi2);
+        // pi + chi + iota, low half first
+        const uint32_t b0l = FZ_SHFL(lo, c.pi0), b1l = FZ_SHFL(lo, c.pi1), b2l = FZ_SHFL(lo, c.pi2);
+        const uint32_t b0h = FZ_SHFL(hi, c.pi0), b1h = FZ_SHFL(hi, c.pi1), b2h = FZ_SHFL(hi, c.pi2);
         lo = b0l ^ (~b1l & b2l) ^ ((uint32_t)RC[r] & is0);
         hi = b0h ^ (~b1h & b2h) ^ ((uint32_t)(RC[r] >> 32) & is0);
     }
@@ -1180,7 +1187,6 @@ static int chain_carveout() {
     static bool done = false;
     if (done) return 0;
     const void* ks[] = {(const void*)agw_absorb_thread_kernel,          (const void*)agw_squeeze_thread_kernel,
-                        (const void*)warpag::agw_absorb_warp_kernel<8>,  (const void*)warpag::agw_squeeze_warp_kernel<8>,
                         (const void*)warpag::agw_absorb_warp_kernel<24>, (const void*)warpag::agw_squeeze_warp_kernel<24>};
     for (const void* k : ks)
         if (check(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "chain kernel carve-out")) return -2;
@@ -1193,13 +1199,7 @@ int launch_agw_absorb(const fz_ctx* ctx, void* state, const uint8_t* ring, size_
     if (n_aggs == 0) return 0;
     if (chain_carveout()) return -2;
     if (use_warp(ctx, n_aggs))
-    {
-        // up to one chain per SM sub-partition the round loop unrolled by 8 has the lowest latency; beyond, full unrolling (see keccak_f_warp_u)
-        if (n_aggs <= (size_t)ctx->sm_count * 4)
-            warpag::agw_absorb_warp_kernel<8><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
-        else
-            warpag::agw_absorb_warp_kernel<24><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
-    }
+        warpag::agw_absorb_warp_kernel<24><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
     else
         agw_absorb_thread_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
     return check(cudaGetLastError(), "agw_absorb launch");
@@ -1210,12 +1210,7 @@ int launch_agw_squeeze(const fz_ctx* ctx, void* state, const unsigned long long*
     if (n_aggs == 0) return 0;
     if (chain_carveout()) return -2;
     if (use_warp(ctx, n_aggs))
-    {
-        if (n_aggs <= (size_t)ctx->sm_count * 4)
-            warpag::agw_squeeze_warp_kernel<8><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
-        else
-            warpag::agw_squeeze_warp_kernel<24><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
-    }
+        warpag::agw_squeeze_warp_kernel<24><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
     else
         agw_squeeze_thread_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
     return check(cudaGetLastError(), "agw_squeeze launch");

@@ -183,6 +183,42 @@ __device__ __forceinline__ void f_v8(uint32_t& lo, uint32_t& hi, const Lane& c, 
     }
 }
 
+
+// V16 / V17: source-level reorderings of the V8 round (the compiler's schedule follows the source order of the shuffles closely)
+template <int UNROLL, int ORDER>
+__device__ __forceinline__ void f_v16(uint32_t& lo, uint32_t& hi, const Lane& c, int L) {
+    constexpr unsigned long long RC[24] = {
+        0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, 0x0000000080000001ULL,
+        0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+        0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL,
+        0x000000000000800aULL, 0x800000008000000aULL, 0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+    const uint32_t is0 = L == 0 ? 0xffffffffu : 0u;
+#pragma unroll UNROLL
+    for (int r = 0; r < 24; ++r) {
+        uint32_t cl, ch, ml, mh, pl, ph;
+        if (ORDER == 0) {   // interleave the halves
+            const uint32_t l1 = SH(lo, c.src5), h1 = SH(hi, c.src5), l2 = SH(lo, c.src10), h2 = SH(hi, c.src10);
+            const uint32_t l3 = SH(lo, c.src15), h3 = SH(hi, c.src15), l4 = SH(lo, c.src20), h4 = SH(hi, c.src20);
+            cl = lo ^ l1 ^ l2 ^ l3 ^ l4; ch = hi ^ h1 ^ h2 ^ h3 ^ h4;
+            ml = SH(cl, c.xm1); pl = SH(cl, c.xp1); mh = SH(ch, c.xm1); ph = SH(ch, c.xp1);
+        } else {            // low half first, its stage-2 shuffles issued before the high half's stage 1 completes
+            const uint32_t l1 = SH(lo, c.src5), l2 = SH(lo, c.src10), l3 = SH(lo, c.src15), l4 = SH(lo, c.src20);
+            const uint32_t h1 = SH(hi, c.src5), h2 = SH(hi, c.src10), h3 = SH(hi, c.src15), h4 = SH(hi, c.src20);
+            cl = lo ^ l1 ^ l2 ^ l3 ^ l4;
+            ml = SH(cl, c.xm1); pl = SH(cl, c.xp1);
+            ch = hi ^ h1 ^ h2 ^ h3 ^ h4;
+            mh = SH(ch, c.xm1); ph = SH(ch, c.xp1);
+        }
+        lo ^= ml ^ __funnelshift_l(ph, pl, 1);
+        hi ^= mh ^ __funnelshift_l(pl, ph, 1);
+        rho(lo, hi, c.rot);
+        const uint32_t b0l = SH(lo, c.pi0), b1l = SH(lo, c.pi1), b2l = SH(lo, c.pi2);
+        const uint32_t b0h = SH(hi, c.pi0), b1h = SH(hi, c.pi1), b2h = SH(hi, c.pi2);
+        lo = b0l ^ (~b1l & b2l) ^ ((uint32_t)RC[r] & is0);
+        hi = b0h ^ (~b1h & b2h) ^ ((uint32_t)(RC[r] >> 32) & is0);
+    }
+}
+
 // V7: two shuffle stages: after the column parity, every lane gathers -- for each of its three pi sources -- the raw
 // lane and the parities of the source's neighbour columns, and applies theta + rho for those three lanes itself.
 struct Lane7 { int s[3], cm[3], cp[3], rot[3]; };
@@ -265,6 +301,10 @@ __global__ void coop2_kernel(int perms, unsigned long long* state_out, long long
         if (V == 13) f_v8<8>(lo, hi, c, L);
         if (V == 14) f_v8<12>(lo, hi, c, L);
         if (V == 15) f_v8<1>(lo, hi, c, L);
+        if (V == 16) f_v16<24, 0>(lo, hi, c, L);
+        if (V == 17) f_v16<24, 1>(lo, hi, c, L);
+        if (V == 18) f_v16<8, 0>(lo, hi, c, L);
+        if (V == 19) f_v16<8, 1>(lo, hi, c, L);
     }
     const long long t1 = clock64();
     if (chain == 0 && L < 25) state_out[L] = ((unsigned long long)hi << 32) | lo;
@@ -397,12 +437,33 @@ int main(int argc, char** argv) {
     RUN_COOP2(7, "V7 shfl x26, 2 stages")
     RUN_COOP2(8, "V8 = V0 unrolled x24")
     RUN_COOP2(9, "V9 = V0 unrolled x4")
+    RUN_COOP2(16, "V16 x24 interleaved halves")
+    RUN_COOP2(17, "V17 x24 low half first")
+    RUN_COOP2(18, "V18 x8 interleaved halves")
+    RUN_COOP2(19, "V19 x8 low half first")
     RUN_COOP2(15, "V15 = V0 mask-iota, x1")
     RUN_COOP2(10, "V10 = V0 unrolled x2")
     RUN_COOP2(11, "V11 = V0 unrolled x3")
     RUN_COOP2(12, "V12 = V0 unrolled x6")
     RUN_COOP2(13, "V13 = V0 unrolled x8")
     RUN_COOP2(14, "V14 = V0 unrolled x12")
+
+    {   // CTA shape: the same 1250 chains as 1-, 2- and 4-warp CTAs (how evenly do they spread over SMs and sub-partitions?)
+        const int shapes[][2] = {{1250, 32}, {625, 64}, {313, 128}, {1184, 32}, {296, 128}, {592, 32}, {148, 128}};
+        for (auto& sh : shapes) {
+            coop2_kernel<17><<<sh[0], sh[1]>>>(10, d_state, d_cyc);
+            CK(cudaEventRecord(e0));
+            coop2_kernel<17><<<sh[0], sh[1]>>>(perms, d_state, d_cyc);
+            CK(cudaEventRecord(e1));
+            CK(cudaDeviceSynchronize());
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+            const int nw = sh[0] * sh[1] / 32;
+            CK(cudaMemcpy(cyc.data(), d_cyc, nw * 8, cudaMemcpyDeviceToHost));
+            long long mx = 0; double avg = 0;
+            for (int i = 0; i < nw; ++i) { mx = cyc[i] > mx ? cyc[i] : mx; avg += (double)cyc[i]; }
+            printf("V17 as %4d CTAs x %3d threads: cycles/round avg %.1f max %.1f, %.3f ms\n", sh[0], sh[1], avg / nw / perms / 24.0, (double)mx / perms / 24.0, ms);
+        }
+    }
     {
         unsigned* d_sink; CK(cudaMalloc(&d_sink, 4));
         const int it = 10000;
