@@ -167,14 +167,14 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     v = n * args.steps / dt
     sample = f"{n} polynomials per step (bounded sample of the 2^20 workload), C oracle port, {threads} threads"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
         "data": "synthetic", "config": {"workload": WORKLOAD, "sample_polys_per_step": n},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
 
 
 def scheme_extras(args, ctx, rank, world, dist):
@@ -411,6 +411,15 @@ def readme_demo():
             "reference_cpu_seconds": "about 5 s in CPython on one core (SURVEY section 6: keygen 1.2 s, sign 0.22 s, aggregate 0.16 s per signer, verify 0.7 s)"}
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -425,6 +434,11 @@ def main():
     ap.add_argument("--full-batch-aggs", type=int, default=10000, help="N = 1 only: also run the whole C5 batch of capacity aggregates on one GPU (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # stdout carries exactly one JSON line: everything libraries print to file descriptor 1 (NCCL's version banner ...) goes to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -443,7 +457,6 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's own log lines (its version banner) must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = native.get_context(SECPAR, local_rank)
     dev = ctx.device
@@ -574,7 +587,7 @@ def main():
             line["extra"] = extra
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
