@@ -120,7 +120,7 @@ def cpu_baseline(target_seconds: float = 10.0):
     import numpy as np
     from oracle import oracle as orc
 
-    threads = orc.max_threads()
+    threads = max(orc.max_threads(), len(os.sched_getaffinity(0)))
     orc.set_threads(threads)
     rng = np.random.default_rng(0xF0510)
     h = (2147465729 - 1) // 2
@@ -146,7 +146,8 @@ def run_reference(args, rank, world):
     import numpy as np
     from oracle import oracle as orc
 
-    threads = orc.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: take the cores this process may run on instead
+    threads = max(orc.max_threads(), len(os.sched_getaffinity(0)))
     orc.set_threads(threads)
     rng = np.random.default_rng(0xF0510)
     h = (2147465729 - 1) // 2
