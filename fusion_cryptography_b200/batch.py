@@ -113,8 +113,18 @@ class Engine:
         sel_d = sel.to(dev, dtype=torch.int32).contiguous() if sel is not None else torch.arange(total, dtype=torch.int32, device=dev)
         perm = ctx.sort_keys(vk_l, vk_r, [int(c) for c in counts], sel=sel_d)
         P = max(1, min(max_count, window_positions // max(n_aggs, 1))) if max_count else 1
+        # A little above two warp-chains per SM sub-partition (8 per SM) the absorb phase is time-sliced: three chains on one
+        # sub-partition saturate its shuffle port and would set the pace of the whole launch (247 instead of 197 cycles per round), so
+        # every launch serves exactly 8 * SMs chains with a block budget and the resting set rotates (fz_hash_ag_absorb_sliced).
+        n_slots = int(os.environ.get("FZ_AGG_SLOTS", 8 * ctx.param("sm_count")))   # (the override lets small tests reach this path)
+        sliced = n_slots < n_aggs <= (3 * n_slots) // 2 and n_aggs < 2816 and os.environ.get("FZ_AGG_SLICED", "1") != "0"
+        if sliced:
+            P = max(1, P // int(os.environ.get("FZ_SL_PDIV", "2")))
+            skip_n = n_aggs - n_slots
+            per_signer = 71.0 if self.secpar == 256 else 22.0       # 136-byte blocks of message text per signer (9,513 B / 2,908 B typical)
+            budget = int(P * per_signer * float(os.environ.get("FZ_SL_BUDGET", "1.01")) * n_aggs / n_slots) + 2
         state = ctx.hash_ag_begin(agg_off, n_aggs)
-        ring, ring_cap, text_pos = ctx.hash_ag_ring(n_aggs, P)
+        ring, ring_cap, text_pos = ctx.hash_ag_ring(n_aggs, 3 * P if sliced else P)   # room for the backlog of the resting chains
         agg_ids = torch.arange(n_aggs, dtype=torch.int32, device=dev)
         main = torch.cuda.current_stream(dev)
         # The per-signer work of the next window (gather, hash_ch, message text) runs beside the sponge chains on a side stream.
@@ -150,11 +160,24 @@ class Engine:
                 for t in (win_off, wend, pos, agg_of, c_w):
                     t.record_stream(main)                # allocated on the side stream, read on the main stream
                 main.wait_event(ready)
-            ctx.hash_ag_absorb_ring(state, ring, ring_cap, wend, win_off, n_aggs)
+            if sliced:
+                k = len(wins)
+                ctx.hash_ag_absorb_sliced(state, ring, ring_cap, wend, n_aggs, ((k + 1) * skip_n) % n_aggs, n_slots, budget)
+            else:
+                ctx.hash_ag_absorb_ring(state, ring, ring_cap, wend, win_off, n_aggs)
             absorbed = torch.cuda.Event()
             absorbed.record(main)
             wins.append({"win_off": win_off, "n": n_win, "pos": pos, "agg_of": agg_of, "max": int(cnt.max()), "absorbed": absorbed,
                          "c": c_w if keep_c else None})
+        if sliced:
+            # the text is complete: two more rotating launches, then one over every chain without a budget closes what is left
+            k = len(wins)
+            for extra in range(int(os.environ.get("FZ_SL_EXTRA", "2"))):
+                ctx.hash_ag_absorb_sliced(state, ring, ring_cap, wend, n_aggs, ((k + 1 + extra) * skip_n) % n_aggs, n_slots, budget)
+            ctx.hash_ag_absorb_sliced(state, ring, ring_cap, wend, n_aggs, 0, n_aggs, 1 << 62)
+            still_open = ctx.hash_ag_open_sponges(state, n_aggs)
+            if still_open:
+                raise native.FusionB200Error(f"time-sliced aggregation hash: {still_open} sponges not closed")
         if overlap:
             for t in (ring, text_pos, agg_ids, agg_off, perm, sel_d):
                 t.record_stream(prep)

@@ -406,6 +406,18 @@ int fz_hash_ag_absorb_ring(fz_ctx* ctx, void* state, const uint8_t* ring, size_t
     return launch_agw_absorb(ctx, state, ring, ring_cap, (const unsigned long long*)wend, (const unsigned long long*)win_off, n_aggs, (cudaStream_t)stream);
 }
 
+// Time-sliced absorb for warp-per-aggregate batches slightly above two chains per SM sub-partition: one launch advances the n_active
+// aggregates first_active .. (mod n_aggs) by at most budget_blocks 136-byte blocks each; wend as written by fz_hash_ag_text (bit 63 =
+// text complete).  The caller rotates first_active so that every aggregate rests equally often, keeps the rings large enough for the
+// backlog of the resting aggregates, and finishes with launches over all aggregates until every sponge is closed.
+int fz_hash_ag_absorb_sliced(fz_ctx* ctx, void* state, const uint8_t* ring, size_t ring_cap, const uint64_t* wend, size_t n_aggs, size_t first_active,
+                             size_t n_active, uint64_t budget_blocks, void* stream) {
+    FZ_REQUIRE(ctx && (n_aggs == 0 || (state && ring && wend)), "fz_hash_ag_absorb_sliced: NULL argument");
+    FZ_REQUIRE(n_active <= n_aggs && (n_aggs == 0 || first_active < n_aggs), "fz_hash_ag_absorb_sliced: bad active range");
+    return launch_agw_absorb_sliced(ctx, state, ring, ring_cap, (const unsigned long long*)wend, n_aggs, first_active, n_active, budget_blocks,
+                                    (cudaStream_t)stream);
+}
+
 int fz_hash_ag_squeeze_xof(fz_ctx* ctx, void* state, const uint64_t* win_off, size_t n_aggs, uint8_t* xof, size_t xof_cap, uint32_t* bpos_out,
                            void* stream) {
     FZ_REQUIRE(ctx && (n_aggs == 0 || (state && win_off && xof && bpos_out)), "fz_hash_ag_squeeze_xof: NULL argument");

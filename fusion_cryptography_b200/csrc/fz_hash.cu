@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(128) agw_len_kernel(int level, int d, const in
 __global__ void __launch_bounds__(128) agw_layout_kernel(const uint32_t* __restrict__ piece_len, const unsigned long long* __restrict__ win_off,
                                                           const unsigned long long* __restrict__ agg_off, size_t n_aggs, uint8_t dst0,
                                                           unsigned long long* __restrict__ text_pos, unsigned long long* __restrict__ piece_off,
-                                                          unsigned long long* __restrict__ wend, uint8_t* __restrict__ ring, size_t ring_cap) {
+                                                          unsigned long long* __restrict__ wend, uint8_t* __restrict__ ring, size_t ring_cap, uint32_t w0) {
     const int lane = threadIdx.x & 31;
     const size_t j = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (j >= n_aggs) return;
@@ -593,7 +593,9 @@ __global__ void __launch_bounds__(128) agw_layout_kernel(const uint32_t* __restr
         if (p < hi) piece_off[p] = pos + x - v;
         pos += __shfl_sync(0xffffffffu, x, 31);
     }
-    if (lane == 0) { text_pos[j] = pos; wend[j] = pos; }
+    // bit 63 of wend: the message text of this aggregate is complete (its last signer is in this window or an earlier one)
+    const bool complete = (unsigned long long)w0 + (hi - lo) >= agg_off[j + 1] - agg_off[j];
+    if (lane == 0) { text_pos[j] = pos; wend[j] = pos | (complete ? AGW_TEXT_COMPLETE : 0ULL); }
 }
 
 // dst and src are congruent mod 16; bytes outside [dst, dst + len) are never written (neighbouring pieces are written concurrently)
@@ -812,7 +814,7 @@ int launch_agw_text(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r,
         agw_len_kernel<<<(unsigned)((n_win + 3) / 4), 128, 0, st>>>(level, ctx->d, vk_l, vk_r, digests, c_hat, win_off, agg_of, agg_off, n_win, w0, piece_len);
         if (check(cudaGetLastError(), "agw_len launch")) return -2;
     }
-    agw_layout_kernel<<<(unsigned)((n_aggs + 3) / 4), 128, 0, st>>>(piece_len, win_off, agg_off, n_aggs, dst0, text_pos, piece_off, wend, ring, ring_cap);
+    agw_layout_kernel<<<(unsigned)((n_aggs + 3) / 4), 128, 0, st>>>(piece_len, win_off, agg_off, n_aggs, dst0, text_pos, piece_off, wend, ring, ring_cap, w0);
     if (check(cudaGetLastError(), "agw_layout launch")) return -2;
     if (n_win) {
         static bool attr = false;

@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(32) agw_absorb_thread_kernel(AgState* __restri
     const uint32_t absorbed = s->absorbed + (uint32_t)(win_off[j + 1] - win_off[j]);
     const bool closing = absorbed == s->total;
     unsigned long long rpos = s->rpos;
-    const unsigned long long end = wend[j];
+    const unsigned long long end = wend[j] & ~AGW_TEXT_COMPLETE;
     s->absorbed = absorbed;
     if (rpos + KECCAK_RATE > end && !closing) return;
     unsigned long long a[25];
@@ -1051,7 +1051,7 @@ __global__ void __launch_bounds__(32) agw_absorb_warp_kernel(AgState* __restrict
     const uint32_t absorbed = s->absorbed + (uint32_t)(win_off[j + 1] - win_off[j]);
     const bool closing = absorbed == s->total;
     unsigned long long rpos = s->rpos;
-    const unsigned long long end = wend[j];
+    const unsigned long long end = wend[j] & ~AGW_TEXT_COMPLETE;
     __syncwarp();
     if (L == 0) s->absorbed = absorbed;
     if (rpos + KECCAK_RATE > end && !closing) return;
@@ -1088,6 +1088,72 @@ __global__ void __launch_bounds__(32) agw_absorb_warp_kernel(AgState* __restrict
         keccak_f_warp_u<UNROLL>(lo, hi, c, L);
         rpos = end;
         if (L == 0) { s->phase = 1; s->bpos = 0; }
+    }
+    if (L < 25) s->a[L] = ((unsigned long long)hi << 32) | lo;
+    if (L == 0) s->rpos = rpos;
+}
+
+// Time-sliced form of the ring-fed absorb for batches a little larger than two chains per SM sub-partition (8 per SM): three chains
+// on one sub-partition saturate its shuffle port (3 x 81 issue cycles per round against a 197-cycle round) and run at 247 cycles per
+// round, which would set the time of the whole launch.  Here a launch serves exactly n_active chains -- the aggregates
+// first_active .. first_active + n_active - 1 (mod n_aggs) -- and every chain absorbs at most budget_blocks blocks, so all CTAs of
+// a launch finish together; the caller rotates the set that rests.  A chain closes its message when the text is complete
+// (bit 63 of wend) and fewer than 136 bytes are left.
+template <int UNROLL>
+__global__ void __launch_bounds__(128) agw_absorb_sliced_kernel(AgState* __restrict__ st, const uint8_t* __restrict__ ring, size_t ring_cap,
+                                                                const unsigned long long* __restrict__ wend, size_t n_aggs, size_t first_active,
+                                                                size_t n_active, unsigned long long budget_blocks) {
+    // four chains per CTA, one per SM sub-partition: the even spread over the sub-partitions does not depend on what else is resident
+    const int L = threadIdx.x & 31;
+    const size_t slot = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (slot >= n_active) return;
+    size_t j = first_active + slot;
+    if (j >= n_aggs) j -= n_aggs;
+    AgState* s = st + j;
+    if (s->phase != 0) return;
+    const unsigned long long we = wend[j];
+    const unsigned long long end = we & ~AGW_TEXT_COMPLETE;
+    const bool complete = (we & AGW_TEXT_COMPLETE) != 0;
+    unsigned long long rpos = s->rpos;
+    if (end - rpos > ring_cap) {   // the text writer lapped this chain (budget too small for the text produced): fail loudly, never hash garbage
+        if (L == 0) s->phase = 0xDEAD;
+        return;
+    }
+    unsigned long long nb = (end - rpos) / KECCAK_RATE;
+    if (nb > budget_blocks) nb = budget_blocks;
+    const bool closing = complete && rpos + nb * KECCAK_RATE + KECCAK_RATE > end;
+    if (nb == 0 && !closing) return;
+    const Lane c = lane_init(L);
+    uint32_t lo = 0, hi = 0;
+    if (L < 25) { const unsigned long long v = s->a[L]; lo = (uint32_t)v; hi = (uint32_t)(v >> 32); }
+    const uint8_t* rj = ring + j * ring_cap;
+    uint2 nxt = make_uint2(0u, 0u);
+    if (nb && L < KECCAK_RATE_LANES) nxt = __ldcs(reinterpret_cast<const uint2*>(rj + (rpos % ring_cap)) + L);
+    for (unsigned long long b = 0; b < nb; ++b) {
+        lo ^= nxt.x;
+        hi ^= nxt.y;
+        rpos += KECCAK_RATE;
+        nxt = make_uint2(0u, 0u);
+        if (b + 1 < nb && L < KECCAK_RATE_LANES) nxt = __ldcs(reinterpret_cast<const uint2*>(rj + (rpos % ring_cap)) + L);
+        keccak_f_warp_u<UNROLL>(lo, hi, c, L);
+    }
+    if (closing) {
+        const uint32_t rem = (uint32_t)(end - rpos);
+        if (L < KECCAK_RATE_LANES) {
+            unsigned long long w = 0;
+            if ((uint32_t)(8 * L) < rem) {
+                w = *(reinterpret_cast<const unsigned long long*>(rj + (rpos % ring_cap)) + L);
+                const uint32_t valid = rem - 8 * L;
+                if (valid < 8) w &= (1ULL << (8 * valid)) - 1ULL;
+            }
+            if ((rem >> 3) == (uint32_t)L) w ^= 0x1FULL << (8 * (rem & 7));
+            if (L == 16) w ^= 0x8000000000000000ULL;
+            lo ^= (uint32_t)w;
+            hi ^= (uint32_t)(w >> 32);
+        }
+        keccak_f_warp_u<UNROLL>(lo, hi, c, L);
+        rpos = end;
+        if (L == 0) { s->phase = 1; s->bpos = 0; s->absorbed = s->total; }
     }
     if (L < 25) s->a[L] = ((unsigned long long)hi << 32) | lo;
     if (L == 0) s->rpos = rpos;
@@ -1187,7 +1253,8 @@ static int chain_carveout() {
     static bool done = false;
     if (done) return 0;
     const void* ks[] = {(const void*)agw_absorb_thread_kernel,          (const void*)agw_squeeze_thread_kernel,
-                        (const void*)warpag::agw_absorb_warp_kernel<24>, (const void*)warpag::agw_squeeze_warp_kernel<24>};
+                        (const void*)warpag::agw_absorb_warp_kernel<24>, (const void*)warpag::agw_squeeze_warp_kernel<24>,
+                        (const void*)warpag::agw_absorb_sliced_kernel<24>};
     for (const void* k : ks)
         if (check(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "chain kernel carve-out")) return -2;
     done = true;
@@ -1203,6 +1270,16 @@ int launch_agw_absorb(const fz_ctx* ctx, void* state, const uint8_t* ring, size_
     else
         agw_absorb_thread_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
     return check(cudaGetLastError(), "agw_absorb launch");
+}
+
+int launch_agw_absorb_sliced(const fz_ctx* ctx, void* state, const uint8_t* ring, size_t ring_cap, const unsigned long long* wend, size_t n_aggs,
+                             size_t first_active, size_t n_active, unsigned long long budget_blocks, cudaStream_t st) {
+    if (n_aggs == 0 || n_active == 0) return 0;
+    (void)ctx;
+    if (chain_carveout()) return -2;
+    warpag::agw_absorb_sliced_kernel<24><<<(unsigned)((n_active + 3) / 4), 128, 0, st>>>((AgState*)state, ring, ring_cap, wend, n_aggs, first_active, n_active,
+                                                                                        budget_blocks);
+    return check(cudaGetLastError(), "agw_absorb_sliced launch");
 }
 
 int launch_agw_squeeze(const fz_ctx* ctx, void* state, const unsigned long long* win_off, size_t n_aggs, uint8_t* xof, size_t xof_cap, uint32_t* bpos_out,

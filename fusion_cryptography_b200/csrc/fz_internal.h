@@ -71,8 +71,12 @@ int launch_hash_ag_squeeze(const fz_ctx* ctx, void* state, const unsigned long l
 
 int launch_agw_absorb(const fz_ctx* ctx, void* state, const uint8_t* ring, size_t ring_cap, const unsigned long long* wend,
                       const unsigned long long* win_off, size_t n_aggs, cudaStream_t st);
+int launch_agw_absorb_sliced(const fz_ctx* ctx, void* state, const uint8_t* ring, size_t ring_cap, const unsigned long long* wend, size_t n_aggs,
+                             size_t first_active, size_t n_active, unsigned long long budget_blocks, cudaStream_t st);
 int launch_agw_squeeze(const fz_ctx* ctx, void* state, const unsigned long long* win_off, size_t n_aggs, uint8_t* xof, size_t xof_cap, uint32_t* bpos_out,
                        cudaStream_t st);
+// bit 63 of the per-aggregate message length written by the text stage: the text is complete
+constexpr unsigned long long AGW_TEXT_COMPLETE = 1ULL << 63;
 // fz_hash.cu (windowed text / decode)
 size_t agw_max_piece();
 int launch_agw_text(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, const int32_t* c_hat, const unsigned long long* win_off,

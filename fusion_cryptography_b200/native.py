@@ -489,6 +489,16 @@ def hash_ag_decode(self, xof, xof_cap: int, bpos, win_off, agg_of, n_window: int
     return out
 
 
+def hash_ag_absorb_sliced(self, state, ring, ring_cap: int, wend, n_aggs: int, first_active: int, n_active: int, budget_blocks: int) -> None:
+    self._chk(self.lib.fz_hash_ag_absorb_sliced(self._h, _ptr(state), _ptr(ring), C.c_size_t(ring_cap), _ptr(wend), C.c_size_t(n_aggs),
+                                                C.c_size_t(first_active), C.c_size_t(n_active), C.c_uint64(budget_blocks), self._stream()))
+
+
+def hash_ag_open_sponges(self, state, n_aggs: int) -> int:
+    """Number of aggregates whose message has not been closed yet (phase word of the state records); synchronises."""
+    return int((state.view(torch.int32).view(-1, 128)[:n_aggs, 107] != 1).sum().item())
+
+
 def hash_ag_fast(self, vk_l_s, vk_r_s, dg_s, c_hat_s, counts) -> torch.Tensor:
     """fusion.py:632-652 like hash_ag, through the ring-fed kernels in one window: the message text is written by a warp per signer,
     the sponge chains only permute, the squeezed blocks are decoded in parallel (0.64 s instead of 1.0 s for one capacity aggregate)."""
@@ -588,5 +598,5 @@ def sign_mac_rows(self, sk_hat, c_hat, out=None) -> torch.Tensor:
 for _f in (_u8, _pack_messages, pack_messages, _ws, sha3_256, shake256, hash_msg, format_text, decode_poly, hash_ch, _agg_off, hash_ag, sort_keys, gather_sorted,
            aggregate_sum, fold_partials, verify_check, hash_ag_begin, hash_ag_absorb, hash_ag_squeeze, aggregate_sum_off,
            verify_target, verify_finish, hash_ag_ring, hash_ag_xof_buffer, hash_ag_text, hash_ag_absorb_ring, hash_ag_squeeze_xof,
-           hash_ag_decode, hash_ag_fast, _seed_keys, sample_coef, sample_ntt, keygen, keygen_sign, sign_mac_rows):
+           hash_ag_decode, hash_ag_absorb_sliced, hash_ag_open_sponges, hash_ag_fast, _seed_keys, sample_coef, sample_ntt, keygen, keygen_sign, sign_mac_rows):
     setattr(Context, _f.__name__, _f)

@@ -113,6 +113,10 @@ int fz_hash_ag_text(fz_ctx* ctx, const int32_t* vk_l_w, const int32_t* vk_r_w, c
                     size_t ring_cap, uint64_t* wend_out, void* ws, size_t ws_bytes, void* stream);
 int fz_hash_ag_absorb_ring(fz_ctx* ctx, void* state, const uint8_t* ring, size_t ring_cap, const uint64_t* wend, const uint64_t* win_off, size_t n_aggs,
                            void* stream);
+/* time-sliced absorb (same sponge, fusion.py:591): one launch advances n_active aggregates, first_active.. modulo n_aggs, by at
+ * most budget_blocks blocks each; wend from fz_hash_ag_text (bit 63 set once an aggregate's text is complete) */
+int fz_hash_ag_absorb_sliced(fz_ctx* ctx, void* state, const uint8_t* ring, size_t ring_cap, const uint64_t* wend, size_t n_aggs, size_t first_active,
+                             size_t n_active, uint64_t budget_blocks, void* stream);
 int fz_hash_ag_squeeze_xof(fz_ctx* ctx, void* state, const uint64_t* win_off, size_t n_aggs, uint8_t* xof, size_t xof_cap, uint32_t* bpos_out,
                            void* stream);
 int fz_hash_ag_decode(fz_ctx* ctx, const uint8_t* xof, size_t xof_cap, const uint32_t* bpos, const uint64_t* win_off, const uint32_t* agg_of,

@@ -1,6 +1,8 @@
 """Batched engine (fusion_cryptography_b200.batch) on the GPU: BASELINE configs [2]-[4] at test sizes,
 against the CPU oracle; chunking, sliding key windows, tampered aggregates, the single-aggregate
 sharded path (world size 1) and size-independent properties at larger sizes."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -81,6 +83,16 @@ def test_aggregate_verify_batch(engines, oracle, scheme_golden, secpar):
                 assert torch.equal(aggs, ref_aggs), (impl, max_pos)
     finally:
         eng.ctx.set_option("hash_ag_impl", 0)
+    # the time-sliced absorb (batches a little above 8 warp-chains per SM): pretend the GPU has room for 6 chains, so that 6 of the 8
+    # aggregates advance per launch with a block budget while the resting pair rotates
+    os.environ["FZ_AGG_SLOTS"] = "6"
+    try:
+        for max_pos in (1 << 17, 40, 16):
+            aggs = eng.aggregate(kb.vk_l, kb.vk_r, msgs, sigs, counts, sel=sel_t, max_positions=max_pos)
+            assert torch.equal(aggs, ref_aggs), ("sliced", max_pos)
+            assert host(eng.verify(kb.vk_l, kb.vk_r, msgs, aggs, counts, sel=sel_t, max_positions=max_pos)).tolist() == [0] * len(counts)
+    finally:
+        del os.environ["FZ_AGG_SLOTS"]
     hvl, hvr, hs = host(kb.vk_l), host(kb.vk_r), host(sigs)
     oracle.set_threads(oracle.max_threads())
     off = 0

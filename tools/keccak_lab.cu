@@ -312,6 +312,50 @@ __global__ void coop2_kernel(int perms, unsigned long long* state_out, long long
     if (L == 0) cycles_out[chain] = t1 - t0;
 }
 
+
+// V20: V17 with the column parity (stage 1) through shared memory: 1 STS.64 + 4 LDS.64 instead of 8 shuffles
+template <int UNROLL>
+__device__ __forceinline__ void f_v20(uint32_t& lo, uint32_t& hi, const Lane& c, int L, uint2* buf) {
+    constexpr unsigned long long RC[24] = {
+        0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, 0x0000000080000001ULL,
+        0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+        0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL,
+        0x000000000000800aULL, 0x800000008000000aULL, 0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+    const uint32_t is0 = L == 0 ? 0xffffffffu : 0u;
+#pragma unroll UNROLL
+    for (int r = 0; r < 24; ++r) {
+        uint2* b = buf + (r & 1) * 32;
+        b[L] = make_uint2(lo, hi);
+        __syncwarp();
+        const uint2 a1 = b[c.src5], a2 = b[c.src10], a3 = b[c.src15], a4 = b[c.src20];
+        const uint32_t cl = lo ^ a1.x ^ a2.x ^ a3.x ^ a4.x;
+        const uint32_t ml = SH(cl, c.xm1), pl = SH(cl, c.xp1);
+        const uint32_t ch = hi ^ a1.y ^ a2.y ^ a3.y ^ a4.y;
+        const uint32_t mh = SH(ch, c.xm1), ph = SH(ch, c.xp1);
+        lo ^= ml ^ __funnelshift_l(ph, pl, 1);
+        hi ^= mh ^ __funnelshift_l(pl, ph, 1);
+        rho(lo, hi, c.rot);
+        const uint32_t b0l = SH(lo, c.pi0), b1l = SH(lo, c.pi1), b2l = SH(lo, c.pi2);
+        const uint32_t b0h = SH(hi, c.pi0), b1h = SH(hi, c.pi1), b2h = SH(hi, c.pi2);
+        lo = b0l ^ (~b1l & b2l) ^ ((uint32_t)RC[r] & is0);
+        hi = b0h ^ (~b1h & b2h) ^ ((uint32_t)(RC[r] >> 32) & is0);
+    }
+}
+template <int UNROLL>
+__global__ void coop20_kernel(int perms, unsigned long long* state_out, long long* cycles_out) {
+    __shared__ uint2 sm[4 * 64];
+    const int L = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const Lane c = lane_init(L);
+    const int chain = blockIdx.x * (blockDim.x >> 5) + w;
+    unsigned long long v = L < 25 ? (unsigned long long)(L + 1) * 0x9E3779B97F4A7C15ULL + (unsigned long long)chain : 0ULL;
+    uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    const long long t0 = clock64();
+    for (int p = 0; p < perms; ++p) f_v20<UNROLL>(lo, hi, c, L, sm + w * 64);
+    const long long t1 = clock64();
+    if (chain == 0 && L < 25) state_out[L] = ((unsigned long long)hi << 32) | lo;
+    if (L == 0) cycles_out[chain] = t1 - t0;
+}
+
 // SHFL characteristics: dependent chain (latency) and batches of 8 independent shuffles (issue interval)
 __global__ void shfl_kernel(int iters, int mode, long long* cycles_out, unsigned* sink) {
     const int L = threadIdx.x & 31;
@@ -449,7 +493,7 @@ int main(int argc, char** argv) {
     RUN_COOP2(14, "V14 = V0 unrolled x12")
 
     {   // CTA shape: the same 1250 chains as 1-, 2- and 4-warp CTAs (how evenly do they spread over SMs and sub-partitions?)
-        const int shapes[][2] = {{1250, 32}, {625, 64}, {313, 128}, {1184, 32}, {296, 128}, {592, 32}, {148, 128}};
+        const int shapes[][2] = {{1250, 32}, {625, 64}, {313, 128}, {1184, 32}, {296, 128}, {592, 32}, {148, 128}, {1776, 32}};
         for (auto& sh : shapes) {
             coop2_kernel<17><<<sh[0], sh[1]>>>(10, d_state, d_cyc);
             CK(cudaEventRecord(e0));
@@ -462,6 +506,25 @@ int main(int argc, char** argv) {
             long long mx = 0; double avg = 0;
             for (int i = 0; i < nw; ++i) { mx = cyc[i] > mx ? cyc[i] : mx; avg += (double)cyc[i]; }
             printf("V17 as %4d CTAs x %3d threads: cycles/round avg %.1f max %.1f, %.3f ms\n", sh[0], sh[1], avg / nw / perms / 24.0, (double)mx / perms / 24.0, ms);
+        }
+    }
+
+    {
+        const int shapes[][2] = {{1250, 32}, {1184, 32}, {592, 32}, {148, 32}, {1776, 32}};
+        for (auto& sh : shapes) {
+            coop20_kernel<24><<<sh[0], sh[1]>>>(10, d_state, d_cyc);
+            CK(cudaEventRecord(e0));
+            coop20_kernel<24><<<sh[0], sh[1]>>>(perms, d_state, d_cyc);
+            CK(cudaEventRecord(e1));
+            CK(cudaDeviceSynchronize());
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+            const int nw = sh[0] * sh[1] / 32;
+            CK(cudaMemcpy(cyc.data(), d_cyc, nw * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(got.data(), d_state, 200, cudaMemcpyDeviceToHost));
+            bool ok = true; for (int k = 0; k < 25; ++k) ok = ok && got[k] == ref[k];
+            long long mx = 0; double avg = 0;
+            for (int i = 0; i < nw; ++i) { mx = cyc[i] > mx ? cyc[i] : mx; avg += (double)cyc[i]; }
+            printf("V20 (smem parity) as %4d CTAs x %3d threads: cycles/round avg %.1f max %.1f, %.3f ms %s\n", sh[0], sh[1], avg / nw / perms / 24.0, (double)mx / perms / 24.0, ms, ok ? "ok" : "MISMATCH");
         }
     }
     {
