@@ -535,6 +535,10 @@ __global__ void __launch_bounds__(32) hash_ag_squeeze_thread_kernel(AgState* __r
 __global__ void __launch_bounds__(32) agw_absorb_thread_kernel(AgState* __restrict__ st, const uint8_t* __restrict__ ring, size_t ring_cap,
                                                                 const unsigned long long* __restrict__ wend, const unsigned long long* __restrict__ win_off,
                                                                 size_t n_aggs) {
+    // The next block travels HBM -> shared memory with cp.async while the current one is permuted.  (Plain loads into registers are
+    // sunk by the compiler to just before their use, behind the permutation, which exposed the whole memory latency: 14 % of the
+    // stall samples.)  Word k of thread t sits at stage[buf][k][t]: conflict-free.
+    __shared__ __align__(8) unsigned long long stage[2][KECCAK_RATE_LANES][32];
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_aggs) return;
     AgState* s = st + j;
@@ -548,29 +552,33 @@ __global__ void __launch_bounds__(32) agw_absorb_thread_kernel(AgState* __restri
     unsigned long long a[25];
 #pragma unroll
     for (int k = 0; k < 25; ++k) a[k] = s->a[k];
-    const unsigned long long* base = reinterpret_cast<const unsigned long long*>(ring + j * ring_cap);
-    unsigned long long nxt[KECCAK_RATE_LANES];
+    const uint8_t* base = ring + j * ring_cap;
+    const int t = threadIdx.x;
+    auto fetch = [&](unsigned long long pos, int buf) {   // 17 asynchronous 8-byte copies of the block at message offset pos
+        const uint8_t* src = base + (pos % ring_cap);
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&stage[buf][k][t]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + 8 * k) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     bool have = rpos + KECCAK_RATE <= end;
-    if (have) {
-        const unsigned long long* b = base + (rpos % ring_cap) / 8;
-#pragma unroll
-        for (int k = 0; k < KECCAK_RATE_LANES; ++k) nxt[k] = __ldcs(b + k);
-    }
+    int buf = 0;
+    if (have) fetch(rpos, 0);
     while (have) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-        for (int k = 0; k < KECCAK_RATE_LANES; ++k) a[k] ^= nxt[k];
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) a[k] ^= stage[buf][k][t];
         rpos += KECCAK_RATE;
         have = rpos + KECCAK_RATE <= end;
-        if (have) {
-            const unsigned long long* b = base + (rpos % ring_cap) / 8;
-#pragma unroll
-            for (int k = 0; k < KECCAK_RATE_LANES; ++k) nxt[k] = __ldcs(b + k);
-        }
+        buf ^= 1;
+        if (have) fetch(rpos, buf);
         keccak_f(a);
     }
     if (closing) {   // last (partial) block with SHAKE padding; rem < 136
         const uint32_t rem = (uint32_t)(end - rpos);
-        const unsigned long long* b = base + (rpos % ring_cap) / 8;
+        const unsigned long long* b = reinterpret_cast<const unsigned long long*>(base + (rpos % ring_cap));
 #pragma unroll
         for (int k = 0; k < KECCAK_RATE_LANES; ++k) {
             unsigned long long w = 0;
