@@ -165,6 +165,11 @@ int fz_polymul(fz_ctx* ctx, const int32_t* a, const int32_t* b, int32_t* out, si
     return launch_polymul(ctx, a, b, out, n_polys, (cudaStream_t)stream);
 }
 
+int fz_ntt_pass(fz_ctx* ctx, const int32_t* a, const int32_t* b_hat, int32_t* out, size_t n_polys, void* stream) {
+    FZ_REQUIRE(ctx && (n_polys == 0 || (a && b_hat && out)), "fz_ntt_pass: NULL argument");
+    return launch_ntt_pass(ctx, a, b_hat, out, n_polys, (cudaStream_t)stream);
+}
+
 int fz_matvec(fz_ctx* ctx, const int32_t* A, const int32_t* s, int32_t* out, size_t batch, void* stream) {
     FZ_REQUIRE(ctx && (batch == 0 || (A && s && out)), "fz_matvec: NULL argument");
     return launch_matvec(ctx, A, s, (size_t)ctx->d, (size_t)ctx->ell * ctx->d, out, batch, (cudaStream_t)stream);
@@ -205,9 +210,7 @@ static int host_pipeline(fz_ctx* ctx, int mode, const int32_t* host_in, const in
         int32_t* buf = (int32_t*)((char*)ctx->scratch + (size_t)bi * chunk * poly_bytes);
         rc = check(cudaMemcpyAsync(buf, host_in + done * ctx->d, n * poly_bytes, cudaMemcpyHostToDevice, st[bi]), "H2D");
         if (!rc && mode == 2) {
-            rc = launch_ntt(ctx, 0, buf, buf, n, st[bi]);
-            if (!rc) rc = launch_pointwise(ctx, buf, dev_bhat + done * ctx->d, nullptr, buf, n * ctx->d, st[bi]);
-            if (!rc) rc = launch_ntt(ctx, 1, buf, buf, n, st[bi]);
+            rc = launch_ntt_pass(ctx, buf, dev_bhat + done * ctx->d, buf, n, st[bi]);   // in place: every lane reads its tile before it writes it
         } else if (!rc) {
             rc = launch_ntt(ctx, mode, buf, buf, n, st[bi]);
         }

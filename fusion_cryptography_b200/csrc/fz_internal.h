@@ -31,6 +31,7 @@ int check(cudaError_t e, const char* what);
 int ntt_init_tables(fz_ctx* ctx);
 int launch_ntt(const fz_ctx* ctx, int inverse, const int32_t* in, int32_t* out, size_t n_polys, cudaStream_t st);
 int launch_polymul(const fz_ctx* ctx, const int32_t* a, const int32_t* b, int32_t* out, size_t n_polys, cudaStream_t st);
+int launch_ntt_pass(const fz_ctx* ctx, const int32_t* a, const int32_t* bhat, int32_t* out, size_t n_polys, cudaStream_t st);
 int launch_pointwise_add(const fz_ctx* ctx, const int32_t* a, const int32_t* b, int32_t* out, size_t n_coef, cudaStream_t st);
 int launch_pointwise(const fz_ctx* ctx, const int32_t* a, const int32_t* b, const int32_t* c, int32_t* out, size_t n_coef, cudaStream_t st);
 

@@ -312,6 +312,84 @@ __global__ void __launch_bounds__(NTT_THREADS) polymul_kernel(const int32_t* a, 
     }
 }
 
+// out = INTT(NTT(a) o b_hat): transform(transform(a) * b_hat) of algebra/polynomials.py:391-433 / :341-385 in ONE pass over HBM --
+// a in the coefficient domain, b_hat already in the NTT domain (a public matrix row, a challenge): 3 KiB of traffic per polynomial
+// instead of the 7 KiB of forward transform + pointwise product + inverse transform as three kernels.
+template <int LOGD>
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const int32_t* a, const int32_t* __restrict__ bhat, int32_t* out,   // a == out is allowed
+                                                               
+                                                                size_t n_polys) {
+    using C = Cfg<LOGD>;
+    __shared__ __align__(16) uint32_t smem[(NTT_THREADS / 32) * C::WARP_WORDS];
+    // The lane-dependent twiddles of the two contiguous passes (15 Shoup pairs each) would occupy 60 registers if both sets stayed
+    // resident; they live in shared memory instead, one row per lane-in-polynomial (15 x 8 bytes: the TPP rows fall on distinct
+    // banks), and each set is fetched right before its pass.
+    __shared__ __align__(8) Sh tw_sm[2][C::TPP][15];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tau = lane % C::TPP, pw = lane / C::TPP;
+    uint32_t* tile = smem + warp * C::WARP_WORDS + C::base(pw);
+    if (threadIdx.x < C::TPP) {
+        Sh t[15];
+        load_tw2<LOGD>(C::fwd(), (int)threadIdx.x, t);
+#pragma unroll
+        for (int i = 0; i < 15; ++i) tw_sm[0][threadIdx.x][i] = t[i];
+        load_tw2<LOGD>(C::inv(), (int)threadIdx.x, t);
+#pragma unroll
+        for (int i = 0; i < 15; ++i) tw_sm[1][threadIdx.x][i] = t[i];
+    }
+    __syncthreads();
+    const size_t per_cta = (NTT_THREADS / 32) * C::PPW, stride = (size_t)gridDim.x * per_cta;
+    size_t p = (size_t)blockIdx.x * per_cta + warp * C::PPW + pw;
+    int32_t raw[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) raw[k] = p < n_polys ? a[p * C::D + tau + C::TPP * k] : 0;
+    for (size_t p0 = (size_t)blockIdx.x * per_cta; p0 < n_polys; p0 += stride, p += stride) {
+        const bool live = p < n_polys;
+        uint32_t x[16], y[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = to_lazy(raw[k]);
+        {   // prefetch the next tile's coefficients while this one is transformed
+            const size_t pn = p + stride;
+            const int32_t* src = a + pn * C::D + tau;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) raw[k] = pn < n_polys ? src[C::TPP * k] : 0;
+        }
+        int4 bv[4];   // the 16 NTT-domain coefficients this lane owns after the transpose: issued early, used after the forward transform
+        {
+            const int4* sb = reinterpret_cast<const int4*>(bhat + p * C::D + tau * 16);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bv[c] = live ? ld_stream(sb + c) : make_int4(0, 0, 0, 0);
+        }
+        fwd_strided<LOGD>(x);
+        xchg_s2c<LOGD>(tile, tau, x, y);
+        {
+            Sh tw[15];
+#pragma unroll
+            for (int i = 0; i < 15; ++i) tw[i] = tw_sm[0][tau][i];
+            fwd_contig<LOGD>(y, tw);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            y[4 * c] = mul_lazy(y[4 * c], to_lazy(bv[c].x)); y[4 * c + 1] = mul_lazy(y[4 * c + 1], to_lazy(bv[c].y));
+            y[4 * c + 2] = mul_lazy(y[4 * c + 2], to_lazy(bv[c].z)); y[4 * c + 3] = mul_lazy(y[4 * c + 3], to_lazy(bv[c].w));
+        }
+        {
+            Sh tw[15];
+#pragma unroll
+            for (int i = 0; i < 15; ++i) tw[i] = tw_sm[1][tau][i];
+            inv_contig<LOGD>(y, tw);
+        }
+        xchg_c2s<LOGD>(tile, tau, y, x);
+        int32_t o[16];
+        inv_strided<LOGD>(x, o);
+        if (live) {
+            int32_t* dst = out + p * C::D + tau;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) dst[C::TPP * k] = o[k];
+        }
+    }
+}
+
 // out = cent(a + b); polynomials.py:282-318 (__add__), also the coefficient representation's :114-148
 __global__ void __launch_bounds__(256) pointwise_add_kernel(const int4* __restrict__ a, const int4* __restrict__ b, int4* __restrict__ out, size_t n4) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -434,6 +512,15 @@ int launch_polymul(const fz_ctx* ctx, const int32_t* a, const int32_t* b, int32_
     else
         polymul_kernel<6><<<persistent_grid(ctx, polymul_kernel<6>, NTT_THREADS, (n_polys + 31) / 32), NTT_THREADS, 0, st>>>(a, b, out, n_polys);
     return check(cudaGetLastError(), "polymul launch");
+}
+
+int launch_ntt_pass(const fz_ctx* ctx, const int32_t* a, const int32_t* bhat, int32_t* out, size_t n_polys, cudaStream_t st) {
+    if (n_polys == 0) return 0;
+    if (ctx->logd == 8)
+        ntt_pass_kernel<8><<<persistent_grid(ctx, ntt_pass_kernel<8>, NTT_THREADS, (n_polys + 7) / 8), NTT_THREADS, 0, st>>>(a, bhat, out, n_polys);
+    else
+        ntt_pass_kernel<6><<<persistent_grid(ctx, ntt_pass_kernel<6>, NTT_THREADS, (n_polys + 31) / 32), NTT_THREADS, 0, st>>>(a, bhat, out, n_polys);
+    return check(cudaGetLastError(), "ntt_pass launch");
 }
 
 int launch_pointwise_add(const fz_ctx* ctx, const int32_t* a, const int32_t* b, int32_t* out, size_t n_coef, cudaStream_t st) {

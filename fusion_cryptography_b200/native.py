@@ -163,6 +163,16 @@ class Context:
         return out
 
     # ------------------------------------------------------------------ K4-K5
+    def ntt_pass(self, a, b_hat, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """INTT(NTT(a) o b_hat) fused in one kernel (3 KiB of HBM traffic per polynomial instead of 7 KiB)."""
+        a, b_hat = self._dev(a, "a"), self._dev(b_hat, "b_hat")
+        if a.shape != b_hat.shape:
+            raise ValueError("ntt_pass: shape mismatch")
+        n = self._polys(a, "a")
+        out = torch.empty_like(a) if out is None else out
+        self._chk(self.lib.fz_ntt_pass(self._h, _ptr(a), _ptr(b_hat), _ptr(out), C.c_size_t(n), self._stream()))
+        return out
+
     def matvec(self, A, s, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """out[b] = A (1 x ell) . s[b] (ell x 1);  A: [ell, d], s: [batch, ell, d] -> [batch, d]."""
         A, s = self._dev(A, "A"), self._dev(s, "s")

@@ -56,6 +56,9 @@ int fz_pointwise_add(fz_ctx* ctx, const int32_t* a, const int32_t* b, int32_t* o
 int fz_pointwise_muladd(fz_ctx* ctx, const int32_t* a, const int32_t* b, const int32_t* c, int32_t* out, size_t n_polys, void* stream);
 /* algebra/ntt.py:380-484 ntt_poly_mult (result only): out = INTT(NTT(a) o NTT(b)), fused */
 int fz_polymul(fz_ctx* ctx, const int32_t* a, const int32_t* b, int32_t* out, size_t n_polys, void* stream);
+/* transform(transform(a) * b_hat) (algebra/polynomials.py:391-433 around :341-385) in one pass over HBM: a, out in the coefficient
+ * domain, b_hat in the NTT domain; bit-identical to fz_ntt_fwd -> fz_pointwise_mul -> fz_ntt_inv */
+int fz_ntt_pass(fz_ctx* ctx, const int32_t* a, const int32_t* b_hat, int32_t* out, size_t n_polys, void* stream);
 
 /* GeneralMatrix.__mul__ matmul branch (algebra/matrices.py:121-131) for the scheme's shapes:
  * out[b] = A(1 x ell) . s[b](ell x 1);  A: [ell][d], s: [batch][ell][d], out: [batch][d].

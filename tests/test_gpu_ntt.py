@@ -124,3 +124,30 @@ def test_ntt_host_path(ctxs, oracle):
     assert np.array_equal(hout.numpy(), oracle.ntt_fwd(256, a))
     ctx.ntt_host(hout, hin, inverse=True)
     assert np.array_equal(hin.numpy(), a)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("secpar", [128, 256])
+def test_fused_pass_equals_three_kernels(secpar):
+    """fz_ntt_pass = INTT(NTT(a) o b_hat) in one kernel: the same bits as forward transform, pointwise product, inverse transform
+    (algebra/polynomials.py:391-433, :341-385), on a ragged count, out of place and in place, and against the oracle."""
+    import torch
+    from fusion_cryptography_b200 import native
+    from oracle import oracle as orc
+
+    ctx = native.get_context(secpar)
+    d = ctx.d
+    h = (native.Q - 1) // 2
+    rng = np.random.default_rng(secpar + 7)
+    n = 4099
+    a = rng.integers(-h, h + 1, size=(n, d)).astype(np.int32)
+    b = rng.integers(-h, h + 1, size=(n, d)).astype(np.int32)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    want = ctx.ntt_inv(ctx.pointwise_mul(ctx.ntt_fwd(ta), tb))
+    got = ctx.ntt_pass(ta, tb)
+    assert torch.equal(got, want)
+    inplace = ta.clone()
+    ctx.ntt_pass(inplace, tb, out=inplace)
+    assert torch.equal(inplace, want)
+    k = 64
+    assert np.array_equal(got[:k].cpu().numpy(), orc.ntt_inv(secpar, orc.pointwise_mul(orc.ntt_fwd(secpar, a[:k]), b[:k])))
