@@ -3,9 +3,11 @@ behaviour), with the transforms executed by the sm_100a kernels of libfusion_b20
 
 Reference: algebra/ntt.py.  The number-theory helpers (:17-213) are once-per-parameter-set host
 utilities (out of the hot path) and stay on the host; ``cooley_tukey_ntt`` (:216-291),
-``gentleman_sande_intt`` (:294-377) and ``ntt_poly_mult`` (:380-484) run on the GPU for the scheme's
-parameter sets (q = 2147465729 with d = 64 or 256 and the twiddle tables of psi = 23584283 / 3337519).
-Other (modulus, degree, table) combinations raise NotImplementedError: there is no CPU fallback.
+``gentleman_sande_intt`` (:294-377) and ``ntt_poly_mult`` (:380-484) run on the GPU: on the compile-time
+kernels for the scheme's parameter sets (q = 2147465729 with d = 64 or 256 and the twiddle tables of
+psi = 23584283 / 3337519), on the general ring kernels (``fz_ring_*``) for every other odd prime modulus
+below 2^31, power-of-two degree up to 16384 and caller-supplied table.  Larger moduli or degrees raise
+NotImplementedError: there is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -146,11 +148,12 @@ def _validate(val, modulus, root_order, table, table_name):
         raise NotImplementedError(f"root_order={root_order}=degree={len(val)} is not implemented")
 
 
-def _require_scheme(modulus: int, degree: int, table: List[int], inverse: bool) -> int:
-    if modulus != SCHEME_Q or degree not in _SCHEME or [t % modulus for t in table] != scheme_tables(degree)[1 if inverse else 0]:
-        raise NotImplementedError(
-            "libfusion_b200 transforms only the scheme's parameter sets (q = 2147465729, degree 64 or 256, the reference's "
-            "root-power tables); there is no CPU fallback for other moduli, degrees or tables")
+def _scheme_secpar(modulus: int, degree: int, table: List[int], inverse: bool) -> Optional[int]:
+    """the scheme's security level when (modulus, degree, table) is one of its two parameter sets, else None"""
+    if modulus != SCHEME_Q or degree not in _SCHEME or len(table) != degree:
+        return None
+    if [t % modulus for t in table] != scheme_tables(degree)[1 if inverse else 0]:
+        return None
     return _SCHEME[degree][0]
 
 
@@ -159,28 +162,32 @@ def _centre_list(vals: List[int], modulus: int) -> List[int]:
     return [((v + h) % modulus) - h for v in vals]
 
 
-def _run(secpar: int, vals: List[int], op: str) -> List[int]:
+def _transform(val: List[int], modulus: int, table: List[int], inverse: bool) -> List[int]:
+    """One polynomial through the device: the scheme's compile-time kernels for its two parameter sets, the general ring
+    kernels (fz_ring_*) for every other modulus below 2^31 / degree up to 16384 / table.  No CPU fallback."""
     import torch
 
-    ctx = _native.get_context(secpar)
-    t = torch.tensor(_centre_list(vals, SCHEME_Q), dtype=torch.int32)
-    out = getattr(ctx, op)(t)
-    return out.cpu().tolist()
+    degree = len(val)
+    secpar = _scheme_secpar(modulus, degree, table, inverse)
+    if secpar is not None:
+        eng = _native.get_context(secpar)
+    else:
+        eng = _native.get_ring(modulus, degree, None if inverse else table, table if inverse else None)
+    t = torch.tensor(_centre_list(val, modulus), dtype=torch.int32)
+    return (eng.ntt_inv(t) if inverse else eng.ntt_fwd(t)).cpu().tolist()
 
 
 def cooley_tukey_ntt(val: List[int], modulus: int, root_order: int, bit_rev_root_powers: List[int]) -> List[int]:
     """In place forward negacyclic NTT, natural order in, bit-reversed order out (reference :216-291)."""
     _validate(val, modulus, root_order, bit_rev_root_powers, "root_powers")
-    secpar = _require_scheme(modulus, len(val), bit_rev_root_powers, inverse=False)
-    val[:] = _run(secpar, val, "ntt_fwd")
+    val[:] = _transform(val, modulus, bit_rev_root_powers, inverse=False)
     return val
 
 
 def gentleman_sande_intt(val: List[int], modulus: int, root_order: int, bit_rev_inv_root_powers: List[int]) -> List[int]:
     """In place inverse transform incl. the n^-1 scaling (reference :294-377)."""
     _validate(val, modulus, root_order, bit_rev_inv_root_powers, "inv_root_powers")
-    secpar = _require_scheme(modulus, len(val), bit_rev_inv_root_powers, inverse=True)
-    val[:] = _run(secpar, val, "ntt_inv")
+    val[:] = _transform(val, modulus, bit_rev_inv_root_powers, inverse=True)
     return val
 
 
@@ -203,13 +210,39 @@ def ntt_poly_mult(f: List[int], g: List[int], modulus: int, root: int, inv_root:
     if (root * inv_root) % modulus != 1:
         raise ValueError("Input inv_root must be the inverse of the root of unity.")
     degree = len(f)
-    if modulus != SCHEME_Q or degree not in _SCHEME or root != _SCHEME[degree][1]:
-        raise NotImplementedError("libfusion_b200 multiplies only in the scheme's rings (q = 2147465729, degree 64 / 256, the reference's psi)")
+    if not is_pow_two_geq_two(degree):  # raised by the reference's first cooley_tukey_ntt call (:255-258)
+        raise ValueError(f"len(val)={degree} must be a power of 2 greater than 1")
+    if not all(isinstance(v, int) for v in f) or not all(isinstance(v, int) for v in g):
+        raise TypeError(f"val must be a list of ints, but got {type(f)}")
     import torch
 
-    ctx = _native.get_context(_SCHEME[degree][0])
+    if modulus == SCHEME_Q and degree in _SCHEME and root == _SCHEME[degree][1]:
+        eng = _native.get_context(_SCHEME[degree][0])
+    else:
+        eng = ring_for(modulus, degree, root, inv_root)
     fc, gc = _centre_list(f, modulus), _centre_list(g, modulus)
-    out = ctx.polymul(torch.tensor(fc, dtype=torch.int32), torch.tensor(gc, dtype=torch.int32)).cpu().tolist()
+    out = eng.polymul(torch.tensor(fc, dtype=torch.int32), torch.tensor(gc, dtype=torch.int32)).cpu().tolist()
     f[:] = fc
     g[:] = gc
     return out
+
+
+_POWER_TABLES: Dict[Tuple[int, int, int], List[int]] = {}
+
+
+def power_table(modulus: int, degree: int, root: int) -> List[int]:
+    """bit_reverse_copy([root^i mod q, i < degree]) (algebra/polynomials.py:396-397, :414-417), cached per ring: the
+    reference rebuilds it (degree modular exponentiations and a string-based bit reversal) on every transform"""
+    key = (modulus, degree, root)
+    if key not in _POWER_TABLES:
+        acc, powers = 1, []
+        for _ in range(degree):
+            powers.append(acc)
+            acc = acc * root % modulus
+        _POWER_TABLES[key] = bit_reverse_copy(powers)
+    return _POWER_TABLES[key]
+
+
+def ring_for(modulus: int, degree: int, root: int, inv_root: int):
+    """the device ring (fz_ring) of Z_q[X]/(X^d + 1) with the power tables of (root, inv_root)"""
+    return _native.get_ring(modulus, degree, power_table(modulus, degree, root), power_table(modulus, degree, inv_root))

@@ -112,16 +112,20 @@ class PolynomialRepresentation(object):
     def _ring(self) -> Tuple[int, int, int, int, int]:
         return (self.modulus, self.degree, self.root, self.inv_root, self.root_order)
 
-    def _secpar(self) -> int:
+    def _secpar(self) -> Optional[int]:
+        """the scheme's security level when this is one of its two rings, else None"""
         sc = _ntt._SCHEME.get(self.degree)
         if self.modulus != SCHEME_Q or sc is None or self.root != sc[1] or self.inv_root != sc[2] or self.root_order != 2 * self.degree:
-            raise NotImplementedError(
-                "libfusion_b200 computes only in the scheme's rings (q = 2147465729, degree 64 / 256 with the reference's roots); "
-                "there is no CPU fallback for other parameters")
+            return None
         return sc[0]
 
     def _ctx(self):
-        return _native.get_context(self._secpar())
+        """The device engine of this ring: the scheme context (compile-time kernels) for the scheme's two parameter sets, a general
+        ring (fz_ring_*: any odd prime modulus below 2^31, power-of-two degree up to 16384) otherwise.  No CPU fallback."""
+        secpar = self._secpar()
+        if secpar is not None:
+            return _native.get_context(secpar)
+        return _ntt.ring_for(self.modulus, self.degree, self.root, self.inv_root)
 
     def _get_list(self) -> List[int]:
         if self._vals is None:
@@ -348,10 +352,16 @@ for _cls in (PolynomialRepresentation, PolynomialCoefficientRepresentation, Poly
 
 
 def transform(x: Union[PolynomialCoefficientRepresentation, PolynomialNTTRepresentation]):
-    """Coefficient <-> NTT representation (reference :391-433); the input object is left untouched."""
+    """Coefficient <-> NTT representation (reference :391-433); the input object is left untouched.  Rings the reference's
+    cooley_tukey_ntt / gentleman_sande_intt would reject (root_order other than twice the degree, a degree that is no power of
+    two, a composite modulus) are rejected with the same exceptions (algebra/ntt.py:239-270)."""
     if isinstance(x, PolynomialCoefficientRepresentation):
+        if x._secpar() is None:
+            _ntt._validate(x._peek(), x.modulus, x.root_order, _ntt.power_table(x.modulus, x.degree, x.root), "root_powers")
         return PolynomialNTTRepresentation._from_tensor(x._ring(), x._ctx().ntt_fwd(x._tensor()))
     elif isinstance(x, PolynomialNTTRepresentation):
+        if x._secpar() is None:
+            _ntt._validate(x._peek(), x.modulus, x.root_order, _ntt.power_table(x.modulus, x.degree, x.inv_root), "inv_root_powers")
         return PolynomialCoefficientRepresentation._from_tensor(x._ring(), x._ctx().ntt_inv(x._tensor()))
     else:
         raise NotImplementedError(f"Transform for {type(x)} not implemented")
@@ -381,9 +391,9 @@ def sample_polynomial_coefficient_representation(modulus: int, degree: int, root
                                                    coefficients=coefficients)
     proto = PolynomialCoefficientRepresentation(modulus=modulus, degree=degree, root=root, inv_root=inv_root, root_order=root_order,
                                                 coefficients=[0] * degree)
-    t = proto._ctx().sample_coef([seed], norm_bound=bound, weight_bound=num)[0]
     _random.seed(seed)
-    _host_draw_coefficients(degree, bound, num)  # state side effect only
+    _host_draw_coefficients(degree, bound, num)  # state side effect only (and the reference's ValueError when bound = 0 < num: randrange(0))
+    t = proto._ctx().sample_coef([seed], norm_bound=max(bound, 1), weight_bound=num)[0]
     return PolynomialCoefficientRepresentation._from_tensor(proto._ring(), t)
 
 

@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const int32_t* a,
         {
             const int4* sb = reinterpret_cast<const int4*>(bhat + p * C::D + tau * 16);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) bv[c] = live ? ld_stream(sb + c) : make_int4(0, 0, 0, 0);
+            for (int c = 0; c < 4; ++c) bv[c] = live ? __ldg(sb + c) : make_int4(0, 0, 0, 0);   // L1-allocating: the four 16-byte pieces of a lane share two sectors (a no-allocate load fetched them twice from DRAM: 2.89 GB read per launch against 2.15 GB algorithmic)
         }
         fwd_strided<LOGD>(x);
         xchg_s2c<LOGD>(tile, tau, x, y);

@@ -121,7 +121,7 @@ __device__ __forceinline__ uint32_t mt_randbelow(Mt& s, uint32_t n) {
 // mode 1: public-matrix values randrange(q) - q//2 (polynomials.py:480)
 // keys: [n][key_stride] 32-bit limbs, klen[n] limbs used (>= 1)
 __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(int mode, const uint32_t* __restrict__ keys, int key_stride, const int32_t* __restrict__ klen,
-                                                              size_t n, int d, uint32_t bound, int weight, int32_t* __restrict__ out) {
+                                                              size_t n, int d, uint32_t q, uint32_t bound, int weight, int32_t* __restrict__ out) {
     extern __shared__ __align__(16) uint32_t smp_sm[];
     const size_t i = (size_t)blockIdx.x * SMP_STREAMS + threadIdx.x;
     if (threadIdx.x >= SMP_STREAMS || i >= n) return;   // no block-wide barrier below
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(int mode, const uin
     mt_seed(s, key, kl);
     int32_t* o = out + i * d;
     if (mode == 1) {
-        for (int k = 0; k < d; ++k) o[k] = (int32_t)((long long)mt_randbelow(s, Q) - (long long)HALF);
+        for (int k = 0; k < d; ++k) o[k] = (int32_t)((long long)mt_randbelow(s, q) - (long long)(q / 2));   // q = 2147465729 for the scheme
         return;
     }
     if (weight >= d) {
@@ -213,8 +213,16 @@ int sample_init_tables(fz_ctx* ctx) {
 int launch_sample(const fz_ctx* ctx, int mode, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, uint32_t bound, int weight,
                   int32_t* out, cudaStream_t st) {
     if (n == 0) return 0;
-    sample_kernel<<<(unsigned)((n + SMP_STREAMS - 1) / SMP_STREAMS), SMP_THREADS, SMP_SMEM, st>>>(mode, keys, key_stride, klen, n, ctx->d, bound, weight, out);
+    sample_kernel<<<(unsigned)((n + SMP_STREAMS - 1) / SMP_STREAMS), SMP_THREADS, SMP_SMEM, st>>>(mode, keys, key_stride, klen, n, ctx->d, Q, bound, weight, out);
     return check(cudaGetLastError(), "sample launch");
+}
+
+// the same samplers for any ring (fz_ring_sample_*): degree and modulus are runtime arguments of the kernel
+int launch_sample_ring(int d, uint32_t q, int mode, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, uint32_t bound, int weight,
+                       int32_t* out, cudaStream_t st) {
+    if (n == 0) return 0;
+    sample_kernel<<<(unsigned)((n + SMP_STREAMS - 1) / SMP_STREAMS), SMP_THREADS, SMP_SMEM, st>>>(mode, keys, key_stride, klen, n, d, q, bound, weight, out);
+    return check(cudaGetLastError(), "ring sample launch");
 }
 
 int launch_seeds_to_keys(const fz_ctx* ctx, const unsigned long long* seeds, size_t n, uint32_t* keys, int32_t* klen, cudaStream_t st) {

@@ -215,6 +215,128 @@ class Context:
 _contexts = {}
 
 
+class Ring:
+    """Any ring Z_q[X]/(X^d + 1) of the reference's algebra layer (q an odd prime below 2^31, d = 2^k <= 16384) with caller-supplied
+    bit-reversed power tables; wraps fz_ring_create / fz_ring_destroy.  Same method names as Context for the operations it has."""
+
+    MAX_LOGD = 14
+
+    def __init__(self, modulus: int, degree: int, fwd_table=None, inv_table=None, device: int = 0):
+        if not torch.cuda.is_available():
+            raise FusionB200Error("fusion_cryptography_b200 needs a CUDA device (no CPU fallback)")
+        logd = degree.bit_length() - 1
+        if degree < 2 or (1 << logd) != degree or logd > self.MAX_LOGD or modulus < 3 or modulus % 2 == 0 or modulus >= 1 << 31:
+            raise NotImplementedError(
+                f"libfusion_b200 transforms rings with an odd modulus below 2^31 and a power-of-two degree up to {1 << self.MAX_LOGD} "
+                f"(got modulus={modulus}, degree={degree}); there is no CPU fallback")
+        self.lib = load_library()
+        self.q, self.d, self.logd = modulus, degree, logd
+        self.device_index = device
+        self.device = torch.device("cuda", device)
+        tabs = []
+        for t in (fwd_table, inv_table):
+            if t is None:
+                tabs.append(None)
+                continue
+            if len(t) < degree:
+                raise IndexError("list index out of range")   # what the reference's table[m + i] raises (algebra/ntt.py:280, :360)
+            tabs.append((C.c_uint32 * degree)(*[int(v) % modulus for v in t[:degree]]))
+        self.lib.fz_ring_create.argtypes = [C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        self.lib.fz_ring_destroy.argtypes = [C.c_void_p]
+        with torch.cuda.device(self.device):
+            torch.empty(1, device=self.device)
+            h = C.c_void_p()
+            rc = self.lib.fz_ring_create(C.c_int(device), C.c_uint32(modulus), C.c_int(logd), tabs[0], tabs[1], C.byref(h))
+            if rc:
+                raise FusionB200Error(self.lib.fz_last_error().decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.fz_ring_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    _stream = Context._stream
+    _chk = Context._chk
+    _dev = Context._dev
+    _polys = Context._polys
+
+    def _unary(self, fn, x, out):
+        x = self._dev(x, "x")
+        n = self._polys(x, "x")
+        out = torch.empty_like(x) if out is None else out
+        self._chk(fn(self._h, _ptr(x), _ptr(out), C.c_size_t(n), self._stream()))
+        return out
+
+    def _binary(self, fn, a, b, out, what):
+        a, b = self._dev(a, "a"), self._dev(b, "b")
+        if a.shape != b.shape:
+            raise ValueError(f"{what}: shape mismatch")
+        n = self._polys(a, "a")
+        out = torch.empty_like(a) if out is None else out
+        self._chk(fn(self._h, _ptr(a), _ptr(b), _ptr(out), C.c_size_t(n), self._stream()))
+        return out
+
+    def ntt_fwd(self, x, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self._unary(self.lib.fz_ring_ntt_fwd, x, out)
+
+    def ntt_inv(self, x, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self._unary(self.lib.fz_ring_ntt_inv, x, out)
+
+    def pointwise_mul(self, a, b, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self._binary(self.lib.fz_ring_pointwise_mul, a, b, out, "pointwise_mul")
+
+    def pointwise_add(self, a, b, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self._binary(self.lib.fz_ring_pointwise_add, a, b, out, "pointwise_add")
+
+    def polymul(self, a, b, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """INTT(NTT(a) o NTT(b)), algebra/ntt.py:450-471 (result only)."""
+        fa = self.ntt_fwd(a)
+        fb = self.ntt_fwd(b)
+        self.pointwise_mul(fa, fb, out=fa)
+        return self.ntt_inv(fa, out=out)
+
+    def sample_coef(self, seeds, norm_bound: int = 52, weight_bound=None) -> torch.Tensor:
+        """algebra/polynomials.py:436-467 with integer seeds (device MT19937, CPython's seeding and randrange) -> [n, d]."""
+        keys, klen = Context._seed_keys(self, seeds)
+        out = torch.empty((len(seeds), self.d), dtype=torch.int32, device=self.device)
+        wb = self.d if weight_bound is None else weight_bound
+        self._chk(self.lib.fz_ring_sample_coef(self._h, _ptr(keys), C.c_int(8), _ptr(klen), C.c_size_t(len(seeds)), C.c_int(norm_bound), C.c_int(wb),
+                                               _ptr(out), self._stream()))
+        return out
+
+    def sample_ntt(self, seeds) -> torch.Tensor:
+        """algebra/polynomials.py:470-488 with integer seeds -> [n, d]."""
+        keys, klen = Context._seed_keys(self, seeds)
+        out = torch.empty((len(seeds), self.d), dtype=torch.int32, device=self.device)
+        self._chk(self.lib.fz_ring_sample_ntt(self._h, _ptr(keys), C.c_int(8), _ptr(klen), C.c_size_t(len(seeds)), _ptr(out), self._stream()))
+        return out
+
+
+_rings = {}
+_RING_CACHE = 64
+
+
+def get_ring(modulus: int, degree: int, fwd_table=None, inv_table=None, device: Optional[int] = None) -> Ring:
+    """Rings are cached by (modulus, degree, tables): the reference's callers pass the same few tables over and over."""
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    key = (modulus, degree, None if fwd_table is None else tuple(int(v) % modulus for v in fwd_table[:degree]),
+           None if inv_table is None else tuple(int(v) % modulus for v in inv_table[:degree]), device)
+    r = _rings.get(key)
+    if r is None:
+        if len(_rings) >= _RING_CACHE:
+            _rings.pop(next(iter(_rings))).close()
+        r = _rings[key] = Ring(modulus, degree, fwd_table, inv_table, device)
+    return r
+
+
 def get_context(secpar: int, device: Optional[int] = None) -> Context:
     if device is None:
         device = torch.cuda.current_device() if torch.cuda.is_available() else 0

@@ -177,6 +177,28 @@ int fz_ntt_host(fz_ctx* ctx, int inverse, const int32_t* host_in, int32_t* host_
  * NTT-domain operand b_hat -> INTT -> host out (transform(transform(a) * b_hat)).  Synchronous. */
 int fz_ntt_pass_host(fz_ctx* ctx, const int32_t* host_a, const int32_t* dev_bhat, int32_t* host_out, size_t n_polys);
 
+/* ---- any ring Z_q[X]/(X^d + 1) of the reference's algebra layer ------------------------------------------------------
+ * The scheme's two parameter sets have compile-time kernels (fz_ntt_* above).  A fz_ring computes the same transforms and
+ * pointwise operations for ANY odd prime modulus q < 2^31 and degree d = 2^logd (1 <= logd <= 14) with CALLER-SUPPLIED
+ * bit-reversed power tables, which is the actual contract of cooley_tukey_ntt / gentleman_sande_intt: they take the table
+ * as an argument (algebra/ntt.py:216-219, :294-297) and the reference's own unit tests run them on moduli below 2^17 and
+ * degrees 4..64 (tests/test_ntt.py:18-50).  Tables are HOST arrays of d values (entry 0 is never read by the butterflies);
+ * either (or both, for pointwise operations and sampling only) may be NULL.  Results are canonical centred residues (algebra/ntt.py:93-123). */
+typedef struct fz_ring fz_ring;
+int fz_ring_create(int device, uint32_t q, int logd, const uint32_t* fwd_table, const uint32_t* inv_table, fz_ring** out);
+int fz_ring_destroy(fz_ring* ring);
+/* algebra/ntt.py:271-291 (cooley_tukey_ntt): natural order in, bit-reversed order out; in == out allowed */
+int fz_ring_ntt_fwd(fz_ring* ring, const int32_t* in, int32_t* out, size_t n_polys, void* stream);
+/* algebra/ntt.py:350-377 (gentleman_sande_intt) including the n^-1 = pow(d, q - 2, q) scaling of :353, :373-376 */
+int fz_ring_ntt_inv(fz_ring* ring, const int32_t* in, int32_t* out, size_t n_polys, void* stream);
+/* algebra/polynomials.py:341-385 / :282-318 (and :114-148): cent(x * y), cent(x + y) coefficient by coefficient */
+int fz_ring_pointwise_mul(fz_ring* ring, const int32_t* a, const int32_t* b, int32_t* out, size_t n_polys, void* stream);
+int fz_ring_pointwise_add(fz_ring* ring, const int32_t* a, const int32_t* b, int32_t* out, size_t n_polys, void* stream);
+/* algebra/polynomials.py:436-467 / :470-488 with a seed, for this ring (same key layout as fz_sample_coef / fz_sample_ntt) */
+int fz_ring_sample_coef(fz_ring* ring, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, int norm_bound, int weight_bound, int32_t* out,
+                        void* stream);
+int fz_ring_sample_ntt(fz_ring* ring, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, int32_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -251,6 +251,76 @@ int fzo_polymul(int secpar, const int32_t *a, const int32_t *b, int32_t *out, si
     return 0;
 }
 
+/* ---- any ring Z_q[X]/(X^d + 1), q an odd prime below 2^31, caller-supplied tables ---------------------------------
+ * The same loops as above with the modulus, the degree and the bit-reversed power table as arguments, which is the
+ * signature the reference's functions really have (algebra/ntt.py:216-219, :294-297); the reference's own unit tests
+ * call them on small moduli (tests/test_ntt.py:18-50). */
+
+/* algebra/ntt.py:93-123 with halfmod = q // 2: for 0 <= y < q the shifted term is -1 up to q//2 and 0 above, for any
+ * logmod with 2^logmod >= q/2 (callers pass ceil(log2 q), bit_length or bit_length - 1: ntt.py:272, :448, polynomials.py:61) */
+int64_t fzo_ring_cent(int64_t val, int64_t q) {
+    int64_t y = pymod(val, q);
+    return y > q / 2 ? y - q : y;
+}
+
+/* algebra/ntt.py:271-291 */
+int fzo_ring_ntt_fwd(int64_t q, int d, const int64_t *table, int32_t *polys, size_t n) {
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (long long pi = 0; pi < (long long)n; pi++) {
+        int32_t *val = polys + (size_t)pi * d;
+        int t = d, m = 1;
+        while (m < d) {
+            t /= 2;
+            for (int i = 0; i < m; i++) {
+                int j1 = 2 * i * t, j2 = j1 + t - 1;
+                int64_t s = pymod(table[m + i], q);
+                for (int j = j1; j <= j2; j++) {
+                    int64_t u = val[j], v = pymod((int64_t)val[j + t], q) * s;
+                    val[j] = (int32_t)fzo_ring_cent(u + v, q);
+                    val[j + t] = (int32_t)fzo_ring_cent(u - v, q);
+                }
+            }
+            m *= 2;
+        }
+    }
+    return 0;
+}
+
+/* algebra/ntt.py:350-377, n_inv = pow(n, q - 2, q) (:353) */
+int fzo_ring_ntt_inv(int64_t q, int d, const int64_t *table, int32_t *polys, size_t n) {
+    const int64_t n_inv = powmod(d, q - 2, q);
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (long long pi = 0; pi < (long long)n; pi++) {
+        int32_t *val = polys + (size_t)pi * d;
+        int t = 1, m = d;
+        while (m > 1) {
+            int j1 = 0, h = m / 2;
+            for (int i = 0; i < h; i++) {
+                int j2 = j1 + t - 1;
+                int64_t s = pymod(table[h + i], q);
+                for (int j = j1; j <= j2; j++) {
+                    int64_t u = val[j], v = val[j + t];
+                    val[j] = (int32_t)fzo_ring_cent(u + v, q);
+                    val[j + t] = (int32_t)fzo_ring_cent(pymod(u - v, q) * s, q);
+                }
+                j1 += 2 * t;
+            }
+            t *= 2;
+            m = h;
+        }
+        for (int j = 0; j < d; j++) val[j] = (int32_t)fzo_ring_cent(pymod(val[j], q) * n_inv, q);
+    }
+    return 0;
+}
+
+/* algebra/polynomials.py:341-385 / :282-318: cent(x * y) (mul = 1) or cent(x + y) (mul = 0) */
+int fzo_ring_pointwise(int64_t q, int mul, const int32_t *a, const int32_t *b, int32_t *out, size_t n_coef) {
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (long long i = 0; i < (long long)n_coef; i++)
+        out[i] = (int32_t)fzo_ring_cent(mul ? pymod(a[i], q) * pymod(b[i], q) : (int64_t)a[i] + b[i], q);
+    return 0;
+}
+
 /* algebra/matrices.py:121-131: (1 x ell) . (ell x 1), accumulated left to right
  * with cent after every mul and every add.  A: [ell][d]; s: [batch][ell][d]; out: [batch][d]. */
 static void matvec_one(const fzo_params *p, const int32_t *A, const int32_t *s, int32_t *out) {

@@ -40,6 +40,8 @@ def lib():
         _lib = C.CDLL(_LIB_PATH)
         _lib.fzo_cent.restype = C.c_int64
         _lib.fzo_cent.argtypes = [C.c_int64]
+        _lib.fzo_ring_cent.restype = C.c_int64
+        _lib.fzo_ring_cent.argtypes = [C.c_int64, C.c_int64]
         _lib.fzo_format_vk.restype = C.c_size_t
         _lib.fzo_format_ch.restype = C.c_size_t
         _lib.fzo_format_prehash.restype = C.c_size_t
@@ -129,6 +131,33 @@ def polymul(secpar: int, a, b) -> np.ndarray:
     d = param(secpar, "d")
     out = np.empty_like(a)
     lib().fzo_polymul(C.c_int(secpar), _p(a, _i32p), _p(b, _i32p), _p(out, _i32p), C.c_size_t(a.size // d))
+    return out
+
+
+def _i64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def ring_ntt_fwd(q: int, table, polys) -> np.ndarray:
+    """cooley_tukey_ntt (algebra/ntt.py:271-291) for any odd prime q < 2^31; polys: [n, d] int32, table: d ints."""
+    a = np.atleast_2d(_i32(polys)).copy()
+    t = _i64(table)
+    lib().fzo_ring_ntt_fwd(C.c_int64(q), C.c_int(a.shape[-1]), _p(t, _i64p), _p(a, _i32p), C.c_size_t(a.size // a.shape[-1]))
+    return a
+
+
+def ring_ntt_inv(q: int, table, polys) -> np.ndarray:
+    """gentleman_sande_intt (algebra/ntt.py:350-377) incl. the n^-1 scaling."""
+    a = np.atleast_2d(_i32(polys)).copy()
+    t = _i64(table)
+    lib().fzo_ring_ntt_inv(C.c_int64(q), C.c_int(a.shape[-1]), _p(t, _i64p), _p(a, _i32p), C.c_size_t(a.size // a.shape[-1]))
+    return a
+
+
+def ring_pointwise(q: int, a, b, mul: bool) -> np.ndarray:
+    a, b = _i32(a), _i32(b)
+    out = np.empty_like(a)
+    lib().fzo_ring_pointwise(C.c_int64(q), C.c_int(1 if mul else 0), _p(a, _i32p), _p(b, _i32p), _p(out, _i32p), C.c_size_t(a.size))
     return out
 
 

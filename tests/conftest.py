@@ -43,3 +43,8 @@ def oracle():
 
     orc.lib()
     return orc
+
+
+@pytest.fixture(scope="session")
+def ring_golden():
+    return dict(np.load(os.path.join(GOLDEN, "ring_golden.npz")))

@@ -199,3 +199,26 @@ def test_readme_demo(oracle, golden_json):
     agg = oracle.aggregate(256, vkl, vkr, msgs, np.stack(sigs))
     assert oracle.verify(256, A, vkl, vkr, msgs, agg) == 0
     assert J["verify"] == [True, ""]
+
+
+def test_ring_oracle_matches_reference(ring_golden, oracle):
+    """The general-ring restatement (fzo_ring_*) against the unmodified reference's cooley_tukey_ntt / gentleman_sande_intt /
+    ntt_poly_mult / pointwise operators on 16 rings from (d, q) = (2, 5) to (8192, 2013265921) (tests/golden/make_ring_golden.py)."""
+    G = ring_golden
+    for idx, (d, q) in enumerate(G["rings"]):
+        d, q = int(d), int(q)
+        a, b = G[f"r{idx}_a"], G[f"r{idx}_b"]
+        tw, itw = G[f"r{idx}_tw"], G[f"r{idx}_itw"]
+        assert np.array_equal(oracle.ring_ntt_fwd(q, tw, a), G[f"r{idx}_fwd"]), (d, q)
+        assert np.array_equal(oracle.ring_ntt_inv(q, itw, b), G[f"r{idx}_inv"]), (d, q)
+        assert np.array_equal(oracle.ring_pointwise(q, a, b, True), G[f"r{idx}_mul"]), (d, q)
+        assert np.array_equal(oracle.ring_pointwise(q, a, b, False), G[f"r{idx}_add"]), (d, q)
+        prod = oracle.ring_ntt_inv(q, itw, oracle.ring_pointwise(q, oracle.ring_ntt_fwd(q, tw, a), oracle.ring_ntt_fwd(q, tw, b), True))
+        assert np.array_equal(prod, G[f"r{idx}_prod"]), (d, q)
+    # the scheme's ring through the general functions equals the scheme-specific restatement
+    for secpar in (128, 256):
+        tw, itw = oracle.twiddles(secpar)
+        d = len(tw)
+        x = np.random.default_rng(secpar).integers(-(2**31), 2**31, size=(5, d)).astype(np.int32)
+        assert np.array_equal(oracle.ring_ntt_fwd(2147465729, tw, x), oracle.ntt_fwd(secpar, x))
+        assert np.array_equal(oracle.ring_ntt_inv(2147465729, itw, x), oracle.ntt_inv(secpar, x))
