@@ -421,6 +421,36 @@ def emit(line: dict) -> None:
     out.flush()
 
 
+# SASS mix of the loop body of ntt_pass_kernel<8> (one iteration = one warp = 2 polynomials; cuobjdump -sass of this build, profiles/r01_sass_mix_ntt_pass.txt):
+# 419 IMAD-class instructions (2 issue cycles each on the FMA-heavy pipe of an SM sub-partition, measured with tools/ubench_int.cu) and 186 IMAD.HI / IMAD.WIDE
+# (4 cycles each); 1,397 instructions in all.
+PASS_FMAHEAVY_CYCLES_PER_ITER = 2 * 419 + 4 * 186
+PASS_INSTRUCTIONS_PER_ITER = 1397
+
+
+def int_pipe(ms, n_polys, clocks):
+    """Fraction of the FMA-heavy (IMAD) pipe's peak the fused pass runs at: cycles the pipe needs for the launch (SASS count) / cycles the launch took
+    at the SM clock sampled during the timed region; the ncu counter of the same kernel is quoted beside it."""
+    import torch
+
+    props = torch.cuda.get_device_properties(torch.cuda.current_device())
+    mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+    iters_per_smsp = n_polys / 2.0 / (props.multi_processor_count * 4)
+    need = iters_per_smsp * PASS_FMAHEAVY_CYCLES_PER_ITER
+    took = ms * 1e-3 * mhz * 1e6
+    out = {"pipe": "fmaheavy (IMAD / IMAD.HI / IMAD.WIDE)", "cycles_needed_per_sub_partition": need, "cycles_elapsed": took, "frac": need / took,
+           "issue_slot_frac": iters_per_smsp * PASS_INSTRUCTIONS_PER_ITER / took, "sm_mhz_used": mhz}
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        rec = json.load(open(tp)).get("ntt_pass_kernel<8>", {})
+        for k in ("ncu_fmaheavy_pct", "ncu_alu_pct", "ncu_issue_active_pct", "ncu_dram_pct"):
+            if k in rec:
+                out[k] = rec[k]
+    except Exception:
+        pass
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -587,8 +617,9 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel<8>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": BYTES[dom] * n,
-                         "note": "2,048 modular butterflies + 256 products per 3 KiB: the kernel is bound by integer instruction issue (7 instructions per "
-                                 "butterfly on the FMA-heavy and ALU pipes), not by HBM; the three-kernel form of the same pass moves 7 KiB per polynomial",
+                         "note": "2,048 modular butterflies + 256 products per 3 KiB: the kernel is bound by the FMA-heavy (IMAD) pipe, not by HBM -- see int_pipe; "
+                                 "the three-kernel form of the same pass moves 7 KiB per polynomial",
+                         "int_pipe": int_pipe(kern_ms[dom], n, clocks),
                          "fused_equals_three_kernels": fused_ok,
                          "three_kernel_pass_ms": kern_ms["ntt_fwd"] + kern_ms["pointwise_mul"] + kern_ms["ntt_inv"],
                          "all_kernels": {k: {"ms": kern_ms[k], "GB/s": BYTES[k] * n / (kern_ms[k] / 1000.0) / 1e9,

@@ -237,3 +237,51 @@ def test_ring_samplers(ring_golden):
             rnd.seed(s)
             want.append([rnd.randrange(q) - q // 2 for _ in range(d)])
         assert got == want, (d, q)
+
+
+def test_general_matrix_on_small_rings():
+    """GeneralMatrix + / * over polynomials of small rings, as the reference's tests/test_matrices.py:21-260 exercises them (2 x 2
+    matrices of coefficient-representation polynomials on moduli below 2^17), against a plain schoolbook negacyclic product."""
+    import random
+
+    from fusion_cryptography_b200.algebra.matrices import GeneralMatrix
+    from fusion_cryptography_b200.algebra.ntt import find_primitive_root
+    from fusion_cryptography_b200.algebra.polynomials import (PolynomialCoefficientRepresentation as Poly,
+                                                             PolynomialNTTRepresentation as PolyNTT, transform)
+
+    rng = random.Random(11)
+
+    def school(x, y, d, q):
+        out = [0] * d
+        for i, xi in enumerate(x):
+            for j, yj in enumerate(y):
+                k = i + j
+                out[k % d] += xi * yj * (-1 if k >= d else 1)
+        return [v % q for v in out]
+
+    for d, q in [(4, 17), (8, 97), (16, 193), (64, 257)]:
+        root = find_primitive_root(modulus=q, root_order=2 * d)
+        inv_root = pow(root, q - 2, q)
+        kw = dict(modulus=q, degree=d, root=root, inv_root=inv_root, root_order=2 * d)
+        L = [[[rng.randrange(q) for _ in range(d)] for _ in range(2)] for _ in range(2)]
+        R = [[[rng.randrange(q) for _ in range(d)] for _ in range(2)] for _ in range(2)]
+        ml = GeneralMatrix(matrix=[[Poly(coefficients=list(c), **kw) for c in row] for row in L])
+        mr = GeneralMatrix(matrix=[[Poly(coefficients=list(c), **kw) for c in row] for row in R])
+        prod, ssum = ml * mr, ml + mr
+        for i in range(2):
+            for j in range(2):
+                want = [(a + b) % q for a, b in zip(school(L[i][0], R[0][j], d, q), school(L[i][1], R[1][j], d, q))]
+                assert [c % q for c in prod.matrix[i][j].coefficients] == want, (d, q, i, j)
+                assert [c % q for c in ssum.matrix[i][j].coefficients] == [(a + b) % q for a, b in zip(L[i][j], R[i][j])]
+                assert all(-(q // 2) <= c <= q // 2 for c in prod.matrix[i][j].coefficients)
+        # the same product through the NTT representation (entries transformed one by one), then back
+        nl = GeneralMatrix(matrix=[[transform(p) for p in row] for row in ml.matrix])
+        nr = GeneralMatrix(matrix=[[transform(p) for p in row] for row in mr.matrix])
+        nprod = nl * nr
+        assert nprod.elem_class is PolyNTT
+        for i in range(2):
+            for j in range(2):
+                assert transform(nprod.matrix[i][j]) == prod.matrix[i][j]
+        # matrix * element
+        e = transform(Poly(coefficients=[1] + [0] * (d - 1), **kw))   # the constant polynomial 1
+        assert (nl * e) == nl
