@@ -422,10 +422,10 @@ def emit(line: dict) -> None:
 
 
 # SASS mix of the loop body of ntt_pass_kernel<8> (one iteration = one warp = 2 polynomials; cuobjdump -sass of this build, profiles/r01_sass_mix_ntt_pass.txt):
-# 419 IMAD-class instructions (2 issue cycles each on the FMA-heavy pipe of an SM sub-partition, measured with tools/ubench_int.cu) and 186 IMAD.HI / IMAD.WIDE
-# (4 cycles each); 1,397 instructions in all.
-PASS_FMAHEAVY_CYCLES_PER_ITER = 2 * 419 + 4 * 186
-PASS_INSTRUCTIONS_PER_ITER = 1397
+# 356 IMAD-class instructions (2 issue cycles each on the FMA-heavy pipe of an SM sub-partition, measured with tools/ubench_int.cu) and 186 IMAD.HI / IMAD.WIDE
+# (4 cycles each); 1,233 instructions in all.
+PASS_FMAHEAVY_CYCLES_PER_ITER = 2 * 356 + 4 * 186
+PASS_INSTRUCTIONS_PER_ITER = 1233
 
 
 def int_pipe(ms, n_polys, clocks):

@@ -57,6 +57,18 @@ __device__ __forceinline__ int32_t pl_mul_cent(uint32_t a, uint32_t wlo, uint32_
 // [0, 2q] -> [0, q]
 __device__ __forceinline__ uint32_t red_q(uint32_t x) { return min(x, x - Q); }
 
+// Montgomery product of a reduced residue and ANY int32: yr * b * 2^-32 mod q in [0, q], yr in [0, q].
+// m = lo32(T) * q^-1 makes T - m*q divisible by 2^32, so the quotient is hi32(T) - hi32(m*q) with no borrow; |T| <= q * 2^31
+// puts both high words inside (-q/2, q/2], hence t in (-q, q).  Five instructions (IMAD.WIDE, IMAD, IMAD.HI, IADD3, VIADDMNMX) against the
+// twelve of the pseudo-Mersenne folds for a product of two variables; the caller owes a factor 2^32 (folded into a later constant).
+constexpr uint32_t QINV32 = 1797539329u;   // q^-1 mod 2^32
+__device__ __forceinline__ uint32_t mont_mul(uint32_t yr, int32_t b) {
+    const long long T = (long long)(int32_t)yr * (long long)b;
+    const int32_t m = (int32_t)((uint32_t)T * QINV32);
+    const int32_t t = (int32_t)(T >> 32) - __mulhi(m, (int32_t)Q);
+    return red_q((uint32_t)t + Q);
+}
+
 // any int32 -> lazy unsigned residue in [0, 2q)
 __device__ __forceinline__ uint32_t to_lazy(int32_t x) {
     uint32_t v = (uint32_t)x;

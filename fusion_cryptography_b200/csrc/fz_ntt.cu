@@ -32,9 +32,10 @@ __constant__ Sh c_fwd256[256];
 __constant__ Sh c_inv256[256];
 __constant__ Sh c_fwd64[64];
 __constant__ Sh c_inv64[64];
-// [0] = n^-1, [1] = n^-1 * itw[1]  (last inverse stage with the scaling folded in)
-__constant__ Tw c_last256[2];
-__constant__ Tw c_last64[2];
+// [0] = n^-1, [1] = n^-1 * itw[1]  (last inverse stage with the scaling folded in); [2], [3] = the same times 2^32 (fused pass: pays the
+// 2^-32 of the Montgomery pointwise product)
+__constant__ Tw c_last256[4];
+__constant__ Tw c_last64[4];
 
 template <int LOGD> struct Cfg;
 template <> struct Cfg<8> {
@@ -130,7 +131,7 @@ __device__ __forceinline__ void inv_contig(uint32_t (&y)[16], const Sh (&tw2)[15
 }
 
 // inverse, long-stride stages; the last one carries n^-1 and emits canonical centred values
-template <int LOGD>
+template <int LOGD, int LAST = 0>
 __device__ __forceinline__ void inv_strided(uint32_t (&x)[16], int32_t (&o)[16]) {
     const Sh* tw = Cfg<LOGD>::inv();
 #pragma unroll
@@ -148,8 +149,8 @@ __device__ __forceinline__ void inv_strided(uint32_t (&x)[16], int32_t (&o)[16])
     for (int k = 0; k < 8; ++k) {
         uint32_t a = x[k] + x[k + 8];
         uint32_t b = x[k] - x[k + 8] + Q;
-        o[k] = pl_mul_cent(a, lw[0].lo, lw[0].hi);
-        o[k + 8] = pl_mul_cent(b, lw[1].lo, lw[1].hi);
+        o[k] = pl_mul_cent(a, lw[LAST].lo, lw[LAST].hi);
+        o[k + 8] = pl_mul_cent(b, lw[LAST + 1].lo, lw[LAST + 1].hi);
     }
 }
 
@@ -369,9 +370,9 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const int32_t* a,
             fwd_contig<LOGD>(y, tw);
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            y[4 * c] = mul_lazy(y[4 * c], to_lazy(bv[c].x)); y[4 * c + 1] = mul_lazy(y[4 * c + 1], to_lazy(bv[c].y));
-            y[4 * c + 2] = mul_lazy(y[4 * c + 2], to_lazy(bv[c].z)); y[4 * c + 3] = mul_lazy(y[4 * c + 3], to_lazy(bv[c].w));
+        for (int c = 0; c < 4; ++c) {   // Montgomery products: the factor 2^-32 is paid back by the constants of the last inverse stage
+            y[4 * c] = mont_mul(red_q(y[4 * c]), bv[c].x); y[4 * c + 1] = mont_mul(red_q(y[4 * c + 1]), bv[c].y);
+            y[4 * c + 2] = mont_mul(red_q(y[4 * c + 2]), bv[c].z); y[4 * c + 3] = mont_mul(red_q(y[4 * c + 3]), bv[c].w);
         }
         {
             Sh tw[15];
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const int32_t* a,
         }
         xchg_c2s<LOGD>(tile, tau, y, x);
         int32_t o[16];
-        inv_strided<LOGD>(x, o);
+        inv_strided<LOGD, 2>(x, o);
         if (live) {
             int32_t* dst = out + p * C::D + tau;
 #pragma unroll
@@ -453,7 +454,7 @@ int ntt_init_tables(fz_ctx* ctx) {
         const int logd = levels[L][0], d = 1 << logd;
         const unsigned long long psi = levels[L][1], ipsi = h_powmod(psi, Q - 2), ninv = h_powmod(d, Q - 2);
         Sh f[256], iv[256];
-        Tw last[2];
+        Tw last[4];
         unsigned long long itw1 = 0;
         for (int k = 0; k < d; ++k) {
             unsigned long long w = h_powmod(psi, h_brv(k, logd)), iw = h_powmod(ipsi, h_brv(k, logd));
@@ -465,6 +466,9 @@ int ntt_init_tables(fz_ctx* ctx) {
         }
         last[0] = h_plantard(ninv);
         last[1] = h_plantard((unsigned long long)(((unsigned __int128)ninv * itw1) % Q));
+        const unsigned long long r32 = (1ULL << 32) % Q;
+        last[2] = h_plantard((unsigned long long)(((unsigned __int128)ninv * r32) % Q));
+        last[3] = h_plantard((unsigned long long)(((unsigned __int128)ninv * itw1 % Q) * r32 % Q));
         cudaError_t e;
         if (logd == 8) {
             e = cudaMemcpyToSymbol(c_fwd256, f, sizeof(Sh) * d);
