@@ -9,9 +9,13 @@
 // below 2^17 and degrees 4..64 (tests/test_ntt.py:18-50), not on the scheme's ring.
 //
 // Layout: a CTA owns a TILE of whole polynomials in shared memory (as many as fit in 4,096 coefficients, one polynomial
-// when d is larger), loads them with coalesced 4-byte accesses, runs the log2(d) butterfly stages with one barrier per
-// stage and stores canonical centred residues.  Twiddles are Shoup pairs (w, floor(w * 2^32 / q)) built once per ring
-// on the device; a*w mod q is one IMAD.HI and two IMADs for any 32-bit a because 2q < 2^32 (see fz_common.cuh:sh_mul).
+// when d is larger), loads them with coalesced accesses and runs the log2(d) butterfly stages FOUR AT A TIME: in each pass a
+// thread gathers the 16 coefficients of one radix-16 sub-transform into registers (indices that differ in four consecutive
+// address bits), does its 32 butterflies there and scatters them back, so a degree-256 transform is two shared-memory round
+// trips and two barriers instead of eight.  One pad word per 32 keeps both access shapes (stride >= 32 across the lanes of a
+// warp, and 16 contiguous words per lane in the last pass) free of bank conflicts.  Twiddles are Shoup pairs
+// (w, floor(w * 2^32 / q)) built once per ring on the device and read through L1; a*w mod q is one IMAD.HI and two IMADs for
+// any 32-bit a because 2q < 2^32 (see fz_common.cuh:sh_mul).
 // Results are the canonical centred residues cent() returns (algebra/ntt.py:93-123), whatever logmod the caller of
 // the reference passes: for 0 <= y < q the shifted term is -1 up to q//2 and 0 above.
 #include <cstdio>
@@ -43,6 +47,8 @@ struct RingK {
     int logd;
     Sh ninv;
     unsigned long long mu;
+    uint32_t mu32;   // floor(2^32 / q)
+    uint32_t c31;    // 2^31 mod q
 };
 
 __device__ __forceinline__ uint32_t rq_mul(uint32_t a, Sh w, uint32_t q) {   // a*w mod q in [0, q); a any 32-bit value
@@ -57,13 +63,18 @@ __device__ __forceinline__ uint32_t rq_sub(uint32_t a, uint32_t b, uint32_t q) {
     uint32_t s = a - b + q;
     return min(s, s - q);
 }
-// any int32 -> [0, q)   (Python's %: the result takes the sign of the modulus)
-__device__ __forceinline__ uint32_t rq_from(int32_t x, uint32_t q) {
-    int32_t r = x % (int32_t)q;
-    return (uint32_t)(r < 0 ? r + (int32_t)q : r);
+// any int32 -> [0, q) (Python's %).  x + 2^31 is non-negative; floor((x + 2^31) * mu32 / 2^32) is floor((x + 2^31) / q) or one less, so one
+// fused add-min finishes the reduction, and 2^31 mod q is taken off again: six instructions instead of a 32-bit division.
+__device__ __forceinline__ uint32_t rq_from(int32_t x, const RingK& k) {
+    const uint32_t u = (uint32_t)x ^ 0x80000000u;
+    uint32_t r = u - __umulhi(u, k.mu32) * k.q;      // [0, 2q)
+    r = min(r, r - k.q);
+    return rq_sub(r, k.c31, k.q);
 }
 // [0, q) -> canonical centred residue, algebra/ntt.py:120-123
 __device__ __forceinline__ int32_t rq_cent(uint32_t y, uint32_t q, uint32_t half) { return y > half ? (int32_t)(y - q) : (int32_t)y; }
+
+__device__ __forceinline__ int phys(int e) { return e + (e >> 5); }   // one pad word per 32
 
 __global__ void ring_table_kernel(const uint32_t* __restrict__ table, Sh* out, int d, uint32_t q) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -73,79 +84,181 @@ __global__ void ring_table_kernel(const uint32_t* __restrict__ table, Sh* out, i
     out[i].wq = (uint32_t)(((unsigned long long)w << 32) / q);
 }
 
-// One tile = `polys` whole polynomials of d coefficients in shared memory.
-// Forward (algebra/ntt.py:271-291): stages m = 1, 2, ..., d/2 with t = d/(2m); butterfly (u, v) -> (u + v*s, u - v*s), s = tw[m + i].
-// Inverse (algebra/ntt.py:354-377): stages t = 1, 2, ..., d/2 with h = d/(2t); (u, v) -> (u + v, (u - v)*s), s = itw[h + i]; then * n^-1.
-template <bool INVERSE>
+// One pass = R consecutive butterfly stages on the 2^R coefficients whose (polynomial-local) indices are
+//     (hi << (lo_bits + R)) | (k << lo_bits) | lo,   k = 0 .. 2^R - 1,
+// held in registers by one thread.
+// Forward (algebra/ntt.py:271-291): stage with t = 2^lt pairs (j, j + t) and multiplies by tw[d / 2^(lt+1) + (j >> (lt + 1))]; the pass runs
+// lt = lo_bits + R - 1 down to lo_bits, butterfly (u, v) -> (u + v*s, u - v*s).
+// Inverse (algebra/ntt.py:354-372): lt = lo_bits up to lo_bits + R - 1, (u, v) -> (u + v, (u - v)*s), s = itw[d / 2^(lt+1) + (j >> (lt + 1))].
+template <int R, bool INVERSE, int GS>
+__device__ __forceinline__ void ring_pass(uint32_t* tile, const Sh* __restrict__ tw, uint32_t q, int logd, int lo_bits, int n_items, int tid) {
+    constexpr int N = 1 << R;
+    for (int w = tid; w < n_items; w += GS) {
+        const int p = w >> (logd - R), wi = w & ((1 << (logd - R)) - 1);
+        const int lo = wi & ((1 << lo_bits) - 1), hi = wi >> lo_bits;
+        const int base = (p << logd) + (hi << (lo_bits + R)) + lo;
+        uint32_t x[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) x[k] = tile[phys(base + (k << lo_bits))];
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            if (!INVERSE) {
+                const int lt = lo_bits + R - 1 - s, dk = N >> (s + 1);
+                const Sh* row = tw + ((1 << logd) >> (lt + 1)) + (hi << s);
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    if (k & dk) continue;
+                    const Sh tws = row[k >> (R - s)];
+                    const uint32_t u = x[k], v = rq_mul(x[k + dk], tws, q);
+                    x[k] = rq_add(u, v, q);
+                    x[k + dk] = rq_sub(u, v, q);
+                }
+            } else {
+                const int lt = lo_bits + s, dk = 1 << s;
+                const Sh* row = tw + ((1 << logd) >> (lt + 1)) + (hi << (R - 1 - s));
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    if (k & dk) continue;
+                    const Sh tws = row[k >> (s + 1)];
+                    const uint32_t u = x[k], v = x[k + dk];
+                    x[k] = rq_add(u, v, q);
+                    x[k + dk] = rq_mul(u - v + q, tws, q);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) tile[phys(base + (k << lo_bits))] = x[k];
+    }
+}
+
+template <bool INVERSE, int GS>
+__device__ __forceinline__ void ring_pass_r(int r, uint32_t* tile, const Sh* __restrict__ tw, uint32_t q, int logd, int lo_bits, int n_items, int tid) {
+    switch (r) {
+        case 4: ring_pass<4, INVERSE, GS>(tile, tw, q, logd, lo_bits, n_items, tid); break;
+        case 3: ring_pass<3, INVERSE, GS>(tile, tw, q, logd, lo_bits, n_items, tid); break;
+        case 2: ring_pass<2, INVERSE, GS>(tile, tw, q, logd, lo_bits, n_items, tid); break;
+        default: ring_pass<1, INVERSE, GS>(tile, tw, q, logd, lo_bits, n_items, tid); break;
+    }
+}
+
+// global -> tile: 16-byte loads, four per thread in flight before the first is consumed (VEC needs 16-byte aligned polynomials; the scalar form
+// serves unaligned callers and the d = 2 tails)
+template <bool VEC, int GS>
+__device__ __forceinline__ void ring_load(uint32_t* tile, const int32_t* src, int n_coef, const RingK& k, int tid) {
+    if (VEC) {
+        const int4* src4 = reinterpret_cast<const int4*>(src);
+        const int n4 = n_coef >> 2;
+        for (int i0 = 0; i0 < n4; i0 += 4 * GS) {
+            int4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j * GS + tid;
+                v[j] = i < n4 ? ld_stream(src4 + i) : make_int4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j * GS + tid;
+                if (i < n4) {
+                    uint32_t* t = tile + phys(4 * i);   // 4 * i .. 4 * i + 3 share one 32-word block: contiguous
+                    t[0] = rq_from(v[j].x, k); t[1] = rq_from(v[j].y, k); t[2] = rq_from(v[j].z, k); t[3] = rq_from(v[j].w, k);
+                }
+            }
+        }
+        for (int e = (n4 << 2) + tid; e < n_coef; e += GS) tile[phys(e)] = rq_from(src[e], k);
+    } else {
+        for (int e = tid; e < n_coef; e += GS) tile[phys(e)] = rq_from(src[e], k);
+    }
+}
+
+template <bool VEC, bool SCALE, int GS>
+__device__ __forceinline__ void ring_store(const uint32_t* tile, int32_t* dst, int n_coef, const RingK& k, int tid) {
+    auto fin = [&](uint32_t y) { return rq_cent(SCALE ? rq_mul(y, k.ninv, k.q) : y, k.q, k.half); };
+    if (VEC) {
+        int4* dst4 = reinterpret_cast<int4*>(dst);
+        const int n4 = n_coef >> 2;
+        for (int i = tid; i < n4; i += GS) {
+            const uint32_t* t = tile + phys(4 * i);
+            st_stream(dst4 + i, make_int4(fin(t[0]), fin(t[1]), fin(t[2]), fin(t[3])));
+        }
+        for (int e = (n4 << 2) + tid; e < n_coef; e += GS) dst[e] = fin(tile[phys(e)]);
+    } else {
+        for (int e = tid; e < n_coef; e += GS) dst[e] = fin(tile[phys(e)]);
+    }
+}
+
+// WARP = false: one tile per CTA (any degree), barriers between passes.  WARP = true (d <= 512): every warp owns a private tile of 512
+// coefficients (512 / d whole polynomials: one radix-16 item per lane and pass) and only ever waits for itself (__syncwarp).
+constexpr int RING_WARP_TILE = 512;
+
+template <bool INVERSE, bool VEC, bool WARP>
 __global__ void __launch_bounds__(RING_THREADS) ring_ntt_kernel(RingK k, const Sh* __restrict__ tw, const int32_t* in, int32_t* out, size_t n_polys,
                                                                  int polys_per_tile) {
-    extern __shared__ __align__(16) uint32_t tile[];
+    extern __shared__ __align__(16) uint32_t ring_smem[];
+    constexpr int GS = WARP ? 32 : RING_THREADS;
+    const int tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+    uint32_t* tile = WARP ? ring_smem + (threadIdx.x >> 5) * (RING_WARP_TILE + RING_WARP_TILE / 32) : ring_smem;
+    auto sync = [] { if (WARP) __syncwarp(); else __syncthreads(); };
     const uint32_t q = k.q;
-    const int logd = k.logd, d = 1 << logd;
+    const int logd = k.logd;
     const size_t n_tiles = (n_polys + polys_per_tile - 1) / polys_per_tile;
-    for (size_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+    const size_t first = WARP ? (size_t)blockIdx.x * (RING_THREADS / 32) + (threadIdx.x >> 5) : (size_t)blockIdx.x;
+    const size_t step = WARP ? (size_t)gridDim.x * (RING_THREADS / 32) : (size_t)gridDim.x;
+    for (size_t tl = first; tl < n_tiles; tl += step) {
         const size_t p0 = tl * polys_per_tile;
         const int live = (int)min((size_t)polys_per_tile, n_polys - p0);
         const int n_coef = live << logd;
-        const int32_t* src = in + (p0 << logd);
-        for (int e = threadIdx.x; e < n_coef; e += RING_THREADS) tile[e] = rq_from(src[e], q);
-        __syncthreads();
-        const int n_bf = n_coef >> 1;
+        ring_load<VEC, GS>(tile, in + (p0 << logd), n_coef, k, tid);
+        sync();
+        int32_t* dst = out + (p0 << logd);
         if (!INVERSE) {
-            for (int lt = logd - 1; lt >= 0; --lt) {           // t = 2^lt, m = d / (2t)
-                const int t = 1 << lt, m = d >> (lt + 1);
-                for (int b = threadIdx.x; b < n_bf; b += RING_THREADS) {
-                    const int p = b >> (logd - 1), kk = b & ((d >> 1) - 1);
-                    const int i = kk >> lt, j = kk & (t - 1);
-                    const int idx = (p << logd) + ((i << (lt + 1)) | j);
-                    const Sh w = tw[m + i];
-                    const uint32_t u = tile[idx], v = rq_mul(tile[idx + t], w, q);
-                    tile[idx] = rq_add(u, v, q);
-                    tile[idx + t] = rq_sub(u, v, q);
-                }
-                __syncthreads();
+            for (int a = logd - 1; a >= 0;) {              // stages lt = a, a - 1, ..., a - r + 1
+                const int r = a + 1 < 4 ? a + 1 : 4;
+                ring_pass_r<false, GS>(r, tile, tw, q, logd, a - r + 1, live << (logd - r), tid);
+                sync();
+                a -= r;
             }
-            int32_t* dst = out + (p0 << logd);
-            for (int e = threadIdx.x; e < n_coef; e += RING_THREADS) dst[e] = rq_cent(tile[e], q, k.half);
+            ring_store<VEC, false, GS>(tile, dst, n_coef, k, tid);
         } else {
-            for (int lt = 0; lt < logd; ++lt) {                // t = 2^lt, h = d / (2t)
-                const int t = 1 << lt, h = d >> (lt + 1);
-                for (int b = threadIdx.x; b < n_bf; b += RING_THREADS) {
-                    const int p = b >> (logd - 1), kk = b & ((d >> 1) - 1);
-                    const int i = kk >> lt, j = kk & (t - 1);
-                    const int idx = (p << logd) + ((i << (lt + 1)) | j);
-                    const Sh w = tw[h + i];
-                    const uint32_t u = tile[idx], v = tile[idx + t];
-                    tile[idx] = rq_add(u, v, q);
-                    tile[idx + t] = rq_mul(u - v + q, w, q);
-                }
-                __syncthreads();
+            for (int a = 0; a < logd;) {                   // stages lt = a, a + 1, ..., a + r - 1
+                const int r = logd - a < 4 ? logd - a : 4;
+                ring_pass_r<true, GS>(r, tile, tw, q, logd, a, live << (logd - r), tid);
+                sync();
+                a += r;
             }
-            int32_t* dst = out + (p0 << logd);
-            for (int e = threadIdx.x; e < n_coef; e += RING_THREADS) dst[e] = rq_cent(rq_mul(tile[e], k.ninv, q), q, k.half);
+            ring_store<VEC, true, GS>(tile, dst, n_coef, k, tid);
         }
-        __syncthreads();   // the tile is reused by the next iteration
+        sync();   // the tile is reused by the next iteration
     }
 }
 
 // cent(x * y) / cent(x + y), algebra/polynomials.py:341-385, :282-318 (and :114-148 for the coefficient representation's +)
 template <bool MUL>
-__global__ void __launch_bounds__(256) ring_pointwise_kernel(RingK k, const int32_t* __restrict__ a, const int32_t* __restrict__ b, int32_t* __restrict__ out,
-                                                              size_t n) {
-    const uint32_t q = k.q;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t x = rq_from(a[i], q), y = rq_from(b[i], q);
-        uint32_t r;
-        if (MUL) {
-            const unsigned long long P = (unsigned long long)x * y;             // < 2^62
-            const unsigned long long est = __umul64hi(P, k.mu);                 // floor(P / q) or one less
-            r = (uint32_t)(P - est * q);                                        // [0, 2q), exact in 32 bits since 2q < 2^32
-            r = min(r, r - q);
-        } else {
-            r = rq_add(x, y, q);
-        }
-        out[i] = rq_cent(r, q, k.half);
+__device__ __forceinline__ int32_t ring_pw1(const RingK& k, int32_t a, int32_t b) {
+    const uint32_t q = k.q, x = rq_from(a, k), y = rq_from(b, k);
+    uint32_t r;
+    if (MUL) {
+        const unsigned long long P = (unsigned long long)x * y;             // < 2^62
+        const unsigned long long est = __umul64hi(P, k.mu);                 // floor(P / q) or one less
+        r = (uint32_t)(P - est * q);                                        // [0, 2q), exact in 32 bits since 2q < 2^32
+        r = min(r, r - q);
+    } else {
+        r = rq_add(x, y, q);
     }
+    return rq_cent(r, q, k.half);
+}
+
+// n4 int4 groups (16-byte aligned operands), then the scalar kernel below finishes the tail / unaligned calls
+template <bool MUL>
+__global__ void __launch_bounds__(256) ring_pointwise4_kernel(RingK k, const int4* __restrict__ a, const int4* __restrict__ b, int4* __restrict__ out, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const int4 va = ld_stream(a + i), vb = ld_stream(b + i);
+        st_stream(out + i, make_int4(ring_pw1<MUL>(k, va.x, vb.x), ring_pw1<MUL>(k, va.y, vb.y), ring_pw1<MUL>(k, va.z, vb.z), ring_pw1<MUL>(k, va.w, vb.w)));
+    }
+}
+
+template <bool MUL>
+__global__ void __launch_bounds__(256) ring_pointwise_kernel(RingK k, const int32_t* a, const int32_t* b, int32_t* out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = ring_pw1<MUL>(k, a[i], b[i]);
 }
 
 static uint32_t host_powmod(uint32_t b, uint32_t e, uint32_t m) {
@@ -161,6 +274,8 @@ static uint32_t host_powmod(uint32_t b, uint32_t e, uint32_t m) {
 static RingK ring_k(const fz_ring* r) {
     RingK k;
     k.q = r->q; k.half = r->half; k.logd = r->logd; k.ninv = r->ninv; k.mu = r->mu;
+    k.mu32 = (uint32_t)((1ULL << 32) / r->q);
+    k.c31 = (uint32_t)((1ULL << 31) % r->q);
     return k;
 }
 
@@ -180,28 +295,50 @@ static int upload_table(fz_ring* r, const uint32_t* host_table, Sh** out) {
     return rc;
 }
 
-template <bool INVERSE>
-static int launch_ring_ntt(fz_ring* r, const int32_t* in, int32_t* out, size_t n_polys, cudaStream_t st) {
-    if (n_polys == 0) return 0;
-    const int polys_per_tile = r->d >= RING_TILE ? 1 : RING_TILE / r->d;
-    const size_t smem = sizeof(uint32_t) * (size_t)(r->d >= RING_TILE ? r->d : RING_TILE);
-    auto kern = ring_ntt_kernel<INVERSE>;
+template <bool INVERSE, bool VEC, bool WARP>
+static int launch_ring_ntt_v(fz_ring* r, const int32_t* in, int32_t* out, size_t n_polys, cudaStream_t st) {
+    const size_t tile_words = WARP ? (size_t)RING_WARP_TILE : (size_t)(r->d >= RING_TILE ? r->d : RING_TILE);
+    const int polys_per_tile = (size_t)r->d >= tile_words ? 1 : (int)(tile_words / r->d);
+    const size_t smem = sizeof(uint32_t) * (tile_words + tile_words / 32) * (WARP ? RING_THREADS / 32 : 1);   // one pad word per 32
+    auto kern = ring_ntt_kernel<INVERSE, VEC, WARP>;
     if (smem > 48 * 1024 && check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ring NTT shared memory")) return -2;
     int per_sm = 0;
     if (check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RING_THREADS, smem), "ring NTT occupancy")) return -2;
     const size_t n_tiles = (n_polys + polys_per_tile - 1) / polys_per_tile;
+    const size_t want = WARP ? (n_tiles + RING_THREADS / 32 - 1) / (RING_THREADS / 32) : n_tiles;
     const size_t cap = (size_t)r->sm_count * (per_sm > 0 ? per_sm : 1);
-    kern<<<(unsigned)(n_tiles < cap ? n_tiles : cap), RING_THREADS, smem, st>>>(ring_k(r), INVERSE ? r->inv : r->fwd, in, out, n_polys, polys_per_tile);
+    kern<<<(unsigned)(want < cap ? want : cap), RING_THREADS, smem, st>>>(ring_k(r), INVERSE ? r->inv : r->fwd, in, out, n_polys, polys_per_tile);
     return check(cudaGetLastError(), "ring NTT launch");
+}
+
+template <bool INVERSE>
+static int launch_ring_ntt(fz_ring* r, const int32_t* in, int32_t* out, size_t n_polys, cudaStream_t st) {
+    if (n_polys == 0) return 0;
+    // every tile starts on a multiple of 16 bytes when the operands do (a tile is 512 or >= 4,096 coefficients)
+    const bool vec = (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
+    if (r->d <= RING_WARP_TILE)
+        return vec ? launch_ring_ntt_v<INVERSE, true, true>(r, in, out, n_polys, st) : launch_ring_ntt_v<INVERSE, false, true>(r, in, out, n_polys, st);
+    return vec ? launch_ring_ntt_v<INVERSE, true, false>(r, in, out, n_polys, st) : launch_ring_ntt_v<INVERSE, false, false>(r, in, out, n_polys, st);
 }
 
 template <bool MUL>
 static int launch_ring_pointwise(fz_ring* r, const int32_t* a, const int32_t* b, int32_t* out, size_t n_polys, cudaStream_t st) {
     const size_t n = n_polys << r->logd;
     if (n == 0) return 0;
-    const size_t want = (n + 255) / 256, cap = (size_t)r->sm_count * 8;
-    ring_pointwise_kernel<MUL><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(ring_k(r), a, b, out, n);
-    return check(cudaGetLastError(), "ring pointwise launch");
+    const size_t cap = (size_t)r->sm_count * 8;
+    size_t done = 0;
+    if ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0 && n >= 4) {
+        const size_t n4 = n / 4, want = (n4 + 255) / 256;
+        ring_pointwise4_kernel<MUL><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(ring_k(r), (const int4*)a, (const int4*)b, (int4*)out, n4);
+        if (check(cudaGetLastError(), "ring pointwise launch")) return -2;
+        done = n4 * 4;
+    }
+    if (done < n) {
+        const size_t rest = n - done, want = (rest + 255) / 256;
+        ring_pointwise_kernel<MUL><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(ring_k(r), a + done, b + done, out + done, rest);
+        if (check(cudaGetLastError(), "ring pointwise launch")) return -2;
+    }
+    return 0;
 }
 
 }  // namespace fz

@@ -73,6 +73,15 @@ def test_ring_kernels_match_oracle_on_ragged_batches(oracle, d, q, n):
     assert np.array_equal(host(r.ntt_inv(dev(a))), oracle.ring_ntt_inv(q, itw, a))
     assert np.array_equal(host(r.pointwise_mul(dev(a), dev(b))), oracle.ring_pointwise(q, a, b, True))
     assert np.array_equal(host(r.pointwise_add(dev(a), dev(b))), oracle.ring_pointwise(q, a, b, False))
+    # operands that do not start on a 16-byte boundary take the scalar load / store path
+    buf = torch.zeros(2 * n * d + 3, dtype=torch.int32, device="cuda")
+    ua, ub = buf[1:1 + n * d].view(n, d), buf[n * d + 2:2 * n * d + 2].view(n, d)
+    ua.copy_(dev(a)), ub.copy_(dev(b))
+    assert ua.data_ptr() % 16 != 0
+    assert np.array_equal(host(r.ntt_fwd(ua)), fa)
+    assert np.array_equal(host(r.pointwise_mul(ua, ub)), oracle.ring_pointwise(q, a, b, True))
+    r.ntt_inv(ua, out=ua)
+    assert np.array_equal(host(ua), oracle.ring_ntt_inv(q, itw, a))
     # INTT(NTT(a)) is the canonical centred form of a
     h = q // 2
     assert np.array_equal(host(r.ntt_inv(dev(fa))), ((a.astype(np.int64) + h) % q - h).astype(np.int32))
