@@ -5,6 +5,7 @@ element classes fall back to the reference's element-wise semantics through the 
 """
 from __future__ import annotations
 
+from copy import deepcopy  # noqa: F401  (the reference's module exposes it, and its tests reach it through `from algebra.matrices import *`)
 from typing import List, Union
 
 try:

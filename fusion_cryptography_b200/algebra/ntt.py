@@ -11,6 +11,7 @@ NotImplementedError: there is no CPU fallback.
 """
 from __future__ import annotations
 
+from copy import deepcopy  # noqa: F401  (public names of the reference's module: algebra/ntt.py:4-6)
 from math import ceil, log2
 from typing import Dict, List, Optional, Tuple
 
@@ -22,6 +23,15 @@ except ImportError:  # imported as top-level `algebra.ntt` (drop-in layout)
 _PRIME_CACHE: Dict[int, bool] = {}
 _ROOT_CACHE: Dict[Tuple[int, int], Optional[int]] = {}
 _TABLES: Dict[int, Tuple[List[int], List[int]]] = {}
+
+# the reference's module-level caches (algebra/ntt.py:8-14), under their public names: the first two are the ones this module fills
+CACHED_IS_ODD_PRIME = _PRIME_CACHE
+CACHED_FIND_PRIMITIVE_ROOT = _ROOT_CACHE
+CACHED_PRIMITIVE_ROOTS: Dict[Tuple[int, int], int] = {}
+CACHED_HAS_PRIMITIVE_ROOT_OF_UNITY: Dict[Tuple[int, int], bool] = {}
+CACHED_IS_POW_TWO_GEQ_TWO: Dict[int, bool] = {}
+CACHED_IS_ROOT_OF_UNITY: Dict[Tuple[int, int, int], bool] = {}
+CACHED_IS_PRIMITIVE_ROOT_OF_UNITY: Dict[Tuple[int, int, int], bool] = {}
 
 SCHEME_Q = 2147465729
 _SCHEME = {64: (128, 23584283, 540632852), 256: (256, 3337519, 1978410468)}  # degree -> (secpar, root, inv_root)
@@ -246,3 +256,25 @@ def power_table(modulus: int, degree: int, root: int) -> List[int]:
 def ring_for(modulus: int, degree: int, root: int, inv_root: int):
     """the device ring (fz_ring) of Z_q[X]/(X^d + 1) with the power tables of (root, inv_root)"""
     return _native.get_ring(modulus, degree, power_table(modulus, degree, root), power_table(modulus, degree, inv_root))
+
+
+def ntt_poly_mult_half(f: List[int], g: List[int], modulus: int, root: int, inv_root: int, root_order: int) -> List[int]:
+    """Present for name compatibility only.  The reference's function (algebra/ntt.py:487-596) cannot return a product: for every input
+    that passes its argument checks it ends in ``ValueError: not enough values to unpack (expected 3, got 2)`` (it unpacks three names
+    from pairs, :573-576; observed by running it -- SURVEY quirk Q7).  The same argument errors are raised here, then that ValueError."""
+    if not (isinstance(f, list) and isinstance(g, list) and isinstance(modulus, int) and isinstance(root, int) and isinstance(inv_root, int)
+            and isinstance(root_order, int)):
+        raise ValueError("Input f and g must be lists of integers, input modulus must be integer, and input root and inv_root must be integer.")
+    if not is_odd_prime(modulus):
+        raise ValueError("Modulus must be an odd prime.")
+    if not is_pow_two_geq_two(root_order):
+        raise ValueError("Root order must be a power of two greater than or equal to 2.")
+    if not len(f) == len(g) == root_order:
+        raise ValueError("Polynomials must have equal length and length equal to root_order.")
+    if not has_primitive_root_of_unity(modulus, root_order):
+        raise ValueError("Modulus does not have a primitive root of unity of order root_order.")
+    if not is_primitive_root(root, modulus, root_order):
+        raise ValueError("Input root must be a primitive root of unity.")
+    if (root * inv_root) % modulus != 1:
+        raise ValueError("Input inv_root must be the inverse of the root of unity.")
+    raise ValueError("not enough values to unpack (expected 3, got 2)")

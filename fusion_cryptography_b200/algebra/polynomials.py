@@ -14,6 +14,8 @@ the reference's.
 from __future__ import annotations
 
 import random as _random
+from copy import deepcopy  # noqa: F401  (public names of the reference's module: algebra/polynomials.py:1-3)
+from random import randrange, seed as random_seed  # noqa: F401
 from typing import Dict, List, Optional, Tuple, Union
 
 try:

@@ -261,6 +261,37 @@ __global__ void __launch_bounds__(256) ring_pointwise_kernel(RingK k, const int3
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = ring_pw1<MUL>(k, a[i], b[i]);
 }
 
+// fusion/fusion.py:422-481 (decode_bytes_to_polynomial_coefficients) for any degree: one thread per byte string, coefficients in place in the
+// output.  Signum i is bit i (LSB first) of the big-endian integer of the first ceil(weight / 8) bytes (:446-453); magnitudes are
+// (int(bpc bytes, big-endian) % bound) + 1 (:458-465); then the partial Fisher-Yates for i = d - 1 down to weight + 1 with
+// j = int(bpi bytes) % (i + 1) (:472-480).  Slices past the end of the byte string are shorter or empty, as Python's are.
+__global__ void __launch_bounds__(64) ring_decode_kernel(const uint8_t* __restrict__ bytes, size_t stride, uint32_t blen, size_t n, int d, int weight,
+                                                          uint32_t bound, int bpc, int bpi, int32_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* b = bytes + i * stride;
+    int32_t* o = out + i * d;
+    const uint32_t bfs = (uint32_t)(weight + 7) / 8;
+    uint32_t pos = bfs;
+    for (int k = 0; k < weight; ++k) {
+        unsigned long long acc = 0;
+        for (int t = 0; t < bpc; ++t, ++pos)
+            if (pos < blen) acc = ((acc << 8) | b[pos]) % bound;
+        const int bit = (b[bfs - 1 - (uint32_t)(k >> 3)] >> (k & 7)) & 1;
+        o[k] = (int32_t)(acc + 1) * (2 * bit - 1);
+    }
+    for (int k = weight; k < d; ++k) o[k] = 0;
+    const int num = weight < 1 ? 1 : weight;   // max(1, min(degree, weight_bound)), weight <= d
+    if (num < d)
+        for (int k = d - 1; k > weight; --k) {
+            unsigned long long acc = 0;
+            const uint32_t m = (uint32_t)k + 1;
+            for (int t = 0; t < bpi; ++t, ++pos)
+                if (pos < blen) acc = ((acc << 8) | b[pos]) % m;
+            const int32_t tmp = o[k]; o[k] = o[acc]; o[acc] = tmp;
+        }
+}
+
 static uint32_t host_powmod(uint32_t b, uint32_t e, uint32_t m) {
     unsigned long long r = 1, x = b % m;
     while (e) {
@@ -430,6 +461,27 @@ int fz_ring_sample_coef(fz_ring* r, const uint32_t* keys, int key_stride, const 
 int fz_ring_sample_ntt(fz_ring* r, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, int32_t* out, void* stream) {
     FZR_REQUIRE(r && (n == 0 || (keys && klen && out)) && key_stride >= 1, "fz_ring_sample_ntt: bad argument");
     return launch_sample_ring(r->d, r->q, 1, keys, key_stride, klen, n, 0, 0, out, (cudaStream_t)stream);
+}
+
+// fusion/fusion.py:422-481 for this ring's degree and modulus.  bytes: [n][stride] device bytes of which the first blen of each row are decoded;
+// bytes_per_coefficient / bytes_per_index are the caller's evaluation of :433-434 (they involve a floating-point log2 in the reference).
+// Returns -3 with the reference's message when blen is below the length check of :435-442.
+int fz_ring_decode_poly(fz_ring* r, const uint8_t* bytes, size_t stride, size_t blen, size_t n, long long norm_bound, int weight_bound,
+                        int bytes_per_coefficient, int bytes_per_index, int32_t* out, void* stream) {
+    FZR_REQUIRE(r && (n == 0 || (bytes && out)), "fz_ring_decode_poly: NULL argument");
+    FZR_REQUIRE(weight_bound >= 0 && weight_bound <= r->d, "fz_ring_decode_poly: weight_bound must be in [0, degree]");
+    FZR_REQUIRE(bytes_per_coefficient >= 1 && bytes_per_index >= 1 && blen < (1ull << 32), "fz_ring_decode_poly: bad byte counts");
+    long long bound = norm_bound < (long long)r->half ? norm_bound : (long long)r->half;   // :432
+    if (bound < 1) bound = 1;
+    const size_t total = (size_t)((weight_bound + 7) / 8) + (size_t)(bytes_per_coefficient + bytes_per_index) * weight_bound;   // :435-438
+    if (blen < total) {
+        set_error("Too few bytes to decode polynomial. Expected %zu but got %zu", total, blen);
+        return -3;
+    }
+    if (n == 0) return 0;
+    ring_decode_kernel<<<(unsigned)((n + 63) / 64), 64, 0, (cudaStream_t)stream>>>(bytes, stride, (uint32_t)blen, n, r->d, weight_bound, (uint32_t)bound,
+                                                                                   bytes_per_coefficient, bytes_per_index, out);
+    return check(cudaGetLastError(), "ring decode launch");
 }
 
 }  // extern "C"

@@ -84,6 +84,14 @@ for _secpar, _L in _LEVELS.items():
     _p["bytes_for_one_coef_bdd_by_beta_ag"] = ceil((ceil(log2(2 * _p["beta_ag"] + 1) / 8) + _secpar / 8))
     _p["bytes_for_poly_shuffle"] = _p["degree"] * ceil((ceil(log2(_p["degree"]) / 8) + _secpar / 8))
     PREFIX_PARAMETERS[_secpar] = _p
+    # the reference's per-level module constants (fusion/fusion.py:18-68), under their public names
+    globals().update({
+        f"DEGREE_{_secpar}": _L["degree"], f"ROOT_ORDER_{_secpar}": 2 * _L["degree"], f"RANK_{_secpar}": _L["rank"], f"CAPACITY_{_secpar}": _L["capacity"],
+        f"CH_WEIGHT_{_secpar}": _L["ch_weight"], f"AG_WEIGHT_{_secpar}": _L["ag_weight"], f"SK_BD_{_secpar}": SK_BD, f"CH_BD_{_secpar}": _L["ch_bd"],
+        f"AG_BD_{_secpar}": _L["ag_bd"], f"ROOT_{_secpar}": _L["root"], f"SIGN_PRE_HASH_DST_{_secpar}": _p["sign_pre_hash_dst"],
+        f"SIGN_HASH_DST_{_secpar}": _p["sign_hash_dst"], f"AGG_XOF_DST_{_secpar}": _p["agg_xof_dst"], f"VF_BD_INTERMEDIATE_{_secpar}": _vf_inter,
+        f"VF_BD_{_secpar}": _p["beta_vf"],
+    })
 
 
 # ------------------------------------------------------------------ GPU-backed hashlib look-alikes
@@ -355,13 +363,18 @@ def decode_bytes_to_polynomial_coefficients(b: bytes, log2_bias: int, modulus: i
     total_bytes = _decoder_sizes(log2_bias, modulus, degree, norm_bound, weight_bound)
     if len(b) < total_bytes:
         raise ValueError(f"Too few bytes to decode polynomial. Expected {total_bytes} but got {len(b)}")
-    if modulus != PRIME or degree not in (64, 256):
-        raise NotImplementedError("libfusion_b200 decodes only for the scheme's rings (degree 64 / 256)")
     import torch
 
-    ctx = _native.get_context(128 if degree == 64 else 256)
     data = torch.frombuffer(bytearray(b), dtype=torch.uint8).reshape(1, -1) if len(b) else torch.zeros((1, 1), dtype=torch.uint8)
-    return ctx.decode_poly(data, len(b), log2_bias, norm_bound, weight_bound)[0].cpu().tolist()
+    if modulus == PRIME and degree in (64, 256) and 0 <= weight_bound <= 256:
+        ctx = _native.get_context(128 if degree == 64 else 256)
+        return ctx.decode_poly(data, len(b), log2_bias, norm_bound, weight_bound)[0].cpu().tolist()
+    # any other ring: the general decoder (fz_ring_decode_poly)
+    if not 0 <= weight_bound <= degree:
+        raise NotImplementedError("libfusion_b200 decodes weight bounds between 0 and the degree")
+    bound = max(1, min(modulus // 2, norm_bound))
+    ring = _native.get_ring(modulus, degree)
+    return ring.decode_poly(data, len(b), norm_bound, weight_bound, ceil((log2(bound) + 1 + log2_bias) / 8), ceil((log2(degree) + log2_bias) / 8))[0].cpu().tolist()
 
 
 _PRISTINE["decode_bytes_to_polynomial_coefficients"] = decode_bytes_to_polynomial_coefficients

@@ -311,6 +311,20 @@ class Ring:
                                                _ptr(out), self._stream()))
         return out
 
+    def decode_poly(self, data: torch.Tensor, blen: int, norm_bound: int, weight_bound: int, bytes_per_coefficient: int, bytes_per_index: int) -> torch.Tensor:
+        """fusion/fusion.py:422-481 on [n, stride] uint8 rows (the first blen bytes of each) -> [n, d]."""
+        if data.dtype != torch.uint8:
+            raise TypeError("bytes must be uint8")
+        data = data.to(self.device).contiguous()
+        n, stride = data.shape
+        out = torch.empty((n, self.d), dtype=torch.int32, device=self.device)
+        rc = self.lib.fz_ring_decode_poly(self._h, _ptr(data), C.c_size_t(stride), C.c_size_t(blen), C.c_size_t(n), C.c_longlong(min(norm_bound, 1 << 62)),
+                                          C.c_int(weight_bound), C.c_int(bytes_per_coefficient), C.c_int(bytes_per_index), _ptr(out), self._stream())
+        if rc == -3:
+            raise ValueError(self.lib.fz_last_error().decode())
+        self._chk(rc)
+        return out
+
     def sample_ntt(self, seeds) -> torch.Tensor:
         """algebra/polynomials.py:470-488 with integer seeds -> [n, d]."""
         keys, klen = Context._seed_keys(self, seeds)

@@ -198,6 +198,10 @@ int fz_ring_pointwise_add(fz_ring* ring, const int32_t* a, const int32_t* b, int
 int fz_ring_sample_coef(fz_ring* ring, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, int norm_bound, int weight_bound, int32_t* out,
                         void* stream);
 int fz_ring_sample_ntt(fz_ring* ring, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, int32_t* out, void* stream);
+/* fusion/fusion.py:422-481 (decode_bytes_to_polynomial_coefficients) for this ring: bytes [n][stride] (device), the first blen of each row decoded;
+ * bytes_per_coefficient / bytes_per_index as :433-434 computes them; -3 = the reference's "Too few bytes to decode polynomial" ValueError */
+int fz_ring_decode_poly(fz_ring* ring, const uint8_t* bytes, size_t stride, size_t blen, size_t n, long long norm_bound, int weight_bound,
+                        int bytes_per_coefficient, int bytes_per_index, int32_t* out, void* stream);
 
 #ifdef __cplusplus
 }

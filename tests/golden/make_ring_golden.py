@@ -85,6 +85,28 @@ def main():
         out[f"s{i}_ntt"] = np.array(g.values, dtype=np.int64)
         out[f"s{i}_after_ntt"] = np.array([random.getrandbits(32) for _ in range(4)], dtype=np.int64)
         out[f"s{i}_root"] = np.array([root, inv_root], dtype=np.int64)
+    # the decoder on rings other than the scheme's (the reference's tests/test_fusion.py:475-558 decodes for modulus 65537, degree 1024,
+    # norm_bound 1000, weight_bound 100, log2_bias 256): (log2_bias, modulus, degree, norm_bound, weight_bound, byte pattern, length)
+    from math import ceil, log2
+    import fusion.fusion as ff
+
+    def sizes(lb, q, d, nb, wb):
+        bound = max(1, min(q // 2, nb))
+        bpc, bpi = ceil((log2(bound) + 1 + lb) / 8), ceil((log2(d) + lb) / 8)
+        return ceil(wb / 8) + (bpc + bpi) * wb, ceil(wb / 8) + bpc * wb + bpi * d
+
+    dcases = []
+    for lb, q, d, nb, wb in [(256, 65537, 1024, 1000, 100), (128, 257, 64, 16, 64), (17, 17, 8, 3, 0), (64, 12289, 2048, 10**6, 300), (8, 7681, 256, 1, 17),
+                             (128, 2013265921, 512, 2**29, 257)]:
+        need, full = sizes(lb, q, d, nb, wb)
+        for pat, ln in (("zero", full), ("ones", full), ("rand", full), ("rand", need), ("rand", (need + full) // 2 + 1)):
+            dcases.append((lb, q, d, nb, wb, pat, ln))
+    out["decode_cases"] = np.array([[c[0], c[1], c[2], c[3], c[4], c[6]] for c in dcases], dtype=np.int64)
+    for i, (lb, q, d, nb, wb, pat, ln) in enumerate(dcases):
+        b = bytes(ln) if pat == "zero" else b"\xff" * ln if pat == "ones" else bytes(rng.integers(0, 256, size=ln, dtype=np.uint8))
+        out[f"d{i}_bytes"] = np.frombuffer(b, dtype=np.uint8)
+        out[f"d{i}_coefs"] = np.array(ff.decode_bytes_to_polynomial_coefficients(b=b, log2_bias=lb, modulus=q, degree=d, norm_bound=nb, weight_bound=wb),
+                                      dtype=np.int64)
     np.savez_compressed(os.path.join(OUT, "ring_golden.npz"), **out)
 
 

@@ -294,3 +294,19 @@ def test_general_matrix_on_small_rings():
         # matrix * element
         e = transform(Poly(coefficients=[1] + [0] * (d - 1), **kw))   # the constant polynomial 1
         assert (nl * e) == nl
+
+
+def test_decoder_on_general_rings(ring_golden):
+    """decode_bytes_to_polynomial_coefficients (fusion/fusion.py:422-481) for degrees and weights beyond the scheme's: vectors recorded from the
+    reference for all-zero, all-one and random byte strings, full-length and cut short inside the shuffle -- among them the
+    case of the reference's own tests/test_fusion.py:475-558 -- and its ValueError for strings below the length check."""
+    from fusion_cryptography_b200.fusion import fusion as ff
+
+    G = ring_golden
+    for i, (lb, q, d, nb, wb, ln) in enumerate(G["decode_cases"]):
+        b = G[f"d{i}_bytes"].tobytes()
+        assert len(b) == int(ln)
+        got = ff.decode_bytes_to_polynomial_coefficients(b=b, log2_bias=int(lb), modulus=int(q), degree=int(d), norm_bound=int(nb), weight_bound=int(wb))
+        assert got == [int(x) for x in G[f"d{i}_coefs"]], (i, int(lb), int(q), int(d), int(nb), int(wb), int(ln))
+    with pytest.raises(ValueError, match="Too few bytes to decode polynomial. Expected 6813 but got 10"):
+        ff.decode_bytes_to_polynomial_coefficients(b=bytes(10), log2_bias=256, modulus=65537, degree=1024, norm_bound=1000, weight_bound=100)
