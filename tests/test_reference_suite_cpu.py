@@ -1,7 +1,8 @@
-"""The reference's OWN unit tests of its algebra layer (tests/test_ntt.py, tests/test_polynomials.py, tests/test_matrices.py: 31 tests on
-moduli below 2^17, degrees 4..64 and one 1024) run UNMODIFIED against the host mirror -- classes, operators, validation, exceptions and
-``str()`` formats are ours; the arithmetic the mirror sends to the device is served by the oracle stand-in of tests/refsuite, whose
-functions are the ones the CUDA kernels are compared with bit for bit (tests/test_gpu_ring.py).
+"""The reference's OWN unit tests -- all four files, 53 tests: tests/test_ntt.py, test_polynomials.py, test_matrices.py (moduli below 2^17, degrees
+4..64 and one 1024) and test_fusion.py (setup, keygen, the hash helpers incl. the pytest-mock based ones, decoder, sign, aggregate, verify, tampering)
+-- run UNMODIFIED against the host mirror: classes, operators, validation, exceptions, ``str()`` formats, sorting, the reason strings and the
+module attributes the mocks patch are ours; the calls the mirror makes to the device are served by the oracle stand-in of tests/refsuite, whose
+functions are the ones the CUDA kernels are compared with bit for bit (tests/test_gpu_ring.py, test_gpu_scheme.py, test_gpu_dropin.py).
 
 Runs only where the reference checkout exists (the build container); the test files are read from there into a pytest scratch
 directory -- they are never copied into this repository."""
@@ -14,18 +15,20 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("FUSION_REFERENCE", "/root/reference")
-FILES = ["test_ntt.py", "test_polynomials.py", "test_matrices.py"]
+FILES = ["test_ntt.py", "test_polynomials.py", "test_matrices.py", "test_fusion.py"]
 
 
 @pytest.mark.skipif(not all(os.path.exists(os.path.join(REF, "tests", f)) for f in FILES), reason="no reference checkout here")
-def test_reference_algebra_tests_pass_on_host_mirror(tmp_path):
+def test_reference_unit_tests_pass_on_host_mirror(tmp_path):
     mirror = tmp_path / "mirror"
     mirror.mkdir()
     os.symlink(os.path.join(ROOT, "fusion_cryptography_b200", "algebra"), mirror / "algebra")
+    os.symlink(os.path.join(ROOT, "fusion_cryptography_b200", "fusion"), mirror / "fusion")
     shutil.copy(os.path.join(ROOT, "tests", "refsuite", "device_standin.py"), mirror / "native.py")
     tdir = tmp_path / "tests"
     tdir.mkdir()
     (tdir / "__init__.py").write_text("")   # test_matrices.py imports `tests.test_ntt`; a regular package beats any other `tests` on the path
+    shutil.copy(os.path.join(ROOT, "tests", "refsuite", "mocker_shim.py"), tdir / "conftest.py")
     for f in FILES:
         shutil.copy(os.path.join(REF, "tests", f), tdir / f)
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([str(mirror), str(tmp_path), str(tdir)]), FUSION_B200_REPO=ROOT, PYTHONDONTWRITEBYTECODE="1")
@@ -34,4 +37,4 @@ def test_reference_algebra_tests_pass_on_host_mirror(tmp_path):
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout and "error" not in r.stdout.lower(), tail
-    assert "31 passed" in r.stdout, tail
+    assert "53 passed" in r.stdout, tail
