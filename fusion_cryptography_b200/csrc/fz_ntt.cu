@@ -263,14 +263,6 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) ntt_inv_kernel(co
     }
 }
 
-// lazy [0, 2q] x lazy [0, 2q] -> [0, q], pseudo-Mersenne folds of the 62-bit product
-__device__ __forceinline__ uint32_t mul_lazy(uint32_t a, uint32_t b) {
-    unsigned long long P = (unsigned long long)red_q(a) * red_q(b);
-    unsigned long long f1 = (P >> 31) * MERS_C + (P & 0x7fffffffull);
-    uint32_t f2 = (uint32_t)(f1 >> 31) * MERS_C + (uint32_t)(f1 & 0x7fffffffull);
-    return red_q(f2);
-}
-
 // out = INTT(NTT(a) o NTT(b)): algebra/ntt.py:450-471 (ntt_poly_mult) in one pass over HBM
 template <int LOGD>
 __global__ void __launch_bounds__(NTT_THREADS) polymul_kernel(const int32_t* a, const int32_t* b, int32_t* out, size_t n_polys) {
@@ -300,11 +292,11 @@ __global__ void __launch_bounds__(NTT_THREADS) polymul_kernel(const int32_t* a, 
         xchg_s2c<LOGD>(tile, tau, x, yb);
         fwd_contig<LOGD>(yb, twf);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) ya[k] = mul_lazy(ya[k], yb[k]);
+        for (int k = 0; k < 16; ++k) ya[k] = mont_mul(red_q(ya[k]), (int32_t)red_q(yb[k]));   // [0, q] fits int32; the 2^-32 is repaid by c_last[2..3]
         inv_contig<LOGD>(ya, twi);
         xchg_c2s<LOGD>(tile, tau, ya, x);
         int32_t o[16];
-        inv_strided<LOGD>(x, o);
+        inv_strided<LOGD, 2>(x, o);
         if (live) {
             int32_t* dst = out + p * C::D + tau;
 #pragma unroll

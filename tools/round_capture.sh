@@ -11,4 +11,4 @@ $SHORT > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $SHORT > gpurun_out/${TAG}_ncu1.log 2>&1
 $SHORT > gpurun_out/${TAG}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:ntt_pass_kernel -s 3 -c 2 -f -o gpurun_out/prof_ntt_pass_${TAG} $SHORT > gpurun_out/${TAG}_ncu2.log 2>&1
-tail -3 gpurun_out/${TAG}_pytest.log gpurun_out/${TAG}_smoke.log gpurun_out/${TAG}_ring_times.log
+for f in pytest smoke ring_times; do tail -n 3 gpurun_out/${TAG}_$f.log; done
