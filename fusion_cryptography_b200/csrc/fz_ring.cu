@@ -90,16 +90,43 @@ __global__ void ring_table_kernel(const uint32_t* __restrict__ table, Sh* out, i
 // Forward (algebra/ntt.py:271-291): stage with t = 2^lt pairs (j, j + t) and multiplies by tw[d / 2^(lt+1) + (j >> (lt + 1))]; the pass runs
 // lt = lo_bits + R - 1 down to lo_bits, butterfly (u, v) -> (u + v*s, u - v*s).
 // Inverse (algebra/ntt.py:354-372): lt = lo_bits up to lo_bits + R - 1, (u, v) -> (u + v, (u - v)*s), s = itw[d / 2^(lt+1) + (j >> (lt + 1))].
-template <int R, bool INVERSE, int GS>
-__device__ __forceinline__ void ring_pass(uint32_t* tile, const Sh* __restrict__ tw, uint32_t q, int logd, int lo_bits, int n_items, int tid) {
+// The FIRST pass of a transform gathers its coefficients straight from global memory (any int32 -> [0, q)) and the LAST one scatters canonical
+// centred residues straight back (times n^-1 for the inverse), so only the exchanges BETWEEN passes go through the shared-memory tile: a
+// degree <= 16 transform never touches it, degree 256 crosses it once.  Across the lanes of a warp the global accesses are either consecutive
+// 4-byte words (lo_bits > 0) or one 2^R-word run per lane (lo_bits == 0), moved as 16-byte pieces when the operands are aligned (VEC).
+// The pass with lo_bits == 0 is the one whose twiddles differ from lane to lane (hi = the item index); fetched from global memory they cost a
+// scattered 8-byte load per twiddle and item (the LSU data pipe was the busiest unit, 75 %).  When `twc` is not NULL it holds exactly those
+// twiddles, copied once per CTA into shared memory as [slot][item of the tile]: consecutive lanes read consecutive 8-byte words.
+template <int R, bool INVERSE, int GS, bool FROM_GLOBAL, bool TO_GLOBAL, bool VEC>
+__device__ __forceinline__ void ring_pass(uint32_t* tile, const Sh* __restrict__ tw, const RingK& kk, int lo_bits, int n_items, int tid, const int32_t* gin,
+                                          int32_t* gout, const Sh* twc = nullptr, int twc_items = 0) {
     constexpr int N = 1 << R;
+    const uint32_t q = kk.q;
+    const int logd = kk.logd;
     for (int w = tid; w < n_items; w += GS) {
         const int p = w >> (logd - R), wi = w & ((1 << (logd - R)) - 1);
         const int lo = wi & ((1 << lo_bits) - 1), hi = wi >> lo_bits;
         const int base = (p << logd) + (hi << (lo_bits + R)) + lo;
         uint32_t x[N];
+        if (FROM_GLOBAL) {
+            if (VEC && R >= 2 && lo_bits == 0) {
+                const int4* g4 = reinterpret_cast<const int4*>(gin + base);
 #pragma unroll
-        for (int k = 0; k < N; ++k) x[k] = tile[phys(base + (k << lo_bits))];
+                for (int c = 0; c < N / 4; ++c) {
+                    const int4 v = ld_stream(g4 + c);
+                    x[4 * c] = rq_from(v.x, kk); x[4 * c + 1] = rq_from(v.y, kk); x[4 * c + 2] = rq_from(v.z, kk); x[4 * c + 3] = rq_from(v.w, kk);
+                }
+            } else {
+                int32_t raw[N];
+#pragma unroll
+                for (int k = 0; k < N; ++k) raw[k] = gin[base + (k << lo_bits)];
+#pragma unroll
+                for (int k = 0; k < N; ++k) x[k] = rq_from(raw[k], kk);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < N; ++k) x[k] = tile[phys(base + (k << lo_bits))];
+        }
 #pragma unroll
         for (int s = 0; s < R; ++s) {
             if (!INVERSE) {
@@ -108,7 +135,7 @@ __device__ __forceinline__ void ring_pass(uint32_t* tile, const Sh* __restrict__
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
                     if (k & dk) continue;
-                    const Sh tws = row[k >> (R - s)];
+                    const Sh tws = twc ? twc[(((1 << s) - 1) + (k >> (R - s))) * twc_items + w] : row[k >> (R - s)];
                     const uint32_t u = x[k], v = rq_mul(x[k + dk], tws, q);
                     x[k] = rq_add(u, v, q);
                     x[k + dk] = rq_sub(u, v, q);
@@ -119,70 +146,45 @@ __device__ __forceinline__ void ring_pass(uint32_t* tile, const Sh* __restrict__
 #pragma unroll
                 for (int k = 0; k < N; ++k) {
                     if (k & dk) continue;
-                    const Sh tws = row[k >> (s + 1)];
+                    const Sh tws = twc ? twc[((N - (N >> s)) + (k >> (s + 1))) * twc_items + w] : row[k >> (s + 1)];
                     const uint32_t u = x[k], v = x[k + dk];
                     x[k] = rq_add(u, v, q);
                     x[k + dk] = rq_mul(u - v + q, tws, q);
                 }
             }
         }
+        if (TO_GLOBAL) {
+            int32_t o[N];
 #pragma unroll
-        for (int k = 0; k < N; ++k) tile[phys(base + (k << lo_bits))] = x[k];
+            for (int k = 0; k < N; ++k) o[k] = rq_cent(INVERSE ? rq_mul(x[k], kk.ninv, q) : x[k], q, kk.half);
+            if (VEC && R >= 2 && lo_bits == 0) {
+                int4* g4 = reinterpret_cast<int4*>(gout + base);
+#pragma unroll
+                for (int c = 0; c < N / 4; ++c) st_stream(g4 + c, make_int4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]));
+            } else {
+#pragma unroll
+                for (int k = 0; k < N; ++k) gout[base + (k << lo_bits)] = o[k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < N; ++k) tile[phys(base + (k << lo_bits))] = x[k];
+        }
     }
 }
 
-template <bool INVERSE, int GS>
-__device__ __forceinline__ void ring_pass_r(int r, uint32_t* tile, const Sh* __restrict__ tw, uint32_t q, int logd, int lo_bits, int n_items, int tid) {
+// the pass shapes a transform can need: r stages with r = 1..4; only a 4-stage pass can be a first-but-not-last or a middle pass
+template <bool INVERSE, int GS, bool VEC, bool FROM_GLOBAL, bool TO_GLOBAL>
+__device__ __forceinline__ void ring_pass_r(int r, uint32_t* tile, const Sh* __restrict__ tw, const RingK& k, int lo_bits, int n_items, int tid,
+                                            const int32_t* gin, int32_t* gout, const Sh* twc = nullptr, int twc_items = 0) {
+    if (!TO_GLOBAL) {   // r == 4 by construction
+        ring_pass<4, INVERSE, GS, FROM_GLOBAL, false, VEC>(tile, tw, k, lo_bits, n_items, tid, gin, gout, twc, twc_items);
+        return;
+    }
     switch (r) {
-        case 4: ring_pass<4, INVERSE, GS>(tile, tw, q, logd, lo_bits, n_items, tid); break;
-        case 3: ring_pass<3, INVERSE, GS>(tile, tw, q, logd, lo_bits, n_items, tid); break;
-        case 2: ring_pass<2, INVERSE, GS>(tile, tw, q, logd, lo_bits, n_items, tid); break;
-        default: ring_pass<1, INVERSE, GS>(tile, tw, q, logd, lo_bits, n_items, tid); break;
-    }
-}
-
-// global -> tile: 16-byte loads, four per thread in flight before the first is consumed (VEC needs 16-byte aligned polynomials; the scalar form
-// serves unaligned callers and the d = 2 tails)
-template <bool VEC, int GS>
-__device__ __forceinline__ void ring_load(uint32_t* tile, const int32_t* src, int n_coef, const RingK& k, int tid) {
-    if (VEC) {
-        const int4* src4 = reinterpret_cast<const int4*>(src);
-        const int n4 = n_coef >> 2;
-        for (int i0 = 0; i0 < n4; i0 += 4 * GS) {
-            int4 v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = i0 + j * GS + tid;
-                v[j] = i < n4 ? ld_stream(src4 + i) : make_int4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = i0 + j * GS + tid;
-                if (i < n4) {
-                    uint32_t* t = tile + phys(4 * i);   // 4 * i .. 4 * i + 3 share one 32-word block: contiguous
-                    t[0] = rq_from(v[j].x, k); t[1] = rq_from(v[j].y, k); t[2] = rq_from(v[j].z, k); t[3] = rq_from(v[j].w, k);
-                }
-            }
-        }
-        for (int e = (n4 << 2) + tid; e < n_coef; e += GS) tile[phys(e)] = rq_from(src[e], k);
-    } else {
-        for (int e = tid; e < n_coef; e += GS) tile[phys(e)] = rq_from(src[e], k);
-    }
-}
-
-template <bool VEC, bool SCALE, int GS>
-__device__ __forceinline__ void ring_store(const uint32_t* tile, int32_t* dst, int n_coef, const RingK& k, int tid) {
-    auto fin = [&](uint32_t y) { return rq_cent(SCALE ? rq_mul(y, k.ninv, k.q) : y, k.q, k.half); };
-    if (VEC) {
-        int4* dst4 = reinterpret_cast<int4*>(dst);
-        const int n4 = n_coef >> 2;
-        for (int i = tid; i < n4; i += GS) {
-            const uint32_t* t = tile + phys(4 * i);
-            st_stream(dst4 + i, make_int4(fin(t[0]), fin(t[1]), fin(t[2]), fin(t[3])));
-        }
-        for (int e = (n4 << 2) + tid; e < n_coef; e += GS) dst[e] = fin(tile[phys(e)]);
-    } else {
-        for (int e = tid; e < n_coef; e += GS) dst[e] = fin(tile[phys(e)]);
+        case 4: ring_pass<4, INVERSE, GS, FROM_GLOBAL, true, VEC>(tile, tw, k, lo_bits, n_items, tid, gin, gout, twc, twc_items); break;
+        case 3: ring_pass<3, INVERSE, GS, FROM_GLOBAL, true, VEC>(tile, tw, k, lo_bits, n_items, tid, gin, gout, twc, twc_items); break;
+        case 2: ring_pass<2, INVERSE, GS, FROM_GLOBAL, true, VEC>(tile, tw, k, lo_bits, n_items, tid, gin, gout, twc, twc_items); break;
+        default: ring_pass<1, INVERSE, GS, FROM_GLOBAL, true, VEC>(tile, tw, k, lo_bits, n_items, tid, gin, gout, twc, twc_items); break;
     }
 }
 
@@ -192,41 +194,59 @@ constexpr int RING_WARP_TILE = 512;
 
 template <bool INVERSE, bool VEC, bool WARP>
 __global__ void __launch_bounds__(RING_THREADS) ring_ntt_kernel(RingK k, const Sh* __restrict__ tw, const int32_t* in, int32_t* out, size_t n_polys,
-                                                                 int polys_per_tile) {
+                                                                 int polys_per_tile, int tile_words, int twc_items) {
     extern __shared__ __align__(16) uint32_t ring_smem[];
     constexpr int GS = WARP ? 32 : RING_THREADS;
     const int tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
-    uint32_t* tile = WARP ? ring_smem + (threadIdx.x >> 5) * (RING_WARP_TILE + RING_WARP_TILE / 32) : ring_smem;
+    uint32_t* tile = WARP ? ring_smem + (threadIdx.x >> 5) * tile_words : ring_smem;   // tile_words includes the pad word per 32
     auto sync = [] { if (WARP) __syncwarp(); else __syncthreads(); };
-    const uint32_t q = k.q;
     const int logd = k.logd;
+    const int n_pass = (logd + 3) >> 2, r_odd = logd - 4 * (n_pass - 1);   // n_pass - 1 four-stage passes and one of r_odd = 1..4 stages
+    // twiddles of the lo_bits == 0 pass (forward: the last pass, r_odd stages; inverse: the first pass), [slot][item] behind the tiles
+    const Sh* twc = nullptr;
+    if (twc_items > 0) {
+        Sh* fill = reinterpret_cast<Sh*>(ring_smem + (size_t)tile_words * (WARP ? RING_THREADS / 32 : 1));
+        const int rc = INVERSE ? (logd < 4 ? logd : 4) : r_odd, nc = 1 << rc, per_poly = 1 << (logd - rc);
+        for (int e = threadIdx.x; e < (nc - 1) * twc_items; e += RING_THREADS) {
+            const int slot = e / twc_items, w = e - slot * twc_items, hi = w & (per_poly - 1);
+            int s2 = 0, i2 = 0, idx;
+            if (!INVERSE) {                      // slot = (2^s - 1) + i: stage s of the pass has lt = rc - 1 - s and 2^s twiddles per item
+                while (((2 << s2) - 1) <= slot) ++s2;
+                i2 = slot - ((1 << s2) - 1);
+                idx = ((1 << logd) >> (rc - s2)) + (hi << s2) + i2;
+            } else {                             // slot = (nc - (nc >> s)) + i: stage s has lt = s and nc >> (s + 1) twiddles per item
+                while (nc - (nc >> (s2 + 1)) <= slot) ++s2;
+                i2 = slot - (nc - (nc >> s2));
+                idx = ((1 << logd) >> (s2 + 1)) + (hi << (rc - 1 - s2)) + i2;
+            }
+            fill[e] = tw[idx];
+        }
+        __syncthreads();
+        twc = fill;
+    }
     const size_t n_tiles = (n_polys + polys_per_tile - 1) / polys_per_tile;
     const size_t first = WARP ? (size_t)blockIdx.x * (RING_THREADS / 32) + (threadIdx.x >> 5) : (size_t)blockIdx.x;
     const size_t step = WARP ? (size_t)gridDim.x * (RING_THREADS / 32) : (size_t)gridDim.x;
     for (size_t tl = first; tl < n_tiles; tl += step) {
         const size_t p0 = tl * polys_per_tile;
         const int live = (int)min((size_t)polys_per_tile, n_polys - p0);
-        const int n_coef = live << logd;
-        ring_load<VEC, GS>(tile, in + (p0 << logd), n_coef, k, tid);
-        sync();
-        int32_t* dst = out + (p0 << logd);
-        if (!INVERSE) {
-            for (int a = logd - 1; a >= 0;) {              // stages lt = a, a - 1, ..., a - r + 1
-                const int r = a + 1 < 4 ? a + 1 : 4;
-                ring_pass_r<false, GS>(r, tile, tw, q, logd, a - r + 1, live << (logd - r), tid);
-                sync();
-                a -= r;
-            }
-            ring_store<VEC, false, GS>(tile, dst, n_coef, k, tid);
-        } else {
-            for (int a = 0; a < logd;) {                   // stages lt = a, a + 1, ..., a + r - 1
-                const int r = logd - a < 4 ? logd - a : 4;
-                ring_pass_r<true, GS>(r, tile, tw, q, logd, a, live << (logd - r), tid);
-                sync();
-                a += r;
-            }
-            ring_store<VEC, true, GS>(tile, dst, n_coef, k, tid);
+        const int32_t* gin = in + (p0 << logd);
+        int32_t* gout = out + (p0 << logd);
+        if (n_pass == 1) {
+            ring_pass_r<INVERSE, GS, VEC, true, true>(logd, tile, tw, k, 0, live, tid, gin, gout, twc, twc_items);
+            continue;
         }
+        // forward: stages lt = logd - 1 downwards, the odd-sized pass last (lo_bits = 0); inverse: lt = 0 upwards, the odd-sized pass last (on top)
+        int a = INVERSE ? 0 : logd - 4;
+        ring_pass_r<INVERSE, GS, VEC, true, false>(4, tile, tw, k, a, live << (logd - 4), tid, gin, gout, INVERSE ? twc : nullptr, twc_items);
+        sync();
+        for (int ps = 1; ps < n_pass - 1; ++ps) {
+            a += INVERSE ? 4 : -4;
+            ring_pass_r<INVERSE, GS, VEC, false, false>(4, tile, tw, k, a, live << (logd - 4), tid, gin, gout);
+            sync();
+        }
+        ring_pass_r<INVERSE, GS, VEC, false, true>(r_odd, tile, tw, k, INVERSE ? a + 4 : 0, live << (logd - r_odd), tid, gin, gout, INVERSE ? nullptr : twc,
+                                                   twc_items);
         sync();   // the tile is reused by the next iteration
     }
 }
@@ -328,9 +348,15 @@ static int upload_table(fz_ring* r, const uint32_t* host_table, Sh** out) {
 
 template <bool INVERSE, bool VEC, bool WARP>
 static int launch_ring_ntt_v(fz_ring* r, const int32_t* in, int32_t* out, size_t n_polys, cudaStream_t st) {
-    const size_t tile_words = WARP ? (size_t)RING_WARP_TILE : (size_t)(r->d >= RING_TILE ? r->d : RING_TILE);
-    const int polys_per_tile = (size_t)r->d >= tile_words ? 1 : (int)(tile_words / r->d);
-    const size_t smem = sizeof(uint32_t) * (tile_words + tile_words / 32) * (WARP ? RING_THREADS / 32 : 1);   // one pad word per 32
+    const size_t tile_coefs = WARP ? (size_t)RING_WARP_TILE : (size_t)(r->d >= RING_TILE ? r->d : RING_TILE);
+    const int polys_per_tile = (size_t)r->d >= tile_coefs ? 1 : (int)(tile_coefs / r->d);
+    const size_t tile_words = tile_coefs + tile_coefs / 32;   // one pad word per 32
+    // twiddle cache of the lo_bits == 0 pass: (2^rc - 1) Shoup pairs per item of a tile, kept only while it stays small (d <= 4,096)
+    const int n_pass = (r->logd + 3) / 4, r_odd = r->logd - 4 * (n_pass - 1), rc = INVERSE ? (r->logd < 4 ? r->logd : 4) : r_odd;
+    int twc_items = (int)(tile_coefs >> rc);
+    size_t twc_bytes = sizeof(Sh) * (size_t)((1 << rc) - 1) * twc_items;
+    if (twc_bytes > 32 * 1024) twc_items = 0, twc_bytes = 0;
+    const size_t smem = sizeof(uint32_t) * tile_words * (WARP ? RING_THREADS / 32 : 1) + twc_bytes;
     auto kern = ring_ntt_kernel<INVERSE, VEC, WARP>;
     if (smem > 48 * 1024 && check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ring NTT shared memory")) return -2;
     int per_sm = 0;
@@ -338,7 +364,8 @@ static int launch_ring_ntt_v(fz_ring* r, const int32_t* in, int32_t* out, size_t
     const size_t n_tiles = (n_polys + polys_per_tile - 1) / polys_per_tile;
     const size_t want = WARP ? (n_tiles + RING_THREADS / 32 - 1) / (RING_THREADS / 32) : n_tiles;
     const size_t cap = (size_t)r->sm_count * (per_sm > 0 ? per_sm : 1);
-    kern<<<(unsigned)(want < cap ? want : cap), RING_THREADS, smem, st>>>(ring_k(r), INVERSE ? r->inv : r->fwd, in, out, n_polys, polys_per_tile);
+    kern<<<(unsigned)(want < cap ? want : cap), RING_THREADS, smem, st>>>(ring_k(r), INVERSE ? r->inv : r->fwd, in, out, n_polys, polys_per_tile,
+                                                                          (int)tile_words, twc_items);
     return check(cudaGetLastError(), "ring NTT launch");
 }
 

@@ -30,18 +30,19 @@ def timed(fn, reps=10):
     return e0.elapsed_time(e1) / reps
 
 
-for d, q in ((64, 257), (256, 7681), (256, 2147465729 if False else 2013265921), (1024, 12289), (4096, 2013265921), (16384, 2013265921)):
-    root = root_of(q, 2 * d)
-    r = native.get_ring(q, d, table(root, d, q), table(pow(root, q - 2, q), d, q))
-    n = (1 << 26) // d          # 2^26 coefficients = 256 MiB per operand (larger than the 126 MB L2)
-    g = torch.Generator(device="cuda"); g.manual_seed(1)
-    a = torch.randint(-(q // 2), q // 2 + 1, (n, d), dtype=torch.int32, device="cuda", generator=g)
-    b = torch.randint(-(q // 2), q // 2 + 1, (n, d), dtype=torch.int32, device="cuda", generator=g)
-    o = torch.empty_like(a)
-    byt = a.numel() * 4
-    res = []
-    for name, fn, traffic in (("ntt_fwd", lambda: r.ntt_fwd(a, out=o), 2 * byt), ("ntt_inv", lambda: r.ntt_inv(a, out=o), 2 * byt),
-                              ("pointwise_mul", lambda: r.pointwise_mul(a, b, out=o), 3 * byt), ("pointwise_add", lambda: r.pointwise_add(a, b, out=o), 3 * byt)):
-        ms = timed(fn)
-        res.append(f"{name} {ms:.3f} ms {traffic / ms / 1e6:.0f} GB/s")
-    print(f"d={d} q={q} n={n}: " + "; ".join(res))
+if __name__ == "__main__":
+  for d, q in ((64, 257), (256, 7681), (256, 2147465729 if False else 2013265921), (1024, 12289), (4096, 2013265921), (16384, 2013265921)):
+      root = root_of(q, 2 * d)
+      r = native.get_ring(q, d, table(root, d, q), table(pow(root, q - 2, q), d, q))
+      n = (1 << 26) // d          # 2^26 coefficients = 256 MiB per operand (larger than the 126 MB L2)
+      g = torch.Generator(device="cuda"); g.manual_seed(1)
+      a = torch.randint(-(q // 2), q // 2 + 1, (n, d), dtype=torch.int32, device="cuda", generator=g)
+      b = torch.randint(-(q // 2), q // 2 + 1, (n, d), dtype=torch.int32, device="cuda", generator=g)
+      o = torch.empty_like(a)
+      byt = a.numel() * 4
+      res = []
+      for name, fn, traffic in (("ntt_fwd", lambda: r.ntt_fwd(a, out=o), 2 * byt), ("ntt_inv", lambda: r.ntt_inv(a, out=o), 2 * byt),
+                                ("pointwise_mul", lambda: r.pointwise_mul(a, b, out=o), 3 * byt), ("pointwise_add", lambda: r.pointwise_add(a, b, out=o), 3 * byt)):
+          ms = timed(fn)
+          res.append(f"{name} {ms:.3f} ms {traffic / ms / 1e6:.0f} GB/s")
+      print(f"d={d} q={q} n={n}: " + "; ".join(res))
