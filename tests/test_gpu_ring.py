@@ -310,3 +310,34 @@ def test_decoder_on_general_rings(ring_golden):
         assert got == [int(x) for x in G[f"d{i}_coefs"]], (i, int(lb), int(q), int(d), int(nb), int(wb), int(ln))
     with pytest.raises(ValueError, match="Too few bytes to decode polynomial. Expected 6813 but got 10"):
         ff.decode_bytes_to_polynomial_coefficients(b=bytes(10), log2_bias=256, modulus=65537, degree=1024, norm_bound=1000, weight_bound=100)
+
+
+@pytest.mark.parametrize("d,q,n", [(2, 5, 1027), (8, 17, 333), (64, 257, 1001), (256, 7681, 67), (1024, 12289, 9), (8192, 2013265921, 3)])
+def test_ring_kernels_stay_inside_their_buffers(d, q, n):
+    """Guard words before and after every output (and a poisoned input copy) survive the transforms, the pointwise kernels, the samplers and
+    the decoder on ragged batch sizes: nothing is written outside [n, d] and the inputs are not modified."""
+    from fusion_cryptography_b200 import native
+
+    g = 4096
+    r = native.get_ring(q, d, [1] * d, [1] * d)       # any table will do: only the addresses matter here
+    rng = np.random.default_rng(d + n)
+    a = dev(rng.integers(-(q // 2), q // 2 + 1, size=(n, d)))
+    b = dev(rng.integers(-(q // 2), q // 2 + 1, size=(n, d)))
+    a0, b0 = a.clone(), b.clone()
+
+    def guarded(fn):
+        buf = torch.full((g + n * d + g,), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
+        fn(buf[g:g + n * d].view(n, d))
+        torch.cuda.synchronize()
+        assert bool((buf[:g] == 0x5A5A5A5A).all()) and bool((buf[g + n * d:] == 0x5A5A5A5A).all())
+        assert bool((buf[g:g + n * d] != 0x5A5A5A5A).any()) or q < 1000
+
+    guarded(lambda o: r.ntt_fwd(a, out=o))
+    guarded(lambda o: r.ntt_inv(a, out=o))
+    guarded(lambda o: r.pointwise_mul(a, b, out=o))
+    guarded(lambda o: r.pointwise_add(a, b, out=o))
+    assert torch.equal(a, a0) and torch.equal(b, b0)
+    seeds = list(range(100, 100 + min(n, 40)))
+    for sample in (lambda: r.sample_coef(seeds, norm_bound=max(1, min(q // 2, 7)), weight_bound=d // 2), lambda: r.sample_ntt(seeds)):
+        out = sample()
+        assert out.shape == (len(seeds), d) and int(out.abs().max()) <= q // 2
