@@ -253,9 +253,19 @@ def power_table(modulus: int, degree: int, root: int) -> List[int]:
     return _POWER_TABLES[key]
 
 
+_RINGS_BY_ROOT: Dict[Tuple[int, int, int, int], object] = {}
+
+
 def ring_for(modulus: int, degree: int, root: int, inv_root: int):
-    """the device ring (fz_ring) of Z_q[X]/(X^d + 1) with the power tables of (root, inv_root)"""
-    return _native.get_ring(modulus, degree, power_table(modulus, degree, root), power_table(modulus, degree, inv_root))
+    """the device ring (fz_ring) of Z_q[X]/(X^d + 1) with the power tables of (root, inv_root); looked up by the four integers, so that an
+    operator call on a polynomial does not rebuild (or even hash) two d-entry tables"""
+    key = (modulus, degree, root, inv_root)
+    ring = _RINGS_BY_ROOT.get(key)
+    if ring is None:
+        if len(_RINGS_BY_ROOT) >= 64:
+            _RINGS_BY_ROOT.pop(next(iter(_RINGS_BY_ROOT)))
+        ring = _RINGS_BY_ROOT[key] = _native.get_ring(modulus, degree, power_table(modulus, degree, root), power_table(modulus, degree, inv_root))
+    return ring
 
 
 def ntt_poly_mult_half(f: List[int], g: List[int], modulus: int, root: int, inv_root: int, root_order: int) -> List[int]:

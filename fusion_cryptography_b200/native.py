@@ -346,7 +346,7 @@ def get_ring(modulus: int, degree: int, fwd_table=None, inv_table=None, device: 
     r = _rings.get(key)
     if r is None:
         if len(_rings) >= _RING_CACHE:
-            _rings.pop(next(iter(_rings))).close()
+            _rings.pop(next(iter(_rings)))   # dropped, not closed: a caller may still hold it; fz_ring_destroy runs when the last reference goes
         r = _rings[key] = Ring(modulus, degree, fwd_table, inv_table, device)
     return r
 
