@@ -271,9 +271,18 @@ __global__ void __launch_bounds__(NTT_THREADS) polymul_kernel(const int32_t* a, 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tau = lane % C::TPP, pw = lane / C::TPP;
     uint32_t* tile = smem + warp * C::WARP_WORDS + C::base(pw);
-    Sh twf[15], twi[15];
-    load_tw2<LOGD>(C::fwd(), tau, twf);
-    load_tw2<LOGD>(C::inv(), tau, twi);
+    // the two sets of lane-dependent twiddles live in shared memory, one row per lane-in-polynomial (as in ntt_pass_kernel): 115 -> fewer registers
+    __shared__ __align__(8) Sh tw_sm[2][C::TPP][15];
+    if (threadIdx.x < C::TPP) {
+        Sh t[15];
+        load_tw2<LOGD>(C::fwd(), (int)threadIdx.x, t);
+#pragma unroll
+        for (int i = 0; i < 15; ++i) tw_sm[0][threadIdx.x][i] = t[i];
+        load_tw2<LOGD>(C::inv(), (int)threadIdx.x, t);
+#pragma unroll
+        for (int i = 0; i < 15; ++i) tw_sm[1][threadIdx.x][i] = t[i];
+    }
+    __syncthreads();
     const size_t per_cta = (NTT_THREADS / 32) * C::PPW;
     for (size_t p0 = (size_t)blockIdx.x * per_cta; p0 < n_polys; p0 += (size_t)gridDim.x * per_cta) {
         const size_t p = p0 + warp * C::PPW + pw;
@@ -281,19 +290,32 @@ __global__ void __launch_bounds__(NTT_THREADS) polymul_kernel(const int32_t* a, 
         uint32_t x[16], ya[16], yb[16];
         const int32_t* sa = a + p * C::D + tau;
         const int32_t* sb = b + p * C::D + tau;
+        int32_t rb[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) x[k] = live ? to_lazy(sa[C::TPP * k]) : 0u;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) rb[k] = live ? sb[C::TPP * k] : 0;   // the second operand is in flight while the first is transformed
         fwd_strided<LOGD>(x);
         xchg_s2c<LOGD>(tile, tau, x, ya);
-        fwd_contig<LOGD>(ya, twf);
+        {
+            Sh tw[15];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = live ? to_lazy(sb[C::TPP * k]) : 0u;
-        fwd_strided<LOGD>(x);
-        xchg_s2c<LOGD>(tile, tau, x, yb);
-        fwd_contig<LOGD>(yb, twf);
+            for (int i = 0; i < 15; ++i) tw[i] = tw_sm[0][tau][i];
+            fwd_contig<LOGD>(ya, tw);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) x[k] = to_lazy(rb[k]);
+            fwd_strided<LOGD>(x);
+            xchg_s2c<LOGD>(tile, tau, x, yb);
+            fwd_contig<LOGD>(yb, tw);
+        }
 #pragma unroll
         for (int k = 0; k < 16; ++k) ya[k] = mont_mul(red_q(ya[k]), (int32_t)red_q(yb[k]));   // [0, q] fits int32; the 2^-32 is repaid by c_last[2..3]
-        inv_contig<LOGD>(ya, twi);
+        {
+            Sh tw[15];
+#pragma unroll
+            for (int i = 0; i < 15; ++i) tw[i] = tw_sm[1][tau][i];
+            inv_contig<LOGD>(ya, tw);
+        }
         xchg_c2s<LOGD>(tile, tau, ya, x);
         int32_t o[16];
         inv_strided<LOGD, 2>(x, o);
