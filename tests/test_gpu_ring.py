@@ -341,3 +341,18 @@ def test_ring_kernels_stay_inside_their_buffers(d, q, n):
     for sample in (lambda: r.sample_coef(seeds, norm_bound=max(1, min(q // 2, 7)), weight_bound=d // 2), lambda: r.sample_ntt(seeds)):
         out = sample()
         assert out.shape == (len(seeds), d) and int(out.abs().max()) <= q // 2
+
+
+def test_empty_batches():
+    """zero polynomials: every entry point returns an empty result and launches nothing"""
+    from fusion_cryptography_b200 import native
+
+    r = native.get_ring(257, 64, [1] * 64, [1] * 64)
+    e = torch.empty((0, 64), dtype=torch.int32, device="cuda")
+    for out in (r.ntt_fwd(e), r.ntt_inv(e), r.pointwise_mul(e, e), r.pointwise_add(e, e), r.polymul(e, e), r.sample_coef([]), r.sample_ntt([])):
+        assert out.shape == (0, 64)
+    for secpar in (128, 256):
+        ctx = native.get_context(secpar)
+        z = torch.empty((0, ctx.d), dtype=torch.int32, device="cuda")
+        for out in (ctx.ntt_fwd(z), ctx.ntt_inv(z), ctx.pointwise_mul(z, z), ctx.polymul(z, z), ctx.ntt_pass(z, z)):
+            assert out.shape == (0, ctx.d)
