@@ -136,9 +136,9 @@ __device__ __forceinline__ void ring_pass(uint32_t* tile, const Sh* __restrict__
                 for (int k = 0; k < N; ++k) {
                     if (k & dk) continue;
                     const Sh tws = twc ? twc[(((1 << s) - 1) + (k >> (R - s))) * twc_items + w] : row[k >> (R - s)];
-                    const uint32_t u = x[k], v = rq_mul(x[k + dk], tws, q);
-                    x[k] = rq_add(u, v, q);
-                    x[k + dk] = rq_sub(u, v, q);
+                    const uint32_t u = min(x[k], x[k] - q), v = rq_mul(x[k + dk], tws, q);   // lazy: x in [0, 2q) between the stages (2q < 2^32)
+                    x[k] = u + v;
+                    x[k + dk] = u - v + q;
                 }
             } else {
                 const int lt = lo_bits + s, dk = 1 << s;
@@ -156,7 +156,7 @@ __device__ __forceinline__ void ring_pass(uint32_t* tile, const Sh* __restrict__
         if (TO_GLOBAL) {
             int32_t o[N];
 #pragma unroll
-            for (int k = 0; k < N; ++k) o[k] = rq_cent(INVERSE ? rq_mul(x[k], kk.ninv, q) : x[k], q, kk.half);
+            for (int k = 0; k < N; ++k) o[k] = rq_cent(INVERSE ? rq_mul(x[k], kk.ninv, q) : min(x[k], x[k] - q), q, kk.half);   // forward values are lazy
             if (VEC && R >= 2 && lo_bits == 0) {
                 int4* g4 = reinterpret_cast<int4*>(gout + base);
 #pragma unroll
