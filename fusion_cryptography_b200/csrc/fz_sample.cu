@@ -19,6 +19,10 @@ namespace fz {
 constexpr int MT_N = 624, MT_M = 397;
 constexpr int SMP_STREAMS = 90;             // generators per CTA
 constexpr int SMP_THREADS = 96;
+#ifndef FZ_SMP_TRIP
+#define FZ_SMP_TRIP 16
+#endif
+constexpr int SMP_TRIP = FZ_SMP_TRIP;   // outputs regenerated per trip of the dense draw loop
 constexpr int SMP_WORDS = MT_N + 8;         // state + the (key[j] + j) table of init_by_array
 constexpr int SMP_SMEM = SMP_STREAMS * SMP_WORDS * 4;
 
@@ -88,25 +92,27 @@ __device__ __forceinline__ uint32_t mt_next(Mt& s) {
     return mt_temper(v);
 }
 
-// eight outputs; s.idx is a multiple of 8 (624 = 78 * 8)
-__device__ __forceinline__ void mt_next8(Mt& s, uint32_t (&y)[8]) {
+// B outputs per trip (B = 8 or 16; 624 = 78 * 8 = 39 * 16, so s.idx stays a multiple of B): all 2B + 1 state words are loaded before the first is
+// regenerated -- with three warps per SM the loads of a trip are the only memory-level parallelism there is
+template <int B>
+__device__ __forceinline__ void mt_next_b(Mt& s, uint32_t (&y)[B]) {
     const int k = s.idx;
-    uint32_t a[9], f[8];
+    uint32_t a[B + 1], f[B];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) a[e] = MTW(s, k + e);
-    a[8] = MTW(s, k + 8 == MT_N ? 0 : k + 8);   // word 0 was regenerated 77 blocks ago, as in the sequential twist
+    for (int e = 0; e < B; ++e) a[e] = MTW(s, k + e);
+    a[B] = MTW(s, k + B == MT_N ? 0 : k + B);   // word 0 was regenerated at the start of this round, as in the sequential twist
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < B; ++e) {
         const int km = k + e + MT_M < MT_N ? k + e + MT_M : k + e + MT_M - MT_N;   // old word above k, new word below
         f[e] = MTW(s, km);
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < B; ++e) {
         const uint32_t v = mt_regen(a[e], a[e + 1], f[e]);
         MTW(s, k + e) = v;
         y[e] = mt_temper(v);
     }
-    s.idx = k + 8 == MT_N ? 0 : k + 8;
+    s.idx = k + B == MT_N ? 0 : k + B;
 }
 
 __device__ __forceinline__ uint32_t mt_randbelow(Mt& s, uint32_t n) {
@@ -147,10 +153,10 @@ __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(int mode, const uin
         int k = 0;
         uint32_t have_mag = 0, mag = 0;
         while (k < d) {
-            uint32_t y[8];
-            mt_next8(s, y);
+            uint32_t y[SMP_TRIP];
+            mt_next_b<SMP_TRIP>(s, y);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
+            for (int e = 0; e < SMP_TRIP; ++e) {
                 const uint32_t rm = y[e] >> shb, rs = y[e] >> 30;
                 const uint32_t live = k < d ? 1u : 0u;
                 const uint32_t take_mag = live & (have_mag ^ 1u) & (rm < bound ? 1u : 0u);
