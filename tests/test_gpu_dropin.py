@@ -178,3 +178,31 @@ def test_top_level_dropin_layout():
     assert out.returncode == 0, out.stderr[-2000:]
     assert "130985dc44f2699f1fcffb8fc95a2fbe61682ea97b51ba1d03c2c83c1d735105" in out.stdout  # SURVEY 8c demo digest
     assert "['3h7ujoQfqJ915fsSLGNU', 'eMPYPDeghzvdj9KQ949J']" in out.stdout and "(True, '')" in out.stdout
+
+
+def test_wire_format_round_trip(ff):
+    """keys / signatures / aggregates as int32 blobs; the decoded objects print and verify exactly like the originals"""
+    from fusion_cryptography_b200 import wire
+
+    for secpar in (128, 256):
+        params = ff.fusion_setup(secpar, 7)
+        keys = [ff.keygen(params, 1000 + 2 * i) for i in range(3)]
+        msgs = [f"wire-{i}" for i in range(3)]
+        sigs = [ff.sign(params, k, m) for k, m in zip(keys, msgs)]
+        vks = [k[1] for k in keys]
+        agg = ff.aggregate(params, vks, msgs, sigs)
+        vks2 = [wire.vk_from_bytes(params, wire.vk_to_bytes(params, v)) for v in vks]
+        sigs2 = [wire.signature_from_bytes(params, wire.signature_to_bytes(params, s)) for s in sigs]
+        agg2 = wire.signature_from_bytes(params, wire.signature_to_bytes(params, agg))
+        assert [str(v) for v in vks2] == [str(v) for v in vks] and [str(s) for s in sigs2] == [str(s) for s in sigs] and str(agg2) == str(agg)
+        assert len(wire.vk_to_bytes(params, vks[0])) == 12 + 2 * params.degree * 4
+        assert ff.verify(params, vks2, msgs, agg2) == (True, "")
+        assert str(ff.aggregate(params, vks2, msgs, sigs2)) == str(agg)
+        blob = bytearray(wire.signature_to_bytes(params, agg))
+        with pytest.raises(ValueError):
+            wire.signature_from_bytes(params, bytes(blob[:-4]))
+        with pytest.raises(ValueError):
+            wire.vk_from_bytes(params, bytes(blob))
+        blob[12:16] = (2**31 - 1).to_bytes(4, "little")
+        with pytest.raises(ValueError):
+            wire.signature_from_bytes(params, bytes(blob))
