@@ -80,15 +80,10 @@ class GeneralMatrix:
         base = getattr(self, "_base", None)
         if base is not None and len(self.matrix) == base.shape[0] and all(
                 len(row) == base.shape[1] and all(getattr(e, "_vals", 0) is None and e._t is not None for e in row) for row in self.matrix):
-            ok = True
-            for i, row in enumerate(self.matrix):
-                for j, e in enumerate(row):
-                    if e._t.data_ptr() != base[i, j].data_ptr():
-                        ok = False
-                        break
-                if not ok:
-                    break
-            if ok:
+            # the elements must still be the views handed out with the base (a caller may have replaced an entry): compare addresses by
+            # arithmetic -- indexing base[i, j] would build a fresh view per entry, which dominated small aggregate / verify calls
+            p0, s0, s1 = base.data_ptr(), base.stride(0) * base.element_size(), base.stride(1) * base.element_size()
+            if all(e._t.data_ptr() == p0 + i * s0 + j * s1 for i, row in enumerate(self.matrix) for j, e in enumerate(row)):
                 return base
         return torch.stack([torch.stack([e._tensor() for e in row]) for row in self.matrix])
 
