@@ -486,7 +486,9 @@ def _device_hash_pipeline(params: Params, keys: List[OneTimeVerificationKey], me
 
 def hash_ag(params: Params, keys: List[OneTimeVerificationKey], messages: List[str]) -> List[AggregationCoefficient]:
     """Reference :632-652 (keys are hashed in the order given; aggregate / verify sort first)."""
-    if _patched():
+    # the reference only ever takes str(key) here, so ANY object works as a key (its own KAT generator passes (sk, vk) tuples,
+    # KATs/generate_KAT_values.py:120-133): everything that is not a plain verification key goes through the text-level helpers
+    if _patched() or not all(isinstance(k, OneTimeVerificationKey) for k in keys):
         pre = [hash_message_to_int(params=params, message=m) for _, m in zip(keys, messages)]
         challs = [hash_ch(params=params, key=k, message=m) for k, m in zip(keys, messages)]
         b = hash_vks_and_ints_and_challs_to_bytes(params=params, keys=keys, prehashed_messages=pre, challenges=challs)

@@ -206,3 +206,36 @@ def test_wire_format_round_trip(ff):
         blob[12:16] = (2**31 - 1).to_bytes(4, "little")
         with pytest.raises(ValueError):
             wire.signature_from_bytes(params, bytes(blob))
+
+
+@pytest.mark.parametrize("secpar", [128, 256])
+def test_every_kat_kind_on_the_device(ff, secpar):
+    """Every kind of row the reference's KAT generator writes (KATs/generate_KAT_values.py), on the CUDA path against digests recorded from the
+    unmodified reference (tests/golden/make_kat_golden.py) -- including the kinds whose CSVs the reference's repository is missing, and the
+    generator's (sk, vk) tuples as keys of hash_ag / hash_vks_and_ints_and_challs_to_bytes (only str(key) is hashed there)."""
+    import json
+
+    def sha(x):
+        return hashlib.sha256(str(x).encode()).hexdigest()
+
+    G = json.load(open(os.path.join(ROOT, "tests", "golden", "kat_kinds_golden.json")))[str(secpar)]
+    p = ff.fusion_setup(secpar, G["seed_a"])
+    assert sha(p) == G["setup"]
+    msgs = [str(i) for i in range(10)]
+    otks = [ff.keygen(p, s) for s in G["key_seeds"]]
+    assert [sha(k) for k in otks] == G["keygen"]
+    vks = [k[1] for k in otks]
+    pre = [ff.hash_message_to_int(p, m) for m in msgs]
+    assert [str(i) for i in pre] == G["prehash"]
+    assert [sha(ff.hash_vk_and_int_to_bytes(p, v, i, G["n_ch"])) for v, i in zip(vks, pre)] == G["xof"]
+    challs = [ff.hash_ch(p, v, m) for v, m in zip(vks, msgs)]
+    assert [sha(c) for c in challs] == G["hash_ch"]
+    sigs = [ff.sign(p, k, m) for k, m in zip(otks, msgs)]
+    assert [sha(s) for s in sigs] == G["sign"]
+    assert sha(ff.hash_vks_and_ints_and_challs_to_bytes(p, vks, pre, challs)) == G["ag_bytes_vks"]
+    assert sha(ff.hash_vks_and_ints_and_challs_to_bytes(p, otks, pre, challs)) == G["ag_bytes_tuples"]
+    assert sha(ff.hash_ag(p, vks, msgs)) == G["hash_ag_vks"]
+    assert sha(ff.hash_ag(p, otks, msgs)) == G["hash_ag_tuples"]
+    agg = ff.aggregate(p, vks, msgs, sigs)
+    assert sha(agg) == G["aggregate"]
+    assert list(ff.verify(p, vks, msgs, agg)) == G["verify"]

@@ -38,3 +38,34 @@ def test_reference_unit_tests_pass_on_host_mirror(tmp_path):
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout and "error" not in r.stdout.lower(), tail
     assert "53 passed" in r.stdout, tail
+
+
+GEN = os.path.join(REF, "KATs", "generate_KAT_values.py")
+
+
+@pytest.mark.skipif(not os.path.exists(GEN), reason="no reference checkout here")
+def test_reference_kat_generator_writes_identical_files(tmp_path):
+    """The reference's KAT generator (KATs/generate_KAT_values.py, executed unmodified from the reference checkout with the global generator seeded)
+    run once against the reference and once against the host mirror (device calls served by the oracle stand-in): all 18 CSV files -- 64 MB of
+    text, among them the 12 kinds the reference's repository is missing -- must be byte-identical.  This also pins the state every call leaves
+    CPython's global generator in (the generator draws its seeds from it between calls)."""
+    import hashlib
+
+    runner = ("import random; random.seed(20231018)\n"
+              f"exec(compile(open({GEN!r}).read(), 'generate_KAT_values', 'exec'))\n")
+    mirror = tmp_path / "mirror"
+    mirror.mkdir()
+    os.symlink(os.path.join(ROOT, "fusion_cryptography_b200", "algebra"), mirror / "algebra")
+    os.symlink(os.path.join(ROOT, "fusion_cryptography_b200", "fusion"), mirror / "fusion")
+    shutil.copy(os.path.join(ROOT, "tests", "refsuite", "device_standin.py"), mirror / "native.py")
+    digests = {}
+    for name, path in (("reference", REF), ("mirror", str(mirror))):
+        wd = tmp_path / ("run_" + name)
+        wd.mkdir()
+        env = dict(os.environ, PYTHONPATH=path, FUSION_B200_REPO=ROOT, PYTHONDONTWRITEBYTECODE="1")
+        r = subprocess.run([sys.executable, "-c", runner], cwd=str(wd), env=env, capture_output=True, text=True, timeout=1500)
+        assert r.returncode == 0, (name, (r.stdout + r.stderr)[-3000:])
+        out = wd / "KAT_values"
+        digests[name] = {f: hashlib.sha256((out / f).read_bytes()).hexdigest() for f in sorted(os.listdir(out))}
+    assert len(digests["reference"]) == 18
+    assert digests["mirror"] == digests["reference"]
