@@ -516,7 +516,7 @@ def aggregate(params: Params, keys: List[OneTimeVerificationKey], messages: List
     keys, messages, signatures = keys[:n], messages[:n], signatures[:n]
     ctx = params._ctx()
     d, ell = params.degree, params.num_rows_sk
-    if _patched():
+    if _patched() or not all(isinstance(k, OneTimeVerificationKey) for k in keys):   # like hash_ag: the reference only sorts and hashes str(key) here
         order = sorted(range(n), key=lambda i: str(keys[i]))
         alphas = hash_ag(params=params, keys=[keys[i] for i in order], messages=[messages[i] for i in order])
         import torch

@@ -239,3 +239,15 @@ def test_every_kat_kind_on_the_device(ff, secpar):
     agg = ff.aggregate(p, vks, msgs, sigs)
     assert sha(agg) == G["aggregate"]
     assert list(ff.verify(p, vks, msgs, agg)) == G["verify"]
+
+
+def test_key_objects_other_than_verification_keys(ff):
+    """aggregate() only sorts by and hashes str(key) in the reference, so it accepts e.g. the (sk, vk) tuples of keygen; verify() reads the key's
+    attributes and fails with the reference's AttributeError.  Digest recorded from the reference (fusion_setup(128, 5), keygen seeds 10, 12, 14)."""
+    p = ff.fusion_setup(128, 5)
+    otks = [ff.keygen(p, 10 + 2 * i) for i in range(3)]
+    msgs = ["a", "b", "c"]
+    sigs = [ff.sign(p, k, m) for k, m in zip(otks, msgs)]
+    assert sha(str(ff.aggregate(p, otks, msgs, sigs))) == "f8a7b2a357b56258e5af70178c024968070a4a55bab59eb06009289f6033244d"
+    with pytest.raises(AttributeError, match="'tuple' object has no attribute 'left_vk_hat'"):
+        ff.verify(p, otks, msgs, sigs[0])
