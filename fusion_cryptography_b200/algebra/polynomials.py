@@ -73,6 +73,19 @@ def _eq_zero(x) -> bool:
     return x == 0
 
 
+def _check_same_ring(x, other, cls, op: str) -> None:
+    """The reference's operand checks with its exact messages (algebra/polynomials.py:118-135 / :286-303 for +, :175-194 / :346-369 for *)."""
+    if not isinstance(other, cls):
+        raise NotImplementedError(f"{op} for {type(x)} and {type(other)} not implemented")
+    for differs, add_text, mul_text in ((x.modulus != other.modulus, "moduli", "different moduli"),
+                                        (x.degree != other.degree, "degrees", "different degrees"),
+                                        (x.root != other.root, "roots of unity", "different roots of unity"),
+                                        (x.root_order != other.root_order, "root orders", "difference orders of root of unity")):
+        if differs:
+            raise NotImplementedError(f"Cannot add polynomials with different {add_text}" if op == "Addition"
+                                      else f"{op} for {type(x)} with {mul_text} not implemented")
+
+
 class PolynomialRepresentation(object):
     modulus: int
     degree: int
@@ -199,16 +212,7 @@ class PolynomialCoefficientRepresentation(PolynomialRepresentation):
         return all((x - y) % self.modulus == 0 for x, y in zip(self._peek(), other._peek()))
 
     def _check_other(self, other, what: str):
-        if not isinstance(other, PolynomialCoefficientRepresentation):
-            raise NotImplementedError(f"{what} for {type(self)} and {type(other)} not implemented")
-        elif self.modulus != other.modulus:
-            raise NotImplementedError(f"Cannot {what.lower()[:3]} polynomials with different moduli")
-        elif self.degree != other.degree:
-            raise NotImplementedError(f"Cannot {what.lower()[:3]} polynomials with different degrees")
-        elif self.root != other.root:
-            raise NotImplementedError(f"Cannot {what.lower()[:3]} polynomials with different roots of unity")
-        elif self.root_order != other.root_order:
-            raise NotImplementedError(f"Cannot {what.lower()[:3]} polynomials with different root orders")
+        _check_same_ring(self, other, PolynomialCoefficientRepresentation, what)
 
     def __add__(self, other):
         if _eq_zero(other):
@@ -301,16 +305,7 @@ class PolynomialNTTRepresentation(PolynomialRepresentation):
     __hash__ = None
 
     def _check_other(self, other, verb: str):
-        if not isinstance(other, PolynomialNTTRepresentation):
-            raise NotImplementedError(f"{verb} for {type(self)} and {type(other)} not implemented")
-        elif self.modulus != other.modulus:
-            raise NotImplementedError(f"{verb} of polynomials with different moduli not implemented")
-        elif self.degree != other.degree:
-            raise NotImplementedError(f"{verb} of polynomials with different degrees not implemented")
-        elif self.root != other.root:
-            raise NotImplementedError(f"{verb} of polynomials with different roots of unity not implemented")
-        elif self.root_order != other.root_order:
-            raise NotImplementedError(f"{verb} of polynomials with different root orders not implemented")
+        _check_same_ring(self, other, PolynomialNTTRepresentation, verb)
 
     def __add__(self, other):
         if _eq_zero(other):
@@ -369,6 +364,21 @@ def transform(x: Union[PolynomialCoefficientRepresentation, PolynomialNTTReprese
         raise NotImplementedError(f"Transform for {type(x)} not implemented")
 
 
+def _effective_seed(seed) -> int:
+    """The integer CPython's ``random.seed(seed)`` turns its argument into (Lib/random.py seed(), version 2, and Modules/_randommodule.c
+    random_seed): an int is used as is (its absolute value), str / bytes / bytearray become int.from_bytes(a + sha512(a).digest()), anything
+    else its hash.  The device sampler takes up to 256 bits; longer keys (every str / bytes seed) are refused there."""
+    if isinstance(seed, int):
+        return seed
+    if isinstance(seed, str):
+        seed = seed.encode()
+    if isinstance(seed, (bytes, bytearray)):
+        import hashlib
+
+        return int.from_bytes(bytes(seed) + hashlib.sha512(seed).digest(), "big")
+    return abs(hash(seed))
+
+
 def _host_draw_coefficients(degree: int, bound: int, weight: int) -> List[int]:
     """The reference's draw order on CPython's global generator (:451-459)."""
     coefficients = [(1 + _random.randrange(bound)) * (1 - 2 * _random.randrange(2)) for _ in range(weight)]
@@ -395,7 +405,7 @@ def sample_polynomial_coefficient_representation(modulus: int, degree: int, root
                                                 coefficients=[0] * degree)
     _random.seed(seed)
     _host_draw_coefficients(degree, bound, num)  # state side effect only (and the reference's ValueError when bound = 0 < num: randrange(0))
-    t = proto._ctx().sample_coef([seed], norm_bound=max(bound, 1), weight_bound=num)[0]
+    t = proto._ctx().sample_coef([_effective_seed(seed)], norm_bound=max(bound, 1), weight_bound=num)[0]
     return PolynomialCoefficientRepresentation._from_tensor(proto._ring(), t)
 
 
@@ -406,7 +416,7 @@ def sample_polynomial_ntt_representation(modulus: int, degree: int, root: int, i
         values = [_random.randrange(modulus) - (modulus // 2) for _ in range(degree)]
         return PolynomialNTTRepresentation(modulus=modulus, degree=degree, root=root, inv_root=inv_root, root_order=root_order, values=values)
     proto = PolynomialNTTRepresentation(modulus=modulus, degree=degree, root=root, inv_root=inv_root, root_order=root_order, values=[0] * degree)
-    t = proto._ctx().sample_ntt([seed])[0]
+    t = proto._ctx().sample_ntt([_effective_seed(seed)])[0]
     _random.seed(seed)
     for _ in range(degree):
         _random.randrange(modulus)  # state side effect only

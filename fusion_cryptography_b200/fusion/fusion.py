@@ -306,7 +306,17 @@ def keygen(params: Params, seed: Optional[int]) -> OneTimeKeyTuple:
     ctx = params._ctx()
     d, ell = params.degree, params.num_rows_sk
     ring = params._ring()
-    if seed is None or not (0 <= seed < 2**64 - 1):
+    if isinstance(seed, (str, bytes, bytearray)):
+        # the reference samples the left key from such a seed -- observable only through the caller's global generator -- and then fails at
+        # `seed + 1` (:352); the device sampler takes keys up to 256 bits, a str / bytes seed is 512 bits and more, so only the host side is replayed
+        from random import seed as _reseed
+
+        _reseed(seed)
+        for _ in range(min(d, params.omega_sk)):
+            _random.randrange(params.beta_sk)
+            _random.randrange(2)
+        seed + 1   # TypeError: can only concatenate str (not "int") to str
+    if not isinstance(seed, int) or not (0 <= seed < 2**64 - 1):
         # seeds outside the batched kernel's u64 range (negative / 64 bits and more) take the per-polynomial device
         # sampler through the same matrix code path as the reference; seed=None raises TypeError at `seed + 1`
         # after the left key has consumed the caller's generator, exactly like the reference (:352)
@@ -426,6 +436,9 @@ def _vk_tensors(params: Params, keys: List[OneTimeVerificationKey]):
 
 
 def _encode_messages(params: Params, messages: List[str]) -> List[bytes]:
+    for m in messages:
+        if not isinstance(m, str):   # what the reference's `dst + "," + message` raises (fusion.py:406)
+            raise TypeError(f'can only concatenate str (not "{type(m).__name__}") to str')
     return [m.encode() for m in messages]
 
 
@@ -488,7 +501,8 @@ def hash_ag(params: Params, keys: List[OneTimeVerificationKey], messages: List[s
     """Reference :632-652 (keys are hashed in the order given; aggregate / verify sort first)."""
     # the reference only ever takes str(key) here, so ANY object works as a key (its own KAT generator passes (sk, vk) tuples,
     # KATs/generate_KAT_values.py:120-133): everything that is not a plain verification key goes through the text-level helpers
-    if _patched() or not all(isinstance(k, OneTimeVerificationKey) for k in keys):
+    if _patched() or len(keys) != len(messages) or not all(isinstance(k, OneTimeVerificationKey) for k in keys):
+        # (unequal lengths: the reference zips the per-signer lists but sizes the XOF output by len(keys), :636-647)
         pre = [hash_message_to_int(params=params, message=m) for _, m in zip(keys, messages)]
         challs = [hash_ch(params=params, key=k, message=m) for k, m in zip(keys, messages)]
         b = hash_vks_and_ints_and_challs_to_bytes(params=params, keys=keys, prehashed_messages=pre, challenges=challs)

@@ -30,6 +30,9 @@ def _np(x):
 
 class Ring:
     def __init__(self, q, d, fwd=None, inv=None):
+        for t in (fwd, inv):
+            if t is not None and len(t) < d:
+                raise IndexError("list index out of range")   # as native.Ring does (the reference's table[m + i])
         self.q, self.d, self.fwd, self.inv, self.device = q, d, fwd, inv, torch.device("cpu")
 
     @staticmethod

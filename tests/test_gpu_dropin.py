@@ -251,3 +251,17 @@ def test_key_objects_other_than_verification_keys(ff):
     assert sha(str(ff.aggregate(p, otks, msgs, sigs))) == "f8a7b2a357b56258e5af70178c024968070a4a55bab59eb06009289f6033244d"
     with pytest.raises(AttributeError, match="'tuple' object has no attribute 'left_vk_hat'"):
         ff.verify(p, otks, msgs, sigs[0])
+
+
+def test_differential_battery_on_the_device():
+    """tests/refsuite/differential_cases.py (about 150 ordinary, edge and erroneous calls over the reference's three modules) in the drop-in layout on
+    the CUDA path, against the outcomes recorded from the unmodified reference (tests/golden/make_differential_golden.py)."""
+    import json
+
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "fusion_cryptography_b200"))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "refsuite", "differential_cases.py")], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    got = json.loads(r.stdout.strip().splitlines()[-1])
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "differential_golden.json")))
+    diff = {k: (v, got.get(k)) for k, v in want.items() if got.get(k) != v}
+    assert not diff, diff

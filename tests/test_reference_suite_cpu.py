@@ -69,3 +69,28 @@ def test_reference_kat_generator_writes_identical_files(tmp_path):
         digests[name] = {f: hashlib.sha256((out / f).read_bytes()).hexdigest() for f in sorted(os.listdir(out))}
     assert len(digests["reference"]) == 18
     assert digests["mirror"] == digests["reference"]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "fusion", "fusion.py")), reason="no reference checkout here")
+def test_differential_battery_against_the_reference(tmp_path):
+    """tests/refsuite/differential_cases.py -- about 150 ordinary, edge and erroneous calls over algebra.ntt, algebra.polynomials, algebra.matrices
+    and fusion.fusion (digests of str(result), or the exception's type and text) -- run with the names resolving to the unmodified reference and to
+    the host mirror: every outcome must be identical.  It found (and now pins) the reference's exact NotImplementedError texts for mixed-ring
+    operands, hash_ag's behaviour for unequal list lengths and for arbitrary key objects, and its handling of non-int seeds and non-str messages."""
+    import json
+
+    mirror = tmp_path / "mirror"
+    mirror.mkdir()
+    os.symlink(os.path.join(ROOT, "fusion_cryptography_b200", "algebra"), mirror / "algebra")
+    os.symlink(os.path.join(ROOT, "fusion_cryptography_b200", "fusion"), mirror / "fusion")
+    shutil.copy(os.path.join(ROOT, "tests", "refsuite", "device_standin.py"), mirror / "native.py")
+    script = os.path.join(ROOT, "tests", "refsuite", "differential_cases.py")
+    out = {}
+    for name, path in (("reference", REF), ("mirror", str(mirror))):
+        env = dict(os.environ, PYTHONPATH=path, FUSION_B200_REPO=ROOT, PYTHONDONTWRITEBYTECODE="1")
+        r = subprocess.run([sys.executable, script], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=1500)
+        assert r.returncode == 0, (name, (r.stdout + r.stderr)[-3000:])
+        out[name] = json.loads(r.stdout.strip().splitlines()[-1])
+    assert len(out["reference"]) >= 150
+    diff = {k: (v, out["mirror"].get(k)) for k, v in out["reference"].items() if out["mirror"].get(k) != v}
+    assert not diff, diff
