@@ -180,6 +180,25 @@ case("xof_arbitrary_key", lambda: ff.hash_vk_and_int_to_bytes(p128, "not a key",
 case("sample_matrix", lambda: ff.sample_coefficient_matrix(seed=3, modulus=257, degree=8, root_order=16, root=root, inv_root=inv_root, num_rows=2, num_cols=3,
                                                             norm_bound=4, weight_bound=5))
 case("sample_ntt_matrix", lambda: ff.sample_ntt_matrix(seed=3, modulus=257, degree=8, root_order=16, root=root, inv_root=inv_root, num_rows=2, num_cols=2))
+
+
+def big_key(p, seed):
+    """a key pair built by hand from secret polynomials with coefficients up to q/2: consistent (vk = A * sk), far outside the scheme's norm bound"""
+    mk = lambda sd: ff.sample_coefficient_matrix(seed=sd, modulus=p.modulus, degree=p.degree, root_order=p.root_order, root=p.root, inv_root=p.inv_root,  # noqa: E731
+                                                 num_rows=p.num_rows_sk, num_cols=p.num_cols_sk, norm_bound=p.modulus // 2, weight_bound=p.degree)
+    hat = lambda m: GeneralMatrix(matrix=[[transform(e) for e in row] for row in m.matrix])  # noqa: E731
+    sl, sr = hat(mk(seed)), hat(mk(seed + 1))
+    return (ff.OneTimeSigningKey(seed=seed, left_sk_hat=sl, right_sk_hat=sr),
+            ff.OneTimeVerificationKey(left_vk_hat=p.public_challenge * sl, right_vk_hat=p.public_challenge * sr))
+
+
+bk = big_key(p128, 21)
+case("handmade_key", lambda: bk[1])
+bsig = ff.sign(p128, bk, "big")
+case("handmade_sign", lambda: bsig)
+bagg = ff.aggregate(p128, [bk[1]], ["big"], [bsig])
+case("verify_norm_too_large", lambda: ff.verify(p128, [bk[1]], ["big"], bagg))
+case("verify_mixed_norm", lambda: ff.verify(p128, [bk[1], k128[1]], ["big", "m"], ff.aggregate(p128, [bk[1], k128[1]], ["big", "m"], [bsig, ff.sign(p128, k128, "m")])))
 case("setup_unknown", lambda: sorted(vars(ff.fusion_setup(64, 1))))
 case("setup_none", lambda: len(str(ff.fusion_setup(128, None))) > 1000)
 
