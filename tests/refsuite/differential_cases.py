@@ -105,6 +105,21 @@ random.seed(4)
 case("sample_coef_unseeded", lambda: sample_polynomial_coefficient_representation(norm_bound=5, weight_bound=3, seed=None, **kw))
 case("sample_ntt_unseeded", lambda: sample_polynomial_ntt_representation(seed=None, **kw))
 
+# ---- larger rings (the general-ring kernels on the device)
+for dd, qq in ((64, 7681), (1024, 12289), (2048, 65537 * 0 + 12289)):
+    rr = find_primitive_root(modulus=qq, root_order=2 * dd)
+    kk = dict(modulus=qq, degree=dd, root=rr, inv_root=pow(rr, qq - 2, qq), root_order=2 * dd)
+    f = sample_polynomial_coefficient_representation(norm_bound=qq // 2, weight_bound=dd, seed=1000 + dd, **kk)
+    g = sample_polynomial_coefficient_representation(norm_bound=3, weight_bound=dd // 3, seed=2000 + dd, **kk)
+    h = sample_polynomial_ntt_representation(seed=3000 + dd, **kk)
+    case(f"big_sample_{dd}", lambda: (f, g, h))
+    case(f"big_transform_{dd}", lambda: (transform(f), transform(h)))
+    case(f"big_roundtrip_{dd}", lambda: transform(transform(f)) == f)
+    case(f"big_ntt_ops_{dd}", lambda: (transform(f) * transform(g) + h, transform(f) - h))
+    if dd <= 1024:
+        case(f"big_coef_mul_{dd}", lambda: f * g)
+        case(f"big_convolution_{dd}", lambda: transform(transform(f) * transform(g)) == f * g)
+
 # ---- algebra.matrices
 M1 = GeneralMatrix(matrix=[[ca, cb], [cb, ca]])
 M2 = GeneralMatrix(matrix=[[cb], [ca]])

@@ -91,6 +91,6 @@ def test_differential_battery_against_the_reference(tmp_path):
         r = subprocess.run([sys.executable, script], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=1500)
         assert r.returncode == 0, (name, (r.stdout + r.stderr)[-3000:])
         out[name] = json.loads(r.stdout.strip().splitlines()[-1])
-    assert len(out["reference"]) >= 157
+    assert len(out["reference"]) >= 173
     diff = {k: (v, out["mirror"].get(k)) for k, v in out["reference"].items() if out["mirror"].get(k) != v}
     assert not diff, diff
