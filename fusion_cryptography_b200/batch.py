@@ -31,7 +31,7 @@ VERIFY_REASONS = {
 
 @dataclass
 class KeyBatch:
-    sk_hat: torch.Tensor  # [n, 2, d]: the one distinct row of sk_l / sk_r (all ell rows of a seeded key are equal)
+    sk_hat: Optional[torch.Tensor]  # [n, 2, d] (None for keys from keygen_rows): the one distinct row of sk_l / sk_r (all ell rows of a seeded key are equal)
     vk_l: torch.Tensor    # [n, d]
     vk_r: torch.Tensor    # [n, d]
     sk_l: Optional[torch.Tensor] = None  # [n, ell, d] when materialised
@@ -78,6 +78,37 @@ class Engine:
         for lo in range(0, n, chunk):
             hi = min(n, lo + chunk)
             self.ctx.keygen_sign(self.A, seeds_d[lo:hi], msgs[lo:hi], vk_l[lo:hi], vk_r[lo:hi], sigs[lo:hi] if keep_sigs else sigs[: hi - lo])
+        return vk_l, vk_r, (sigs if keep_sigs else None)
+
+    def keygen_rows(self, row_seeds) -> KeyBatch:
+        """General ell-row keygen: row_seeds [n, 2, ell] u64, one sampler seed per secret-key row (2*ell generators, 2*ell transforms and two
+        ell-term products per key; nothing of quirk Q1 is used).  Keys are materialised as ell rows (166 KiB per key at secpar 256)."""
+        sk_l, sk_r, vk_l, vk_r = self.ctx.keygen_rows(self.A, row_seeds)
+        return KeyBatch(sk_hat=None, vk_l=vk_l, vk_r=vk_r, sk_l=sk_l, sk_r=sk_r)
+
+    def keygen_sign_rows(self, row_seeds, msgs: Sequence[bytes], chunk: int = 8192, keep_sigs: bool = True):
+        """keygen + sign through the general ell-row kernels only (fz_keygen_rows -> fz_hash_ch -> fz_sign_mac), chunked so that the secret
+        keys of one chunk (2 * ell KiB each) are the only ones resident.  Returns (vk_l, vk_r, sigs or None)."""
+        import numpy as np
+
+        ctx, dev = self.ctx, self.ctx.device
+        if not isinstance(row_seeds, torch.Tensor):
+            row_seeds = torch.from_numpy(np.ascontiguousarray(row_seeds, dtype=np.uint64).view(np.int64))
+        row_seeds = row_seeds.to(dev)
+        n = row_seeds.shape[0]
+        if not isinstance(msgs, native.PackedMessages):
+            msgs = ctx.pack_messages(list(msgs))
+        vk_l = torch.empty((n, self.d), dtype=torch.int32, device=dev)
+        vk_r = torch.empty((n, self.d), dtype=torch.int32, device=dev)
+        c = min(chunk, max(n, 1))
+        sigs = torch.empty((n if keep_sigs else c, self.ell, self.d), dtype=torch.int32, device=dev)
+        sk = (torch.empty((c, self.ell, self.d), dtype=torch.int32, device=dev), torch.empty((c, self.ell, self.d), dtype=torch.int32, device=dev))
+        for lo in range(0, n, c):
+            hi = min(n, lo + c)
+            sk_l, sk_r, vl, vr = ctx.keygen_rows(self.A, row_seeds[lo:hi], out=sk)
+            vk_l[lo:hi], vk_r[lo:hi] = vl, vr
+            c_hat = ctx.hash_ch(vl, vr, ctx.hash_msg(msgs[lo:hi]))
+            ctx.sign_mac(sk_l, sk_r, c_hat, out=sigs[lo:hi] if keep_sigs else sigs[: hi - lo])
         return vk_l, vk_r, (sigs if keep_sigs else None)
 
     # ------------------------------------------------------------------ aggregate / verify

@@ -561,6 +561,33 @@ int fz_keygen(fz_ctx* ctx, const int32_t* A, const uint64_t* seeds, size_t n, in
     return rc;
 }
 
+// The general ell-row form of fusion.py:338-373: row k of sk_l[i] is sample_polynomial_coefficient_representation(seed = row_seeds[i][0][k])
+// (algebra/polynomials.py:436-467), row k of sk_r[i] comes from row_seeds[i][1][k]; then the 2*ell transforms of fusion.py:364-368 and the two
+// 1 x ell by ell x 1 products of :369-370.  With row_seeds[i][0][k] = seed_i and row_seeds[i][1][k] = seed_i + 1 for every k this IS
+// keygen(params, seed_i) computed the long way (2*ell generators, 2*ell transforms, ell-term products) -- no use of quirk Q1.
+size_t fz_keygen_rows_workspace(const fz_ctx* ctx, size_t n) { return r256(2 * n * ctx->ell * 4 * 4) + r256(2 * n * ctx->ell * 4) + 1024; }
+
+int fz_keygen_rows(fz_ctx* ctx, const int32_t* A, const uint64_t* row_seeds, size_t n, int32_t* sk_l, int32_t* sk_r, int32_t* vk_l, int32_t* vk_r, void* ws,
+                   size_t ws_bytes, void* stream) {
+    FZ_REQUIRE(ctx && (n == 0 || (A && row_seeds && sk_l && sk_r && vk_l && vk_r && ws)), "fz_keygen_rows: NULL argument");
+    if (n == 0) return 0;
+    const size_t ell = ctx->ell, d = ctx->d;
+    Carver cv(ws, ws_bytes);
+    uint32_t* keys = cv.take<uint32_t>(2 * n * ell * 4);
+    int32_t* klen = cv.take<int32_t>(2 * n * ell);
+    FZ_REQUIRE(cv.ok, "fz_keygen_rows: workspace too small (see fz_keygen_rows_workspace)");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_row_seeds_to_keys(ctx, (const unsigned long long*)row_seeds, n, (int)ell, keys, klen, st);   // side-major keys
+    // one generator per row, written straight into the secret-key matrices (beta_sk = 52, omega_sk = d: fusion.py:87, 90)
+    if (!rc) rc = launch_sample(ctx, 0, keys, 4, klen, n * ell, 52u, ctx->d, sk_l, st);
+    if (!rc) rc = launch_sample(ctx, 0, keys + n * ell * 4, 4, klen + n * ell, n * ell, 52u, ctx->d, sk_r, st);
+    if (!rc) rc = launch_ntt(ctx, 0, sk_l, sk_l, n * ell, st);
+    if (!rc) rc = launch_ntt(ctx, 0, sk_r, sk_r, n * ell, st);
+    if (!rc) rc = launch_matvec(ctx, A, sk_l, d, ell * d, vk_l, n, st);
+    if (!rc) rc = launch_matvec(ctx, A, sk_r, d, ell * d, vk_r, n, st);
+    return rc;
+}
+
 // fusion.py:338-373 + 534-557 in one call: n one-time keys from u64 seeds, each signing message i (msgs[offs[i]..offs[i+1]) on
 // the device).  The secret keys never leave the workspace; vk_l / vk_r: [n][d], sig: [n][ell][d].
 size_t fz_keygen_sign_workspace(const fz_ctx* ctx, size_t n) {

@@ -197,6 +197,21 @@ __global__ void seeds_to_keys_kernel(const unsigned long long* __restrict__ seed
     else { k1[0] = (uint32_t)s1; k1[1] = (uint32_t)(s1 >> 32); k1[2] = 0; k1[3] = 0; klen[2 * i + 1] = k1[1] ? 2 : 1; }
 }
 
+// u64 row seeds [n][2][rows] -> limb keys, side-major [2][n][rows] (general ell-row keygen: every row of a key matrix has its own seed;
+// side-major so that each side is one contiguous sampler launch writing straight into sk_l / sk_r)
+__global__ void row_seeds_to_keys_kernel(const unsigned long long* __restrict__ seeds, size_t n, int rows, uint32_t* __restrict__ keys,
+                                         int32_t* __restrict__ klen) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n * rows) return;
+    const size_t i = t / (2 * (size_t)rows), r = t % (2 * (size_t)rows);
+    const size_t side = r / rows, k = r % rows;
+    const size_t o = side * n * rows + i * rows + k;
+    const unsigned long long s0 = seeds[t];
+    uint32_t* k0 = keys + o * 4;
+    k0[0] = (uint32_t)s0; k0[1] = (uint32_t)(s0 >> 32); k0[2] = 0; k0[3] = 0;
+    klen[o] = k0[1] ? 2 : 1;
+}
+
 // dst[b][r][:] = src[b][:] for r < rows  (quirk Q1: every row of a seeded key matrix is the same polynomial)
 __global__ void __launch_bounds__(256) replicate_rows_kernel(const int4* __restrict__ src, int4* __restrict__ dst, size_t batch0, int rows, int d4,
                                                                size_t src_batch_stride4) {
@@ -236,6 +251,13 @@ int launch_seeds_to_keys(const fz_ctx* ctx, const unsigned long long* seeds, siz
     seeds_to_keys_kernel<<<(int)((n + 127) / 128), 128, 0, st>>>(seeds, n, keys, klen);
     (void)ctx;
     return check(cudaGetLastError(), "seeds_to_keys launch");
+}
+
+int launch_row_seeds_to_keys(const fz_ctx* ctx, const unsigned long long* seeds, size_t n, int rows, uint32_t* keys, int32_t* klen, cudaStream_t st) {
+    if (n == 0) return 0;
+    row_seeds_to_keys_kernel<<<(unsigned)((2 * n * rows + 127) / 128), 128, 0, st>>>(seeds, n, rows, keys, klen);
+    (void)ctx;
+    return check(cudaGetLastError(), "row_seeds_to_keys launch");
 }
 
 int launch_replicate_rows(const fz_ctx* ctx, const int32_t* src, int32_t* dst, size_t batch, int rows, size_t src_batch_stride, cudaStream_t st) {

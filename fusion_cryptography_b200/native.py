@@ -724,6 +724,32 @@ def keygen(self, A, seeds, want_sk: bool = True):
     return sk_l, sk_r, sk_hat, vk_l, vk_r
 
 
+def keygen_rows(self, A, row_seeds, out=None):
+    """fz_keygen_rows: the general ell-row keygen (fusion.py:338-373 without quirk Q1).  row_seeds: [n, 2, ell] u64 (numpy array or an
+    int64 device tensor holding the same bits): one sampler seed per row of sk_l (side 0) and sk_r (side 1).
+    Returns (sk_l, sk_r, vk_l, vk_r) with sk_*: [n, ell, d]; `out` may supply (sk_l, sk_r) buffers to reuse."""
+    A = self._dev(A)
+    if not isinstance(row_seeds, torch.Tensor):
+        import numpy as np
+        row_seeds = torch.from_numpy(np.ascontiguousarray(row_seeds, dtype=np.uint64).view(np.int64))
+    row_seeds = row_seeds.to(self.device).contiguous()
+    if row_seeds.dim() != 3 or row_seeds.shape[1] != 2 or row_seeds.shape[2] != self.ell:
+        raise ValueError(f"keygen_rows: row_seeds must be [n, 2, {self.ell}]")
+    n = row_seeds.shape[0]
+    self.lib.fz_keygen_rows_workspace.restype = C.c_size_t
+    ws = self._ws(self.lib.fz_keygen_rows_workspace(self._h, C.c_size_t(n)))
+    if out is not None:
+        sk_l, sk_r = out[0][:n], out[1][:n]
+    else:
+        sk_l = torch.empty((n, self.ell, self.d), dtype=torch.int32, device=self.device)
+        sk_r = torch.empty((n, self.ell, self.d), dtype=torch.int32, device=self.device)
+    vk_l = torch.empty((n, self.d), dtype=torch.int32, device=self.device)
+    vk_r = torch.empty((n, self.d), dtype=torch.int32, device=self.device)
+    self._chk(self.lib.fz_keygen_rows(self._h, _ptr(A), _ptr(row_seeds), C.c_size_t(n), _ptr(sk_l), _ptr(sk_r), _ptr(vk_l), _ptr(vk_r), _ptr(ws),
+                                      C.c_size_t(ws.numel()), self._stream()))
+    return sk_l, sk_r, vk_l, vk_r
+
+
 def keygen_sign(self, A, seeds: torch.Tensor, msgs: "PackedMessages", vk_l, vk_r, sig) -> None:
     """fz_keygen_sign: seeds (int64 view of u64, device), packed messages on the device; writes vk_l / vk_r [n, d] and sig [n, ell, d]."""
     n = seeds.numel()
@@ -744,5 +770,5 @@ def sign_mac_rows(self, sk_hat, c_hat, out=None) -> torch.Tensor:
 for _f in (_u8, _pack_messages, pack_messages, _ws, sha3_256, shake256, hash_msg, format_text, decode_poly, hash_ch, _agg_off, hash_ag, sort_keys, gather_sorted,
            aggregate_sum, fold_partials, verify_check, hash_ag_begin, hash_ag_absorb, hash_ag_squeeze, aggregate_sum_off,
            verify_target, verify_finish, hash_ag_ring, hash_ag_xof_buffer, hash_ag_text, hash_ag_absorb_ring, hash_ag_squeeze_xof,
-           hash_ag_decode, hash_ag_absorb_sliced, hash_ag_open_sponges, hash_ag_fast, _seed_keys, sample_coef, sample_ntt, keygen, keygen_sign, sign_mac_rows):
+           hash_ag_decode, hash_ag_absorb_sliced, hash_ag_open_sponges, hash_ag_fast, _seed_keys, sample_coef, sample_ntt, keygen, keygen_rows, keygen_sign, sign_mac_rows):
     setattr(Context, _f.__name__, _f)

@@ -13,6 +13,13 @@ the aggregation of a single large aggregate whose signatures are spread over the
 
 Centred partials are below 2^30 in magnitude, so an int32 ncclSum over 8 ranks could overflow; the
 partials are gathered and folded by fz_fold_partials instead (exact, and cheaper than a 64-bit reduce).
+
+verify_one_sharded has the same shape: steps 1-3, then every rank forms the partial target
+sum_i (vk_l_i * c_i + vk_r_i) * alpha_i over ITS slice of the sorted signers (fusion.py:706-714; d values), the
+world_size partial targets are gathered and added modulo q, and fusion.py:715-728 runs on the complete target.
+
+The serial sponge of step 3 (279 K dependent Keccak-f for a capacity aggregate at secpar 256) is the latency floor of
+both: sharding one aggregate spreads its DATA (83 KiB per signature) and its per-signer work, not its hash.
 """
 from __future__ import annotations
 
@@ -68,19 +75,8 @@ def aggregate_one_sharded(engine, vk_l: torch.Tensor, vk_r: torch.Tensor, msgs: 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n = vk_l.shape[0]
-    dg = ctx.hash_msg(msgs)
-    perm = ctx.sort_keys(vk_l, vk_r, [n])                              # sorted position -> original signer
-    vl_s, vr_s, dg_s = ctx.gather_sorted(vk_l, vk_r, dg, perm)
-    # (1) challenges for this rank's slice of the sorted positions, (2) all-gather
-    s0, s1 = shard_bounds(n, rank, world)
-    c_loc = ctx.hash_ch(vl_s[s0:s1], vr_s[s0:s1], dg_s[s0:s1])
-    if world > 1:
-        sizes = [shard_bounds(n, r, world)[1] - shard_bounds(n, r, world)[0] for r in range(world)]
-        c_s = all_gather_rows(c_loc, sizes, group)
-    else:
-        c_s = c_loc
-    # (3) serial aggregation hash, redundantly on every rank
-    alpha = ctx.hash_ag_fast(vl_s, vr_s, dg_s, c_s, [n])
+    # (1) challenges for this rank's slice of the sorted positions, (2) all-gather, (3) serial aggregation hash on every rank
+    perm, _, _, _, alpha, _ = _sorted_challenges(ctx, vk_l, vk_r, msgs, rank, world, group)
     # (4) partial sum over the signers whose signatures live here (original index in [lo, hi))
     lo, hi = shard_bounds(n, rank, world)
     mine = (perm >= lo) & (perm < hi)
@@ -92,3 +88,50 @@ def aggregate_one_sharded(engine, vk_l: torch.Tensor, vk_r: torch.Tensor, msgs: 
         partial = torch.zeros((1, ctx.ell, ctx.d), dtype=torch.int32, device=ctx.device)
     # (5) gather + fold
     return reduce_partial_aggregates(partial, ctx.fold_partials, group)
+
+
+def _sorted_challenges(ctx, vk_l, vk_r, msgs, rank: int, world: int, group=None):
+    """Steps 1-3 shared by the two sharded paths: sort, this rank's slice of the challenges, all-gather, serial hash."""
+    n = vk_l.shape[0]
+    dg = ctx.hash_msg(msgs)
+    perm = ctx.sort_keys(vk_l, vk_r, [n])                              # sorted position -> original signer
+    vl_s, vr_s, dg_s = ctx.gather_sorted(vk_l, vk_r, dg, perm)
+    s0, s1 = shard_bounds(n, rank, world)
+    c_loc = ctx.hash_ch(vl_s[s0:s1], vr_s[s0:s1], dg_s[s0:s1])
+    if world > 1:
+        sizes = [shard_bounds(n, r, world)[1] - shard_bounds(n, r, world)[0] for r in range(world)]
+        c_s = all_gather_rows(c_loc, sizes, group)
+    else:
+        c_s = c_loc
+    alpha = ctx.hash_ag_fast(vl_s, vr_s, dg_s, c_s, [n])
+    return perm, vl_s, vr_s, c_s, alpha, (s0, s1)
+
+
+def verify_one_sharded(engine, vk_l: torch.Tensor, vk_r: torch.Tensor, msgs: Sequence[bytes], agg: torch.Tensor, group=None) -> torch.Tensor:
+    """SURVEY 8(e) row 4 / fusion.py:680-728 for ONE aggregate of N signers whose target terms are sharded over the ranks:
+    rank r owns the sorted signer positions shard_bounds(N, r, world).  All ranks hold the keys, the messages and the
+    aggregate signature agg [1, ell, d].  Returns the uint8 code [1] (batch.VERIFY_REASONS) on every rank.
+    The argument checks of fusion.py:686-689 are the caller's (as in Engine.verify)."""
+    ctx = engine.ctx
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = vk_l.shape[0]
+    if n > ctx.capacity:
+        raise ValueError("verify_one_sharded: Too many keys.")
+    if len(msgs) != n:
+        raise ValueError("verify_one_sharded: Number of keys and messages must be equal.")
+    perm, vl_s, vr_s, c_s, alpha, (s0, s1) = _sorted_challenges(ctx, vk_l, vk_r, msgs, rank, world, group)
+    win_off = torch.tensor([0, s1 - s0], dtype=torch.int64, device=vl_s.device)
+    if s1 > s0:
+        part = ctx.verify_target(vl_s[s0:s1].contiguous(), vr_s[s0:s1].contiguous(), c_s[s0:s1].contiguous(), alpha[s0:s1].contiguous(), win_off, 1)
+    else:
+        part = torch.zeros((1, ctx.d), dtype=torch.int32, device=vl_s.device)
+    if world > 1:
+        bufs = [torch.empty_like(part) for _ in range(world)]
+        dist.all_gather(bufs, part.contiguous(), group=group)
+        target = bufs[0]
+        for b in bufs[1:]:
+            target = ctx.pointwise_add(target, b)                     # exact: every partial is a centred residue
+    else:
+        target = part
+    return ctx.verify_finish(engine.A, target, agg)

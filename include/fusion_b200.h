@@ -161,6 +161,13 @@ int fz_sample_ntt(fz_ctx* ctx, const uint32_t* keys, int key_stride, const int32
 size_t fz_keygen_workspace(const fz_ctx* ctx, size_t n);
 int fz_keygen(fz_ctx* ctx, const int32_t* A, const uint64_t* seeds, size_t n, int32_t* sk_l, int32_t* sk_r, int32_t* sk_hat, int32_t* vk_l, int32_t* vk_r,
               void* ws, size_t ws_bytes, void* stream);
+/* fusion.py:338-373 in its general ell-row form: row k of sk_l[i] / sk_r[i] is sample_polynomial_coefficient_representation
+ * (algebra/polynomials.py:436-467) seeded with row_seeds[i][0][k] / row_seeds[i][1][k] (u64, [n][2][ell]), then the 2*ell transforms of
+ * fusion.py:364-368 and the two ell-term products of :369-370 (fz_matvec).  row_seeds[i][0][*] = s, row_seeds[i][1][*] = s + 1 reproduces
+ * keygen(params, s) without using the fact that a seeded key has identical rows.  sk_l, sk_r: [n][ell][d] (required), vk_l, vk_r: [n][d]. */
+size_t fz_keygen_rows_workspace(const fz_ctx* ctx, size_t n);
+int fz_keygen_rows(fz_ctx* ctx, const int32_t* A, const uint64_t* row_seeds, size_t n, int32_t* sk_l, int32_t* sk_r, int32_t* vk_l, int32_t* vk_r, void* ws,
+                   size_t ws_bytes, void* stream);
 /* keygen (fusion.py:338-373) + sign (fusion.py:534-557) of n one-time keys in one call: key i comes from seeds[i] and signs
  * the message bytes msgs[offs[i]..offs[i+1]) (device memory).  vk_l / vk_r: [n][d], sig: [n][ell][d]. */
 size_t fz_keygen_sign_workspace(const fz_ctx* ctx, size_t n);

@@ -128,15 +128,27 @@ def test_single_aggregate_sharded_world1(engines, oracle):
     agg = parallel.aggregate_one_sharded(eng, vk_l, vk_r, msgs, sigs)
     want = oracle.aggregate(256, host(vk_l), host(vk_r), msgs, host(sigs))
     assert np.array_equal(host(agg[0]), want)
+    # the sharded verification of one aggregate (world size 1 here; world size 2 runs on gloo in tests/test_parallel_cpu.py,
+    # world sizes 2-8 on NCCL in bench.py / tools/multi_gpu_check.py)
+    assert host(parallel.verify_one_sharded(eng, vk_l, vk_r, msgs, agg)).tolist() == [0]
+    assert host(parallel.verify_one_sharded(eng, vk_l, vk_r, msgs, agg)).tolist() == host(eng.verify(vk_l, vk_r, msgs, agg, [n])).tolist()
+    bad = agg.clone()
+    bad[0, 3, 9] -= 1
+    assert host(parallel.verify_one_sharded(eng, vk_l, vk_r, msgs, bad)).tolist() == [3]
+    with pytest.raises(ValueError, match="equal"):
+        parallel.verify_one_sharded(eng, vk_l, vk_r, msgs[:-1], agg)
 
 
-def test_capacity_aggregate_properties(oracle):
-    """BASELINE config[3] at full size (N = 2818 @256): aggregate and verify one capacity-sized aggregate; properties:
+@pytest.mark.parametrize("secpar", [256, 128])
+def test_capacity_aggregate_properties(oracle, secpar):
+    """BASELINE config[3] at full size (N = 2818 @256, N = 1796 @128 -- at 128 the coefficient decoder of fusion.py:594-629 never runs out of
+    bytes, the other branch of quirk Q4): aggregate and verify one capacity-sized aggregate, bit-exact against the oracle; properties:
     verify accepts, a tampered copy is rejected, and aggregation is the alpha-weighted sum (linearity in the signatures)."""
     from fusion_cryptography_b200.batch import Engine
 
-    eng = Engine(256, seed=42)
+    eng = Engine(secpar, seed=42)
     n = eng.ctx.capacity
+    assert n == {256: 2818, 128: 1796}[secpar]
     seeds = (10**6 + 2 * np.arange(n)).astype(np.uint64)
     msgs = [f"msg-{i:07d}".encode() for i in range(n)]
     vk_l, vk_r, sigs = eng.keygen_sign(seeds, msgs, chunk=1024)
@@ -144,9 +156,9 @@ def test_capacity_aggregate_properties(oracle):
     assert host(eng.verify(vk_l, vk_r, msgs, agg, [n])).tolist() == [0]
     # bit-exact against the oracle at full capacity (one SHAKE256 over 26.8 MB of repr text, 11.2 MB squeezed), and the oracle's verify
     oracle.set_threads(oracle.max_threads())
-    want = oracle.aggregate(256, host(vk_l), host(vk_r), msgs, host(sigs))
+    want = oracle.aggregate(secpar, host(vk_l), host(vk_r), msgs, host(sigs))
     assert np.array_equal(host(agg[0]), want)
-    assert oracle.verify(256, host(eng.A), host(vk_l), host(vk_r), msgs, want) == 0
+    assert oracle.verify(secpar, host(eng.A), host(vk_l), host(vk_r), msgs, want) == 0
     bad = agg.clone()
     bad[0, 5, 7] += 1
     assert host(eng.verify(vk_l, vk_r, msgs, bad, [n])).tolist() == [3]
@@ -157,3 +169,82 @@ def test_capacity_aggregate_properties(oracle):
     # one more key than the capacity is an argument error (fusion.py:686-687)
     with pytest.raises(ValueError, match="Too many keys"):
         eng.verify(vk_l, vk_r, msgs + [b"x"], agg, [n + 1])
+
+
+@pytest.mark.parametrize("secpar", [128, 256])
+def test_norm_bound_rejection_in_a_batch(engines, oracle, secpar):
+    """fusion.py:722-725 through Engine.verify on a batch: an aggregate whose image equals the target but whose coefficient norm exceeds
+    beta_vf is rejected with code 4 ("Norm of aggregate signature too large."), its neighbours in the batch are unaffected.
+    A kernel vector of A (A . k = 0) with a huge coefficient is added to a valid aggregate: with all columns of A equal (quirk Q1),
+    k = (+v, -v, 0, ...) for any polynomial v is one."""
+    eng = engines[secpar]
+    ctx, d, ell = eng.ctx, eng.d, eng.ell
+    n, na = 6, 3
+    seeds = (5 * 10**6 + 2 * np.arange(n)).astype(np.uint64)
+    msgs = [f"nb-{i}".encode() for i in range(n)] * na
+    vk_l, vk_r, sigs = eng.keygen_sign(seeds, msgs[:n])
+    sel = torch.arange(n, dtype=torch.int32).repeat(na)
+    aggs = eng.aggregate(vk_l, vk_r, msgs, sigs, [n] * na, sel=sel, sig_sel=sel)
+    assert host(eng.verify(vk_l, vk_r, msgs, aggs, [n] * na, sel=sel)).tolist() == [0, 0, 0]
+    # v: coefficient polynomial with one entry just above beta_vf / 2 in two rows -> after adding, row 0 has a coefficient above beta_vf
+    beta = oracle.param(secpar, "beta_vf")
+    v = np.zeros((1, d), dtype=np.int32)
+    v[0, 0] = H - 7                                     # far above beta_vf (= q / 4)
+    v_hat = ctx.ntt_fwd(torch.from_numpy(v).cuda())[0]
+    bad = aggs.clone()
+    bad[1, 0] = ctx.pointwise_add(bad[1, 0].contiguous(), v_hat)
+    neg = ((-(v_hat.to(torch.int64)) + H) % Q - H).to(torch.int32)
+    bad[1, 1] = ctx.pointwise_add(bad[1, 1].contiguous(), neg)
+    codes = host(eng.verify(vk_l, vk_r, msgs, bad, [n] * na, sel=sel)).tolist()
+    assert codes == [0, 4, 0], codes
+    hv, hr = host(vk_l), host(vk_r)
+    assert oracle.verify(secpar, host(eng.A), hv, hr, msgs[:n], host(bad[1])) == 4
+    coef = oracle.ntt_inv(secpar, host(bad[1]))
+    assert int(np.abs(coef.astype(np.int64)).max()) > beta
+
+
+@pytest.mark.parametrize("secpar", [128, 256])
+def test_general_row_keygen_sign(engines, oracle, secpar):
+    """fz_keygen_rows / Engine.keygen_sign_rows: the general ell-row keygen + sign (2*ell generators, 2*ell transforms, ell-term products; nothing
+    of quirk Q1): (i) against vectors the unmodified reference produced row by row (tests/golden/make_rows_golden.py), (ii) against the oracle on
+    random row seeds, chunked with a ragged last chunk, (iii) with row seeds (s, s + 1) it IS keygen(params, s), (iv) the sign relation."""
+    import os
+
+    eng = engines[secpar]
+    ctx, ell, d = eng.ctx, eng.ell, eng.d
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rows_golden.npz")))
+    seeds = g[f"row_seeds_{secpar}"]
+    msgs = [str(m).encode() for m in g[f"msgs_{secpar}"]]
+    vk_l, vk_r, sigs = eng.keygen_sign_rows(seeds, msgs)
+    assert np.array_equal(host(vk_l), g[f"vk_l_{secpar}"]) and np.array_equal(host(vk_r), g[f"vk_r_{secpar}"])
+    assert np.array_equal(host(sigs), g[f"sig_{secpar}"])
+    # (ii) random row seeds, 7 keys in chunks of 3
+    rng = np.random.default_rng(99 + secpar)
+    n = 7
+    rs = rng.integers(0, 2**63, size=(n, 2, ell), dtype=np.uint64)
+    rs[1, 0, :3] = [0, 1, 2**32 - 1]
+    m2 = [f"general-{i}".encode() for i in range(n)]
+    vl2, vr2, s2 = eng.keygen_sign_rows(rs, m2, chunk=3)
+    A = host(eng.A)
+    oracle.set_threads(oracle.max_threads())
+    for i in range(n):
+        sk = [oracle.ntt_fwd(secpar, np.stack([oracle.sample_coef_poly(secpar, int(rs[i, side, k])) for k in range(ell)])) for side in range(2)]
+        ovl, ovr = oracle.matvec(secpar, A, sk[0][None])[0], oracle.matvec(secpar, A, sk[1][None])[0]
+        assert np.array_equal(host(vl2[i]), ovl) and np.array_equal(host(vr2[i]), ovr), i
+        assert np.array_equal(host(s2[i]), oracle.sign(secpar, sk[0], sk[1], ovl, ovr, m2[i])), i
+    kb = eng.keygen_rows(rs[:2])
+    assert kb.sk_l.shape == (2, ell, d) and not torch.equal(kb.sk_l[0, 0], kb.sk_l[0, 1])      # rows really differ
+    # (iii) all rows of side 0 seeded s, of side 1 seeded s + 1: the reference's keygen(params, s), the long way round
+    s = np.array([10**6, 10**6 + 2], dtype=np.uint64)
+    rs3 = np.stack([np.repeat(s[:, None], ell, 1), np.repeat(s[:, None] + 1, ell, 1)], axis=1)
+    k3 = eng.keygen_rows(rs3)
+    kq = eng.keygen(s, want_sk=True)
+    assert torch.equal(k3.vk_l, kq.vk_l) and torch.equal(k3.vk_r, kq.vk_r) and torch.equal(k3.sk_l, kq.sk_l) and torch.equal(k3.sk_r, kq.sk_r)
+    # (iv) A . z == vk_l * c + vk_r  (reference tests/test_fusion.py:694-731)
+    c = eng.challenges(vl2, vr2, m2)
+    assert torch.equal(ctx.matvec(eng.A, s2), ctx.pointwise_muladd(vl2, c, vr2))
+    # general-row signatures aggregate and verify like any others
+    agg = eng.aggregate(vl2, vr2, m2, s2, [n])
+    assert host(eng.verify(vl2, vr2, m2, agg, [n])).tolist() == [0]
+    with pytest.raises(ValueError):
+        ctx.keygen_rows(eng.A, rs[:, :, :-1])

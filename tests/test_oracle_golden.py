@@ -222,3 +222,22 @@ def test_ring_oracle_matches_reference(ring_golden, oracle):
         x = np.random.default_rng(secpar).integers(-(2**31), 2**31, size=(5, d)).astype(np.int32)
         assert np.array_equal(oracle.ring_ntt_fwd(2147465729, tw, x), oracle.ntt_fwd(secpar, x))
         assert np.array_equal(oracle.ring_ntt_inv(2147465729, itw, x), oracle.ntt_inv(secpar, x))
+
+
+@pytest.mark.parametrize("secpar", [128, 256])
+def test_general_row_keygen_sign_golden(oracle, secpar):
+    """The general ell-row keygen + sign (every secret-key row from its own sampler seed; tests/golden/make_rows_golden.py drove the
+    unmodified reference's sampler, transform(), GeneralMatrix product and sign()): the oracle's per-row restatement reproduces it."""
+    import os
+
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rows_golden.npz")))
+    A = oracle.setup_A(secpar, 42)
+    seeds = g[f"row_seeds_{secpar}"]
+    ell = oracle.param(secpar, "ell")
+    for i in range(seeds.shape[0]):
+        sk = [oracle.ntt_fwd(secpar, np.stack([oracle.sample_coef_poly(secpar, int(seeds[i, side, k])) for k in range(ell)])) for side in range(2)]
+        vk_l = oracle.matvec(secpar, A, sk[0][None])[0]
+        vk_r = oracle.matvec(secpar, A, sk[1][None])[0]
+        assert np.array_equal(vk_l, g[f"vk_l_{secpar}"][i]) and np.array_equal(vk_r, g[f"vk_r_{secpar}"][i])
+        sig = oracle.sign(secpar, sk[0], sk[1], vk_l, vk_r, str(g[f"msgs_{secpar}"][i]).encode())
+        assert np.array_equal(sig, g[f"sig_{secpar}"][i])

@@ -82,3 +82,106 @@ def test_partial_aggregate_reduce_world2(tmp_path, secpar, n):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, secpar, n, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0.npy") and os.path.exists(tmp_path / "ok1.npy")
+
+
+class _OracleCtx:
+    """Host stand-in for native.Context in the gloo tests: every kernel call of the two sharded single-aggregate paths is answered by the CPU
+    oracle (numpy), so that the N > 1 HOST logic (slicing, gathers, folds) is what these tests exercise.  "Digests" are indices into the
+    message list (the oracle hashes messages itself)."""
+
+    def __init__(self, secpar, A, msgs):
+        from oracle import oracle as orc
+
+        self.orc, self.secpar, self.A, self.msgs = orc, secpar, A, msgs
+        self.d, self.ell, self.capacity, self.device = orc.param(secpar, "d"), orc.param(secpar, "ell"), orc.param(secpar, "capacity"), torch.device("cpu")
+
+    def hash_msg(self, msgs):
+        return torch.arange(len(msgs), dtype=torch.int64).reshape(-1, 1)
+
+    def sort_keys(self, vk_l, vk_r, counts):
+        return torch.from_numpy(self.orc.sort_by_repr(self.secpar, vk_l.numpy(), vk_r.numpy()).astype(np.int64))
+
+    def gather_sorted(self, vk_l, vk_r, dg, perm):
+        return vk_l[perm].contiguous(), vk_r[perm].contiguous(), dg[perm].contiguous()
+
+    def hash_ch(self, vl, vr, dg):
+        out = [self.orc.hash_ch(self.secpar, vl[i].numpy(), vr[i].numpy(), self.msgs[int(dg[i, 0])]) for i in range(vl.shape[0])]
+        return torch.from_numpy(np.stack(out)) if out else torch.zeros((0, self.d), dtype=torch.int32)
+
+    def hash_ag_fast(self, vl_s, vr_s, dg_s, c_s, counts):
+        alpha, ch = self.orc.hash_ag(self.secpar, vl_s.numpy(), vr_s.numpy(), [self.msgs[int(i)] for i in dg_s[:, 0]], want_ch=True)
+        assert np.array_equal(ch, c_s.numpy()), "gathered challenges differ from the oracle's"
+        return torch.from_numpy(alpha)
+
+    @staticmethod
+    def _cent(x):
+        return (((x + H) % Q) - H).astype(np.int32)
+
+    def _mul(self, a, b):
+        return self.orc.pointwise_mul(np.ascontiguousarray(a), np.ascontiguousarray(b)).astype(np.int64)
+
+    def aggregate_sum(self, sigs, rows, alpha, counts):
+        acc = np.zeros((self.ell, self.d), dtype=np.int64)
+        for p, r in enumerate(rows.tolist()):
+            acc += self._mul(sigs[r].numpy(), np.broadcast_to(alpha[p].numpy(), (self.ell, self.d)))
+        return torch.from_numpy(self._cent(acc)).reshape(1, self.ell, self.d)
+
+    def fold_partials(self, parts, n_parts, n_aggs):
+        return _oracle_fold(parts, n_parts, n_aggs)
+
+    def verify_target(self, vl, vr, c, alpha, win_off, n_aggs):
+        acc = np.zeros(self.d, dtype=np.int64)
+        for i in range(vl.shape[0]):
+            t = self._cent(self._mul(vl[i].numpy(), c[i].numpy()) + vr[i].numpy())
+            acc += self._mul(t, alpha[i].numpy())
+        return torch.from_numpy(self._cent(acc)).reshape(1, self.d)
+
+    def pointwise_add(self, a, b):
+        return torch.from_numpy(self._cent(a.numpy().astype(np.int64) + b.numpy()))
+
+    def verify_finish(self, A, target, agg):
+        obs = self.orc.matvec(self.secpar, A, agg.numpy().reshape(1, self.ell, self.d))[0]
+        if not np.array_equal(obs, target.numpy().reshape(-1)):
+            return torch.tensor([3], dtype=torch.uint8)
+        coef = self.orc.ntt_inv(self.secpar, agg.numpy().reshape(self.ell, self.d))
+        return torch.tensor([4 if int(np.abs(coef.astype(np.int64)).max()) > self.orc.param(self.secpar, "beta_vf") else 0], dtype=torch.uint8)
+
+
+class _Eng:
+    def __init__(self, ctx):
+        self.ctx, self.A = ctx, ctx.A
+
+
+def _one_aggregate_worker(rank: int, world: int, port: int, secpar: int, n: int, out_dir: str):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+
+    A = orc.setup_A(secpar, 42)
+    seeds = (3 * 10**6 + 2 * np.arange(n)).astype(np.uint64)
+    msgs = [f"shard-{i}".encode() for i in range(n)]
+    sk_l, sk_r, vl, vr = orc.keygen_batch(secpar, A, seeds)
+    sigs = orc.sign_batch(secpar, sk_l, sk_r, vl, vr, msgs)
+    want = orc.aggregate(secpar, vl, vr, msgs, sigs)
+    eng = _Eng(_OracleCtx(secpar, A, msgs))
+    lo, hi = parallel.shard_bounds(n, rank, world)
+    t_vl, t_vr = torch.from_numpy(vl), torch.from_numpy(vr)
+    agg = parallel.aggregate_one_sharded(eng, t_vl, t_vr, msgs, torch.from_numpy(sigs[lo:hi].copy()))
+    assert np.array_equal(agg[0].numpy(), want), "sharded aggregate differs from the oracle's aggregate"
+    code = parallel.verify_one_sharded(eng, t_vl, t_vr, msgs, agg)
+    assert code.tolist() == [0] and orc.verify(secpar, A, vl, vr, msgs, want) == 0
+    bad = agg.clone()
+    bad[0, 1, 2] += 1
+    assert parallel.verify_one_sharded(eng, t_vl, t_vr, msgs, bad).tolist() == [3]
+    np.save(os.path.join(out_dir, f"one{rank}.npy"), np.array([1]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("secpar,n", [(128, 5), (256, 3)])
+def test_one_aggregate_sharded_world2(tmp_path, secpar, n):
+    """aggregate and verify of ONE aggregate whose signers are split over two ranks."""
+    port = _free_port()
+    mp.spawn(_one_aggregate_worker, args=(2, port, secpar, n, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "one0.npy") and os.path.exists(tmp_path / "one1.npy")
