@@ -111,6 +111,93 @@ class Engine:
             ctx.sign_mac(sk_l, sk_r, c_hat, out=sigs[lo:hi] if keep_sigs else sigs[: hi - lo])
         return vk_l, vk_r, (sigs if keep_sigs else None)
 
+    # ------------------------------------------------------------------ host-buffer pipelines (what a caller with data in host memory runs)
+    def keygen_sign_host(self, seeds_h: torch.Tensor, msg_buf_h: torch.Tensor, msg_offs_h: torch.Tensor, sink, chunk: int = 16384) -> dict:
+        """keygen + sign (fusion.py:338-373, 534-557) END TO END through host memory: seeds_h (int64 view of the u64 seeds), the packed messages
+        (msg_buf_h uint8, msg_offs_h int64 [n + 1]) live in (pinned) host memory; every chunk's verification keys and signatures are copied back
+        into pinned host staging buffers and handed to ``sink(lo, hi, vk_l_h, vk_r_h, sig_h)`` (views valid until the next call but one).
+        Compute of chunk k overlaps the device-to-host copy of chunk k - 1 (two device and two host slots, one copy stream).
+        Returns the byte counts moved each way."""
+        ctx, dev = self.ctx, self.ctx.device
+        n = int(seeds_h.numel())
+        c = max(1, min(chunk, n))
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy", None) is None:
+            self._copy = torch.cuda.Stream(device=dev)
+        copy = self._copy
+        key = ("ksh", c)
+        if getattr(self, "_ksh", None) is None or self._ksh[0] != key:
+            slots = []
+            for _ in range(2):
+                slots.append({
+                    "vk_l": torch.empty((c, self.d), dtype=torch.int32, device=dev), "vk_r": torch.empty((c, self.d), dtype=torch.int32, device=dev),
+                    "sig": torch.empty((c, self.ell, self.d), dtype=torch.int32, device=dev),
+                    "h_vk_l": torch.empty((c, self.d), dtype=torch.int32, pin_memory=True), "h_vk_r": torch.empty((c, self.d), dtype=torch.int32, pin_memory=True),
+                    "h_sig": torch.empty((c, self.ell, self.d), dtype=torch.int32, pin_memory=True)})
+            self._ksh = (key, slots)
+        slots = self._ksh[1]
+        total_bytes = int(msg_offs_h[-1].item())
+        d_buf = torch.empty(total_bytes + 1, dtype=torch.uint8, device=dev)
+        d_offs = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        d_seeds = torch.empty(n, dtype=torch.int64, device=dev)
+        pm = native.PackedMessages(d_buf, d_offs)
+        copied = [None, None]
+        pending = None
+        h2d = d2h = 0
+        for k, lo in enumerate(range(0, n, c)):
+            hi = min(n, lo + c)
+            sl = slots[k & 1]
+            b0, b1 = int(msg_offs_h[lo].item()), int(msg_offs_h[hi].item())
+            d_seeds[lo:hi].copy_(seeds_h[lo:hi], non_blocking=True)
+            d_offs[lo:hi + 1].copy_(msg_offs_h[lo:hi + 1], non_blocking=True)
+            if b1 > b0:
+                d_buf[b0:b1].copy_(msg_buf_h[b0:b1], non_blocking=True)
+            h2d += (hi - lo) * 16 + 8 + (b1 - b0)
+            if copied[k & 1] is not None:
+                main.wait_event(copied[k & 1])       # the slot's previous chunk has left the device
+            m = hi - lo
+            ctx.keygen_sign(self.A, d_seeds[lo:hi], pm[lo:hi], sl["vk_l"][:m], sl["vk_r"][:m], sl["sig"][:m])
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(copy):
+                copy.wait_event(done)
+                sl["h_vk_l"][:m].copy_(sl["vk_l"][:m], non_blocking=True)
+                sl["h_vk_r"][:m].copy_(sl["vk_r"][:m], non_blocking=True)
+                sl["h_sig"][:m].copy_(sl["sig"][:m], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            copied[k & 1] = ev
+            d2h += m * (2 + self.ell) * self.d * 4
+            if pending is not None:
+                pending[0].synchronize()
+                sink(*pending[1])
+            pending = (ev, (lo, hi, sl["h_vk_l"][:m], sl["h_vk_r"][:m], sl["h_sig"][:m]))
+        if pending is not None:
+            pending[0].synchronize()
+            sink(*pending[1])
+        main.wait_stream(copy)
+        return {"h2d_bytes": h2d, "d2h_bytes": d2h}
+
+    def verify_host(self, vk_l_h: torch.Tensor, vk_r_h: torch.Tensor, msgs: Sequence[bytes], sel_h: torch.Tensor, msg_sel_h: torch.Tensor,
+                    aggs_h: torch.Tensor, counts: Sequence[int], codes_h: torch.Tensor) -> dict:
+        """verify (fusion.py:680-728) of a batch of aggregates END TO END through host memory: the key pool (vk_l_h, vk_r_h: [pool, d]), the message
+        pool, the per-position key index sel_h and message index msg_sel_h (int32 [positions]) and the aggregate signatures aggs_h
+        ([n_aggs, ell, d]) are copied to the device, codes_h (uint8 [n_aggs], pinned) receives the result.  Returns the byte counts."""
+        ctx, dev = self.ctx, self.ctx.device
+        vk_l = vk_l_h.to(dev, non_blocking=True)
+        vk_r = vk_r_h.to(dev, non_blocking=True)
+        sel = sel_h.to(dev, non_blocking=True)
+        msel = msg_sel_h.to(dev, non_blocking=True)
+        aggs = aggs_h.to(dev, non_blocking=True)
+        pm = ctx.pack_messages(list(msgs)) if not isinstance(msgs, native.PackedMessages) else msgs
+        dg = ctx.hash_msg(pm).index_select(0, msel.long()).contiguous()
+        codes = self.verify(vk_l, vk_r, None, aggs, counts, sel=sel, digests=dg)
+        codes_h.copy_(codes, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        nbytes = lambda t: t.numel() * t.element_size()
+        return {"h2d_bytes": nbytes(vk_l_h) + nbytes(vk_r_h) + nbytes(sel_h) + nbytes(msg_sel_h) + nbytes(aggs_h) + int(pm.buf.numel()) + int(pm.offs.numel()) * 8,
+                "d2h_bytes": nbytes(codes_h)}
+
     # ------------------------------------------------------------------ aggregate / verify
     # The aggregation hash is one serial sponge per aggregate (fusion.py:591), so a batch is hashed WINDOW BY WINDOW over
     # the sorted signer positions: window w holds positions [w*P, (w+1)*P) of every aggregate.  All chains advance
