@@ -265,16 +265,17 @@ int fz_format_text(fz_ctx* ctx, int mode, const int32_t* vk_l, const int32_t* vk
     return launch_format(ctx, mode, vk_l, vk_r, digests, c_hat, n, out, mode == 0 ? M1_STRIDE : PIECE_STRIDE, out_len, (cudaStream_t)stream);
 }
 
-int fz_decode_poly(fz_ctx* ctx, const uint8_t* bytes, size_t stride, size_t blen, size_t n, int log2_bias, int norm_bound, int weight_bound,
+int fz_decode_poly(fz_ctx* ctx, const uint8_t* bytes, size_t stride, size_t blen, size_t n, long long log2_bias, long long norm_bound, int weight_bound,
                    int32_t* coef_out, void* stream) {
     FZ_REQUIRE(ctx && (n == 0 || (bytes && coef_out)), "fz_decode_poly: NULL argument");
     FZ_REQUIRE(weight_bound >= 0 && weight_bound <= 256, "fz_decode_poly: weight_bound must be in [0, 256]");
+    FZ_REQUIRE(log2_bias > -(1LL << 20) && log2_bias < (1LL << 20), "fz_decode_poly: log2_bias out of range");
     long long bound = norm_bound < 1073732864LL ? norm_bound : 1073732864LL;   // fusion.py:432
     if (bound < 1) bound = 1;
     int lb = 0;
     while ((1LL << (lb + 1)) <= bound) ++lb;
     const int frac = ((1LL << lb) != bound);
-    const int bpc = ceil_div(lb + frac + 1 + log2_bias, 8), bpi = ceil_div(ilog2(ctx->d) + log2_bias, 8);   // fusion.py:433-434
+    const int bpc = ceil_div(lb + frac + 1 + (int)log2_bias, 8), bpi = ceil_div(ilog2(ctx->d) + (int)log2_bias, 8);   // fusion.py:433-434
     const size_t total = (size_t)ceil_div(weight_bound, 8) + (size_t)(bpc + bpi) * weight_bound;             // fusion.py:435-438
     if (blen < total) {
         set_error("Too few bytes to decode polynomial. Expected %zu but got %zu", total, blen);  // fusion.py:439-442

@@ -422,6 +422,23 @@ def _patched() -> bool:
     return any(g[k] is not v for k, v in _PRISTINE.items())
 
 
+def _device_hashable(params: Params, keys) -> bool:
+    """False when some verification key holds a HOST list with a value outside the canonical centred range [-(q//2), q//2] (a hand-made key with
+    v + q, say): the reference hashes and sorts str(key) as it stands, while the device formatter prints the canonical residue, so such keys take
+    the text-level helpers -- as objects that are no verification keys do.  (Device-resident values are canonical by construction.)"""
+    h = params.modulus // 2
+    for k in keys:
+        if not isinstance(k, OneTimeVerificationKey):
+            continue
+        for gm in (k.left_vk_hat, k.right_vk_hat):
+            for row in getattr(gm, "matrix", ()):
+                for e in row:
+                    vals = getattr(e, "_vals", None)
+                    if vals is not None and any(type(v) is not int or v < -h or v > h for v in vals):
+                        return False
+    return True
+
+
 def _vk_tensors(params: Params, keys: List[OneTimeVerificationKey]):
     """([n, d], [n, d]) device tensors of the keys' left / right polynomials."""
     import torch
@@ -447,7 +464,7 @@ def sign(params: Params, key: OneTimeKeyTuple, message: str) -> Signature:
     sk, vk = key
     ctx = params._ctx()
     d, ell = params.degree, params.num_rows_sk
-    if _patched():
+    if _patched() or not _device_hashable(params, [vk]):
         pre_hashed_message = hash_message_to_int(params=params, message=message)
         b = hash_vk_and_int_to_bytes(params=params, key=vk, i=pre_hashed_message, n=_challenge_bytes(params))
         c_hat_t = parse_challenge(params=params, b=b)._tensor().reshape(1, d)
@@ -501,7 +518,7 @@ def hash_ag(params: Params, keys: List[OneTimeVerificationKey], messages: List[s
     """Reference :632-652 (keys are hashed in the order given; aggregate / verify sort first)."""
     # the reference only ever takes str(key) here, so ANY object works as a key (its own KAT generator passes (sk, vk) tuples,
     # KATs/generate_KAT_values.py:120-133): everything that is not a plain verification key goes through the text-level helpers
-    if _patched() or len(keys) != len(messages) or not all(isinstance(k, OneTimeVerificationKey) for k in keys):
+    if _patched() or len(keys) != len(messages) or not all(isinstance(k, OneTimeVerificationKey) for k in keys) or not _device_hashable(params, keys):
         # (unequal lengths: the reference zips the per-signer lists but sizes the XOF output by len(keys), :636-647)
         pre = [hash_message_to_int(params=params, message=m) for _, m in zip(keys, messages)]
         challs = [hash_ch(params=params, key=k, message=m) for k, m in zip(keys, messages)]
@@ -530,7 +547,7 @@ def aggregate(params: Params, keys: List[OneTimeVerificationKey], messages: List
     keys, messages, signatures = keys[:n], messages[:n], signatures[:n]
     ctx = params._ctx()
     d, ell = params.degree, params.num_rows_sk
-    if _patched() or not all(isinstance(k, OneTimeVerificationKey) for k in keys):   # like hash_ag: the reference only sorts and hashes str(key) here
+    if _patched() or not all(isinstance(k, OneTimeVerificationKey) for k in keys) or not _device_hashable(params, keys):   # like hash_ag: the reference only sorts and hashes str(key) here
         order = sorted(range(n), key=lambda i: str(keys[i]))
         alphas = hash_ag(params=params, keys=[keys[i] for i in order], messages=[messages[i] for i in order])
         import torch
@@ -561,7 +578,7 @@ def verify(params: Params, keys: List[OneTimeVerificationKey], messages: List[st
         raise IndexError("list index out of range")  # the reference indexes sorted_vks[0]
     ctx = params._ctx()
     d, ell = params.degree, params.num_rows_sk
-    if _patched():
+    if _patched() or not _device_hashable(params, keys):
         import torch
 
         order = sorted(range(n), key=lambda i: str(keys[i]))

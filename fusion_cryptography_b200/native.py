@@ -23,6 +23,36 @@ class FusionB200Error(RuntimeError):
     pass
 
 
+_CTYPES = {"int": C.c_int, "size_t": C.c_size_t, "uint32_t": C.c_uint32, "uint64_t": C.c_uint64, "int32_t": C.c_int32, "long long": C.c_longlong}
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fusion_b200.h")
+
+
+def parse_prototypes(header_text: str):
+    """{name: (restype, [argtypes])} of every fz_* prototype in include/fusion_b200.h: pointers (and handles) become c_void_p, `const char*` c_char_p,
+    scalars their exact C width -- so that a Python int that does not fit its C parameter raises instead of being truncated silently."""
+    import re
+
+    text = re.sub(r"/\*.*?\*/", " ", header_text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"(?:^|\n)\s*([A-Za-z_][\w \*]*?)\b(fz_\w+)\s*\(([^;{}]*?)\)\s*;", text):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+
+        def ctype(decl: str):
+            decl = decl.strip()
+            if decl in ("void", ""):
+                return None
+            if "*" in decl:
+                base = decl.replace("const", "").split("*")[0].strip()
+                return C.c_char_p if base == "char" else C.c_void_p
+            t = decl.replace("const", "").strip()
+            t = " ".join(t.split()[:-1]) if len(t.split()) > 1 and t.split()[-1] not in ("long", "int") else t   # drop the parameter name
+            return _CTYPES[t]
+
+        argtypes = [ctype(a) for a in args.split(",")] if args and args != "void" else []
+        out[name] = (C.c_char_p if ("char" in ret and "*" in ret) else (C.c_void_p if "*" in ret else _CTYPES[ret]), [a for a in argtypes if a is not None])
+    return out
+
+
 def load_library():
     """Loads the CUDA library; raises (never falls back) when it is missing."""
     global _lib
@@ -36,6 +66,11 @@ def load_library():
     lib.fz_last_error.restype = C.c_char_p
     lib.fz_param.restype = C.c_longlong
     lib.fz_param.argtypes = [C.c_void_p, C.c_char_p]
+    # argument and result types of every entry point, read from the header the library was built against
+    if os.path.exists(HEADER_PATH):
+        for name, (restype, argtypes) in parse_prototypes(open(HEADER_PATH).read()).items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = restype, argtypes
     lib.fz_init.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.fz_destroy.argtypes = [C.c_void_p]
     _lib = lib
@@ -452,7 +487,11 @@ def decode_poly(self, data: torch.Tensor, blen: int, log2_bias: int, norm_bound:
     data = self._u8(data)
     n, stride = data.shape
     out = torch.empty((n, self.d), dtype=torch.int32, device=self.device)
-    rc = self.lib.fz_decode_poly(self._h, _ptr(data), C.c_size_t(stride), C.c_size_t(blen), C.c_size_t(n), C.c_int(log2_bias), C.c_int(norm_bound),
+    # clamp on the host what the reference clamps (fusion.py:432: bound = max(1, min(modulus // 2, norm_bound))): ctypes truncates silently
+    norm_bound = max(1, min(int(norm_bound), Q // 2))
+    if not -(1 << 20) < int(log2_bias) < (1 << 20):
+        raise ValueError("log2_bias out of range")
+    rc = self.lib.fz_decode_poly(self._h, _ptr(data), C.c_size_t(stride), C.c_size_t(blen), C.c_size_t(n), C.c_longlong(log2_bias), C.c_longlong(norm_bound),
                                  C.c_int(weight_bound), _ptr(out), self._stream())
     if rc == -3:
         raise ValueError(self.lib.fz_last_error().decode())

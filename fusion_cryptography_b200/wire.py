@@ -43,6 +43,8 @@ def _unpack(kind: str, params, blob: bytes) -> torch.Tensor:
 def vk_to_bytes(params, vk) -> bytes:
     """OneTimeVerificationKey -> 12 + 2 * d * 4 bytes (left polynomial, right polynomial)"""
     d = params.degree
+    if not _ff._device_hashable(params, [vk]):   # the format holds canonical centred residues; str() of such a key would not survive the round trip
+        raise ValueError("verification key holds values outside the canonical centred range; the wire format cannot represent its str()")
     return _pack("vk", params.secpar, torch.stack([vk.left_vk_hat._tensor().reshape(d), vk.right_vk_hat._tensor().reshape(d)]))
 
 

@@ -80,7 +80,7 @@ int fz_format_text(fz_ctx* ctx, int mode, const int32_t* vk_l, const int32_t* vk
                    uint8_t* out, uint32_t* out_len, void* stream);
 /* fusion.py:422-481 decode_bytes_to_polynomial_coefficients on n byte strings bytes[i*stride .. +blen); returns -3
  * ("Too few bytes ...", the reference's ValueError) when blen is too small.  coef_out: [n][d]. */
-int fz_decode_poly(fz_ctx* ctx, const uint8_t* bytes, size_t stride, size_t blen, size_t n, int log2_bias, int norm_bound, int weight_bound,
+int fz_decode_poly(fz_ctx* ctx, const uint8_t* bytes, size_t stride, size_t blen, size_t n, long long log2_bias, long long norm_bound, int weight_bound,
                    int32_t* coef_out, void* stream);
 /* fusion.py:511-531 hash_ch (prehash digests from fz_hash_msg): c_hat_out: [n][d] */
 size_t fz_hash_ch_workspace(const fz_ctx* ctx, size_t n);

@@ -214,6 +214,30 @@ case("handmade_sign", lambda: bsig)
 bagg = ff.aggregate(p128, [bk[1]], ["big"], [bsig])
 case("verify_norm_too_large", lambda: ff.verify(p128, [bk[1]], ["big"], bagg))
 case("verify_mixed_norm", lambda: ff.verify(p128, [bk[1], k128[1]], ["big", "m"], ff.aggregate(p128, [bk[1], k128[1]], ["big", "m"], [bsig, ff.sign(p128, k128, "m")])))
+
+
+def shifted_key(p, vk):
+    """the same key with non-canonical representatives: some values + q, some - q, one just above q // 2 (str(key), which the reference sorts and
+    hashes, differs from the canonical key's; the values agree modulo q)"""
+    def shift(poly):
+        v = list(poly.values)
+        v[0], v[1], v[2] = v[0] + p.modulus, v[1] - p.modulus, (p.modulus // 2 + 1 if v[2] == -(p.modulus // 2) else v[2])
+        return Ntt(modulus=poly.modulus, degree=poly.degree, root=poly.root, inv_root=poly.inv_root, root_order=poly.root_order, values=v)
+    return ff.OneTimeVerificationKey(left_vk_hat=GeneralMatrix(matrix=[[shift(vk.left_vk_hat.matrix[0][0])]]),
+                                     right_vk_hat=GeneralMatrix(matrix=[[shift(vk.right_vk_hat.matrix[0][0])]]))
+
+
+sk128 = shifted_key(p128, k128[1])
+case("noncanonical_key_str", lambda: sk128)
+case("noncanonical_hash_ch", lambda: ff.hash_ch(p128, sk128, "m"))
+nsig = ff.sign(p128, (k128[0], sk128), "m")
+case("noncanonical_sign", lambda: nsig)
+case("noncanonical_hash_ag", lambda: ff.hash_ag(p128, [sk128, k128[1]], ["m", "n"]))
+nsig2 = ff.sign(p128, k128, "n")
+nagg = ff.aggregate(p128, [sk128, k128[1]], ["m", "n"], [nsig, nsig2])
+case("noncanonical_aggregate", lambda: nagg)
+case("noncanonical_verify", lambda: ff.verify(p128, [sk128, k128[1]], ["m", "n"], nagg))
+case("noncanonical_verify_canonical_keys", lambda: ff.verify(p128, [k128[1], k128[1]], ["m", "n"], nagg))
 case("setup_unknown", lambda: sorted(vars(ff.fusion_setup(64, 1))))
 case("setup_none", lambda: len(str(ff.fusion_setup(128, None))) > 1000)
 

@@ -151,3 +151,57 @@ def test_fused_pass_equals_three_kernels(secpar):
     assert torch.equal(inplace, want)
     k = 64
     assert np.array_equal(got[:k].cpu().numpy(), orc.ntt_inv(secpar, orc.pointwise_mul(orc.ntt_fwd(secpar, a[:k]), b[:k])))
+
+
+@pytest.mark.gpu
+def test_fused_pass_full_size_vs_oracle(ctxs, oracle):
+    """The kernel bench.py times, at bench.py's size: fz_ntt_pass over 2^20 secpar-256 polynomials, every coefficient against the oracle's
+    cooley_tukey_ntt -> cent(x * y) -> gentleman_sande_intt (algebra/ntt.py:271-291, polynomials.py:341-385, ntt.py:350-377), bench.py's seeds."""
+    ctx = ctxs[256]
+    n, d = 1 << 20, 256
+    a = np.random.default_rng(0xF0510).integers(-H, H + 1, size=(n, d), dtype=np.int64).astype(np.int32)
+    b = np.random.default_rng(0xF0511).integers(-H, H + 1, size=(n, d), dtype=np.int64).astype(np.int32)
+    got = ctx.ntt_pass(dev(a), dev(b))
+    oracle.set_threads(oracle.max_threads())
+    want = oracle.ntt_inv(256, oracle.pointwise_mul(oracle.ntt_fwd(256, a), b))
+    assert np.array_equal(host(got), want)
+    # the host-buffer entry point of the end-to-end measurement gives the same bits
+    hin, hout = torch.from_numpy(a).pin_memory(), torch.empty((n, d), dtype=torch.int32).pin_memory()
+    ctx.pass_host(hin, dev(b), hout)
+    assert np.array_equal(hout.numpy(), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("secpar", [128, 256])
+@pytest.mark.parametrize("n", [1, 2, 3, 37, 1025])
+def test_scheme_ntt_kernels_stay_inside_their_buffers(ctxs, secpar, n):
+    """compute-sanitizer is not available on this pool, so: every scheme NTT-family kernel writes into the middle of a larger buffer whose
+    head and tail hold guard words; the guards must survive and the payload must equal the result computed in a separate buffer
+    (warp-private tiles, ragged last warp / last CTA of the persistent grids)."""
+    ctx = ctxs[secpar]
+    d, ell = ctx.d, ctx.ell
+    rng = np.random.default_rng(n + secpar)
+    a = dev(rng.integers(-H, H + 1, size=(n, d)).astype(np.int32))
+    b = dev(rng.integers(-H, H + 1, size=(n, d)).astype(np.int32))
+    c = dev(rng.integers(-H, H + 1, size=(n, d)).astype(np.int32))
+    G, GUARD = 4 * d, 0x5A5A5A5A
+
+    def guarded(fn, rows=n):
+        buf = torch.full((G + rows * d + G,), GUARD, dtype=torch.int32, device="cuda")
+        out = buf[G:G + rows * d].view(rows, d)
+        fn(out)
+        assert bool((buf[:G] == GUARD).all()) and bool((buf[G + rows * d:] == GUARD).all()), "a kernel wrote outside its output"
+        return out.clone()
+
+    assert torch.equal(guarded(lambda o: ctx.ntt_fwd(a, out=o)), ctx.ntt_fwd(a))
+    assert torch.equal(guarded(lambda o: ctx.ntt_inv(a, out=o)), ctx.ntt_inv(a))
+    assert torch.equal(guarded(lambda o: ctx.ntt_pass(a, b, out=o)), ctx.ntt_pass(a, b))
+    assert torch.equal(guarded(lambda o: ctx.polymul(a, b, out=o)), ctx.polymul(a, b))
+    assert torch.equal(guarded(lambda o: ctx.pointwise_mul(a, b, out=o)), ctx.pointwise_mul(a, b))
+    assert torch.equal(guarded(lambda o: ctx.pointwise_add(a, b, out=o)), ctx.pointwise_add(a, b))
+    assert torch.equal(guarded(lambda o: ctx.pointwise_muladd(a, b, c, out=o)), ctx.pointwise_muladd(a, b, c))
+    A = dev(rng.integers(-H, H + 1, size=(ell, d)).astype(np.int32))
+    s = dev(rng.integers(-H, H + 1, size=(n, ell, d)).astype(np.int32))
+    r = dev(rng.integers(-H, H + 1, size=(n, ell, d)).astype(np.int32))
+    assert torch.equal(guarded(lambda o: ctx.matvec(A, s, out=o)), ctx.matvec(A, s))
+    assert torch.equal(guarded(lambda o: ctx.sign_mac(s, r, c, out=o.view(n, ell, d)), rows=n * ell).view(n, ell, d), ctx.sign_mac(s, r, c))

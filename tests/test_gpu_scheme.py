@@ -334,3 +334,57 @@ def test_buffered_and_streaming_hash_agree(ctxs, oracle, secpar):
         xof = oracle.hash_vk_and_int_to_bytes(secpar, vl[i], vr[i], bytes(dg[i]), ctx.param("n_ch"))
         want = oracle.ntt_fwd(secpar, oracle.decode_poly(secpar, xof, secpar, 1, ctx.param("omega_ch")))
         assert np.array_equal(out[0][0][i], want)
+
+
+@pytest.mark.parametrize("secpar", [128, 256])
+@pytest.mark.parametrize("impl", [3, 2])
+def test_hash_pipeline_stays_inside_its_byte_buffers(ctxs, secpar, impl):
+    """compute-sanitizer is not available on this pool, so the byte rings and XOF buffers of the ring-fed aggregation hash (fz_hash_ag_text,
+    fz_hash_ag_absorb_ring, fz_hash_ag_squeeze_xof, fz_hash_ag_decode) are carved out of the middle of larger buffers whose head and tail hold
+    guard bytes: the guards must survive, the state records must stay inside their array, and the coefficients must equal the one-shot hash's.
+    Extreme text lengths (all coefficients -(q-1)/2: the longest repr; all zero: the shortest) sit first and last in their aggregates."""
+    ctx = ctxs[secpar]
+    d = ctx.d
+    rng = np.random.default_rng(5 + secpar + impl)
+    counts = [1, 7, 2, 19]
+    n, n_aggs = sum(counts), len(counts)
+    vl = rng.integers(-H, H + 1, size=(n, d)).astype(np.int32)
+    vr = rng.integers(-H, H + 1, size=(n, d)).astype(np.int32)
+    vl[0] = vr[0] = -H
+    vl[-1] = vr[-1] = 0
+    vl[1] = vr[8] = -H
+    dg = rng.integers(0, 256, size=(n, 32)).astype(np.uint8)
+    dg[0] = 255
+    dg[-1] = 0
+    tvl, tvr, tdg = dev(vl), dev(vr), dev(dg, np.uint8)
+    try:
+        ctx.set_option("hash_ag_impl", impl)
+        c = ctx.hash_ch(tvl, tvr, tdg)
+        want = ctx.hash_ag(tvl, tvr, tdg, c, counts)
+        agg_off, n_total, max_keys = ctx._agg_off(counts)
+        agg_of = torch.repeat_interleave(torch.arange(n_aggs, dtype=torch.int32, device="cuda"), torch.tensor(counts, device="cuda"))
+        GB = 4096
+        ring0, cap, text_pos = ctx.hash_ag_ring(n_aggs, max_keys)
+        xof0, xcap = ctx.hash_ag_xof_buffer(n_aggs, max_keys)
+        rbuf = torch.full((GB + ring0.numel() + GB,), 0xA5, dtype=torch.uint8, device="cuda")
+        xbuf = torch.full((GB + xof0.numel() + GB,), 0xA5, dtype=torch.uint8, device="cuda")
+        ring, xof = rbuf[GB:GB + ring0.numel()], xbuf[GB:GB + xof0.numel()]
+        sb = int(ctx.lib.fz_hash_ag_state_bytes(ctx._h))
+        sbuf = torch.full((GB + n_aggs * sb + GB,), 0xA5, dtype=torch.uint8, device="cuda")
+        state = sbuf[GB:GB + n_aggs * sb]
+        ctx._chk(ctx.lib.fz_hash_ag_begin(ctx._h, state.data_ptr(), agg_off.data_ptr(), n_aggs, ctx._stream()))
+        wend = ctx.hash_ag_text(tvl, tvr, tdg, c, agg_off, agg_of, agg_off, n_aggs, n_total, 0, text_pos, ring, cap)
+        ctx.hash_ag_absorb_ring(state, ring, cap, wend, agg_off, n_aggs)
+        bpos = ctx.hash_ag_squeeze_xof(state, agg_off, n_aggs, xof, xcap)
+        obuf = torch.full((GB + n_total * d + GB,), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
+        out = obuf[GB:GB + n_total * d].view(n_total, d)
+        ctx._chk(ctx.lib.fz_hash_ag_decode(ctx._h, xof.data_ptr(), xcap, bpos.data_ptr(), agg_off.data_ptr(), agg_of.data_ptr(), n_total, out.data_ptr(),
+                                           ctx._stream()))
+        torch.cuda.synchronize()
+        for name, buf, size in (("ring", rbuf, ring0.numel()), ("xof", xbuf, xof0.numel()), ("state", sbuf, n_aggs * sb)):
+            assert bool((buf[:GB] == 0xA5).all()) and bool((buf[GB + size:] == 0xA5).all()), f"{name}: a kernel wrote outside its buffer"
+        g = 0x5A5A5A5A
+        assert bool((obuf[:GB] == g).all()) and bool((obuf[GB + n_total * d:] == g).all()), "decode wrote outside its output"
+        assert torch.equal(out, want)
+    finally:
+        ctx.set_option("hash_ag_impl", 0)
