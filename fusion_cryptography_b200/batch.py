@@ -13,8 +13,6 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
-import os
-
 import torch
 
 from . import native
@@ -30,6 +28,17 @@ VERIFY_REASONS = {
 
 
 @dataclass
+class Tuning:
+    """Knobs of the windowed aggregate / verify pipeline (measured defaults; the tests use them to reach every code path with small batches)."""
+    agg_slots: Optional[int] = None   # warp-chains served per time-sliced absorb launch; None = 8 per SM (two per sub-partition)
+    sliced: bool = True               # time-slice the absorb phase for batches a little above agg_slots chains
+    sliced_window_div: int = 2        # sliced mode: windows are this many times shorter (the byte rings hold the backlog of the resting chains)
+    sliced_budget: float = 1.01       # sliced mode: blocks per launch = expected blocks of one window x this
+    sliced_extra_launches: int = 2    # sliced mode: rotating launches after the last window, before the one that closes everything
+    overlap: bool = True              # per-signer work of window w+1 on a side stream beside the sponge chains of window w
+
+
+@dataclass
 class KeyBatch:
     sk_hat: Optional[torch.Tensor]  # [n, 2, d] (None for keys from keygen_rows): the one distinct row of sk_l / sk_r (all ell rows of a seeded key are equal, SURVEY quirk Q1)
     vk_l: torch.Tensor    # [n, d]
@@ -39,8 +48,10 @@ class KeyBatch:
 
 
 class Engine:
-    def __init__(self, secpar: int, seed: Optional[int] = 42, device: Optional[int] = None, A: Optional[torch.Tensor] = None):
+    def __init__(self, secpar: int, seed: Optional[int] = 42, device: Optional[int] = None, A: Optional[torch.Tensor] = None,
+                 tuning: Optional[Tuning] = None):
         self.ctx = native.get_context(secpar, device)
+        self.tuning = tuning if tuning is not None else Tuning()
         self.secpar, self.d, self.ell = secpar, self.ctx.d, self.ctx.ell
         if A is None:
             # fusion.py:273-282: the 1 x ell public matrix, every column sampled with the same seed
@@ -234,13 +245,14 @@ class Engine:
         # A little above two warp-chains per SM sub-partition (8 per SM) the absorb phase is time-sliced: three chains on one
         # sub-partition saturate its shuffle port and would set the pace of the whole launch (247 instead of 197 cycles per round), so
         # every launch serves exactly 8 * SMs chains with a block budget and the resting set rotates (fz_hash_ag_absorb_sliced).
-        n_slots = int(os.environ.get("FZ_AGG_SLOTS", 8 * ctx.param("sm_count")))   # (the override lets small tests reach this path)
-        sliced = n_slots < n_aggs <= (3 * n_slots) // 2 and n_aggs < 2816 and os.environ.get("FZ_AGG_SLICED", "1") != "0"
+        tn = self.tuning
+        n_slots = tn.agg_slots if tn.agg_slots is not None else 8 * ctx.param("sm_count")
+        sliced = n_slots < n_aggs <= (3 * n_slots) // 2 and n_aggs < 2816 and tn.sliced
         if sliced:
-            P = max(1, P // int(os.environ.get("FZ_SL_PDIV", "2")))
+            P = max(1, P // tn.sliced_window_div)
             skip_n = n_aggs - n_slots
             per_signer = 71.0 if self.secpar == 256 else 22.0       # 136-byte blocks of message text per signer (9,513 B / 2,908 B typical)
-            budget = int(P * per_signer * float(os.environ.get("FZ_SL_BUDGET", "1.01")) * n_aggs / n_slots) + 2
+            budget = int(P * per_signer * tn.sliced_budget * n_aggs / n_slots) + 2
         state = ctx.hash_ag_begin(agg_off, n_aggs)
         ring, ring_cap, text_pos = ctx.hash_ag_ring(n_aggs, 3 * P if sliced else P)   # room for the backlog of the resting chains
         agg_ids = torch.arange(n_aggs, dtype=torch.int32, device=dev)
@@ -248,7 +260,7 @@ class Engine:
         # The per-signer work of the next window (gather, hash_ch, message text) runs beside the sponge chains on a side stream.
         # Measured warm on one B200 (FZ_AGG_OVERLAP=0 keeps everything on one stream): verify of 1,250 capacity aggregates 1.06 s
         # against 1.18 s, of 10,000 aggregates 2.80 s against 3.10 s.
-        overlap = os.environ.get("FZ_AGG_OVERLAP", "1") != "0"
+        overlap = tn.overlap
         prep = self._side_stream() if overlap else main   # one side stream per engine: the caching allocator pools blocks per stream
         if overlap:
             prep.wait_stream(main)
@@ -271,7 +283,7 @@ class Engine:
                 pos = perm.index_select(0, idx)
                 vl_w, vr_w, dg_w = ctx.gather_sorted(vk_l, vk_r, dg_all, pos, sel=sel_d)
                 c_w = ctx.hash_ch(vl_w, vr_w, dg_w)
-                wend = ctx.hash_ag_text(vl_w, vr_w, dg_w, c_w, win_off, agg_of, agg_off, n_aggs, n_win, w, text_pos, ring, ring_cap)
+                wend = ctx.hash_ag_text(vl_w, vr_w, dg_w, c_w, win_off, agg_of, agg_off, n_aggs, n_win, w, text_pos, ring, ring_cap, state=state)
                 ready = torch.cuda.Event()
                 ready.record(prep)
             if overlap:
@@ -290,12 +302,14 @@ class Engine:
         if sliced:
             # the text is complete: two more rotating launches, then one over every chain without a budget closes what is left
             k = len(wins)
-            for extra in range(int(os.environ.get("FZ_SL_EXTRA", "2"))):
+            for extra in range(tn.sliced_extra_launches):
                 ctx.hash_ag_absorb_sliced(state, ring, ring_cap, wend, n_aggs, ((k + 1 + extra) * skip_n) % n_aggs, n_slots, budget)
             ctx.hash_ag_absorb_sliced(state, ring, ring_cap, wend, n_aggs, 0, n_aggs, 1 << 62)
-            still_open = ctx.hash_ag_open_sponges(state, n_aggs)
-            if still_open:
-                raise native.FusionB200Error(f"time-sliced aggregation hash: {still_open} sponges not closed")
+        # every sponge must have closed its message: one that was lapped by the text writer (ring too small for its backlog) is poisoned by the
+        # kernels and shows up here -- fail loudly, never return coefficients hashed from overwritten bytes
+        still_open = ctx.hash_ag_open_sponges(state, n_aggs)
+        if still_open:
+            raise native.FusionB200Error(f"aggregation hash: {still_open} of {n_aggs} sponges did not close their message (text ring overrun)")
         if overlap:
             for t in (ring, text_pos, agg_ids, agg_off, perm, sel_d):
                 t.record_stream(prep)

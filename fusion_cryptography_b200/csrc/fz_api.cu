@@ -6,6 +6,7 @@
 #include <new>
 
 #include "../../include/fusion_b200.h"
+#include <atomic>
 #include "fz_internal.h"
 
 namespace fz {
@@ -17,6 +18,14 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+static std::atomic<unsigned> g_attr_done[64];
+
+bool attr_needed(const fz_ctx* ctx, int slot) {
+    const int dev = ctx && ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
+    const unsigned bit = 1u << slot;
+    return (g_attr_done[dev].fetch_or(bit) & bit) == 0;
 }
 
 int check(cudaError_t e, const char* what) {
@@ -102,7 +111,7 @@ int fz_init(int device, int secpar, fz_ctx** out) {
     cudaDeviceProp prop;
     if (check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { delete c; return -2; }
     c->sm_count = prop.multiProcessorCount;
-    if (ntt_init_tables(c) || hash_init_tables(c) || hashstream_init_tables(c) || sample_init_tables(c)) { delete c; return -2; }
+    if (ntt_init_tables(c) || hash_init_tables(c) || hashstream_init_tables(c) || sample_init_tables(c) || scheme_init(c)) { delete c; return -2; }
     *out = c;
     return 0;
 }
@@ -391,7 +400,7 @@ size_t fz_hash_ag_text_workspace(const fz_ctx* ctx, size_t n_window) { (void)ctx
 
 int fz_hash_ag_text(fz_ctx* ctx, const int32_t* vk_l_w, const int32_t* vk_r_w, const uint8_t* dg_w, const int32_t* c_hat_w, const uint64_t* win_off,
                     const uint32_t* agg_of, const uint64_t* agg_off, size_t n_aggs, size_t n_window, uint32_t w0, uint64_t* text_pos, uint8_t* ring,
-                    size_t ring_cap, uint64_t* wend_out, void* ws, size_t ws_bytes, void* stream) {
+                    size_t ring_cap, const void* state, uint64_t* wend_out, void* ws, size_t ws_bytes, void* stream) {
     FZ_REQUIRE(ctx && (n_aggs == 0 || (win_off && agg_off && text_pos && ring && wend_out)), "fz_hash_ag_text: NULL argument");
     FZ_REQUIRE(n_window == 0 || (vk_l_w && vk_r_w && dg_w && c_hat_w && agg_of && ws), "fz_hash_ag_text: NULL window argument");
     FZ_REQUIRE(ring_cap % 272 == 0 && ring_cap >= 544, "fz_hash_ag_text: ring_cap must be a multiple of 272 (see fz_hash_ag_ring_bytes)");
@@ -400,7 +409,7 @@ int fz_hash_ag_text(fz_ctx* ctx, const int32_t* vk_l_w, const int32_t* vk_r_w, c
     unsigned long long* piece_off = cv.take<unsigned long long>(n_window);
     FZ_REQUIRE(cv.ok, "fz_hash_ag_text: workspace too small (see fz_hash_ag_text_workspace)");
     return launch_agw_text(ctx, vk_l_w, vk_r_w, dg_w, c_hat_w, (const unsigned long long*)win_off, agg_of, (const unsigned long long*)agg_off, n_aggs,
-                           n_window, w0, (unsigned long long*)text_pos, piece_len, piece_off, (unsigned long long*)wend_out, ring, ring_cap,
+                           n_window, w0, (unsigned long long*)text_pos, piece_len, piece_off, (unsigned long long*)wend_out, ring, ring_cap, state,
                            (cudaStream_t)stream);
 }
 

@@ -571,7 +571,8 @@ __global__ void __launch_bounds__(128) agw_len_kernel(int level, int d, const in
 __global__ void __launch_bounds__(128) agw_layout_kernel(const uint32_t* __restrict__ piece_len, const unsigned long long* __restrict__ win_off,
                                                           const unsigned long long* __restrict__ agg_off, size_t n_aggs, uint8_t dst0,
                                                           unsigned long long* __restrict__ text_pos, unsigned long long* __restrict__ piece_off,
-                                                          unsigned long long* __restrict__ wend, uint8_t* __restrict__ ring, size_t ring_cap, uint32_t w0) {
+                                                          unsigned long long* __restrict__ wend, uint8_t* __restrict__ ring, size_t ring_cap, uint32_t w0,
+                                                          const unsigned long long* __restrict__ rpos0, size_t rpos_stride) {
     const int lane = threadIdx.x & 31;
     const size_t j = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (j >= n_aggs) return;
@@ -595,7 +596,9 @@ __global__ void __launch_bounds__(128) agw_layout_kernel(const uint32_t* __restr
     }
     // bit 63 of wend: the message text of this aggregate is complete (its last signer is in this window or an earlier one)
     const bool complete = (unsigned long long)w0 + (hi - lo) >= agg_off[j + 1] - agg_off[j];
-    if (lane == 0) { text_pos[j] = pos; wend[j] = pos | (complete ? AGW_TEXT_COMPLETE : 0ULL); }
+    // ring discipline: everything from the sponge's read position (never ahead of the value read here: it only grows) to the new end must fit
+    const bool overrun = rpos0 != nullptr && pos - rpos0[j * rpos_stride] > ring_cap;
+    if (lane == 0) { text_pos[j] = pos; wend[j] = pos | (complete ? AGW_TEXT_COMPLETE : 0ULL) | (overrun ? AGW_TEXT_OVERRUN : 0ULL); }
 }
 
 // dst and src are congruent mod 16; bytes outside [dst, dst + len) are never written (neighbouring pieces are written concurrently)
@@ -756,12 +759,9 @@ int launch_sponge_bytes(const fz_ctx* ctx, const uint8_t* data, const unsigned l
 int launch_format(const fz_ctx* ctx, int mode, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, const int32_t* c_hat, size_t n,
                   uint8_t* out, size_t out_stride, uint32_t* out_len, cudaStream_t st) {
     if (n == 0) return 0;
-    static bool attr_set = false;
     const int smem = FMT_WARPS * FMT_SMEM_PER_WARP;
-    if (!attr_set) {
-        if (check(cudaFuncSetAttribute(format_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "format smem attr")) return -2;
-        attr_set = true;
-    }
+    if (attr_needed(ctx, ATTR_FORMAT) &&
+        check(cudaFuncSetAttribute(format_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "format smem attr")) return -2;
     size_t blocks = (n + FMT_WARPS - 1) / FMT_WARPS;
     const size_t cap = (size_t)ctx->sm_count * 5;
     if (blocks > cap) blocks = cap;
@@ -806,7 +806,8 @@ size_t agw_max_piece() { return (size_t)FMT_SMEM_PER_WARP + 8; }
 
 int launch_agw_text(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, const int32_t* c_hat, const unsigned long long* win_off,
                     const uint32_t* agg_of, const unsigned long long* agg_off, size_t n_aggs, size_t n_win, uint32_t w0, unsigned long long* text_pos,
-                    uint32_t* piece_len, unsigned long long* piece_off, unsigned long long* wend, uint8_t* ring, size_t ring_cap, cudaStream_t st) {
+                    uint32_t* piece_len, unsigned long long* piece_off, unsigned long long* wend, uint8_t* ring, size_t ring_cap, const void* state,
+                    cudaStream_t st) {
     if (n_aggs == 0) return 0;
     const int level = ctx->secpar == 256 ? 1 : 0;
     const uint8_t dst0 = (uint8_t)(ctx->secpar == 256 ? 3 : 1);
@@ -814,15 +815,14 @@ int launch_agw_text(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r,
         agw_len_kernel<<<(unsigned)((n_win + 3) / 4), 128, 0, st>>>(level, ctx->d, vk_l, vk_r, digests, c_hat, win_off, agg_of, agg_off, n_win, w0, piece_len);
         if (check(cudaGetLastError(), "agw_len launch")) return -2;
     }
-    agw_layout_kernel<<<(unsigned)((n_aggs + 3) / 4), 128, 0, st>>>(piece_len, win_off, agg_off, n_aggs, dst0, text_pos, piece_off, wend, ring, ring_cap, w0);
+    agw_layout_kernel<<<(unsigned)((n_aggs + 3) / 4), 128, 0, st>>>(piece_len, win_off, agg_off, n_aggs, dst0, text_pos, piece_off, wend, ring, ring_cap, w0,
+                                                                    state ? (const unsigned long long*)((const uint8_t*)state + ag_state_rpos_offset()) : nullptr,
+                                                                    ag_state_bytes() / 8);
     if (check(cudaGetLastError(), "agw_layout launch")) return -2;
     if (n_win) {
-        static bool attr = false;
         const int smem = FMT_WARPS * AGW_SMEM_PER_WARP;
-        if (!attr) {
-            if (check(cudaFuncSetAttribute(agw_format_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "agw_format smem attr")) return -2;
-            attr = true;
-        }
+        if (attr_needed(ctx, ATTR_AGW_FORMAT) &&
+            check(cudaFuncSetAttribute(agw_format_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "agw_format smem attr")) return -2;
         size_t blocks = (n_win + FMT_WARPS - 1) / FMT_WARPS;
         const size_t cap = (size_t)ctx->sm_count * 16;
         if (blocks > cap) blocks = cap;

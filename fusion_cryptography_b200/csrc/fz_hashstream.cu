@@ -546,7 +546,8 @@ __global__ void __launch_bounds__(32) agw_absorb_thread_kernel(AgState* __restri
     const uint32_t absorbed = s->absorbed + (uint32_t)(win_off[j + 1] - win_off[j]);
     const bool closing = absorbed == s->total;
     unsigned long long rpos = s->rpos;
-    const unsigned long long end = wend[j] & ~AGW_TEXT_COMPLETE;
+    const unsigned long long end = wend[j] & ~AGW_TEXT_FLAGS;
+    if (wend[j] & AGW_TEXT_OVERRUN) { s->phase = 0xDEAD; return; }   // the writer overwrote bytes this sponge had not absorbed: never hash them
     s->absorbed = absorbed;
     if (rpos + KECCAK_RATE > end && !closing) return;
     unsigned long long a[25];
@@ -1059,8 +1060,12 @@ __global__ void __launch_bounds__(32) agw_absorb_warp_kernel(AgState* __restrict
     const uint32_t absorbed = s->absorbed + (uint32_t)(win_off[j + 1] - win_off[j]);
     const bool closing = absorbed == s->total;
     unsigned long long rpos = s->rpos;
-    const unsigned long long end = wend[j] & ~AGW_TEXT_COMPLETE;
+    const unsigned long long end = wend[j] & ~AGW_TEXT_FLAGS;
     __syncwarp();
+    if (wend[j] & AGW_TEXT_OVERRUN) {   // the writer overwrote bytes this sponge had not absorbed: never hash them
+        if (L == 0) s->phase = 0xDEAD;
+        return;
+    }
     if (L == 0) s->absorbed = absorbed;
     if (rpos + KECCAK_RATE > end && !closing) return;
     const Lane c = lane_init(L);
@@ -1120,10 +1125,10 @@ __global__ void __launch_bounds__(128) agw_absorb_sliced_kernel(AgState* __restr
     AgState* s = st + j;
     if (s->phase != 0) return;
     const unsigned long long we = wend[j];
-    const unsigned long long end = we & ~AGW_TEXT_COMPLETE;
+    const unsigned long long end = we & ~AGW_TEXT_FLAGS;
     const bool complete = (we & AGW_TEXT_COMPLETE) != 0;
     unsigned long long rpos = s->rpos;
-    if (end - rpos > ring_cap) {   // the text writer lapped this chain (budget too small for the text produced): fail loudly, never hash garbage
+    if ((we & AGW_TEXT_OVERRUN) || end - rpos > ring_cap) {   // the text writer lapped this chain (budget too small for the text produced): fail loudly, never hash garbage
         if (L == 0) s->phase = 0xDEAD;
         return;
     }
@@ -1199,6 +1204,7 @@ __global__ void __launch_bounds__(32) agw_squeeze_warp_kernel(AgState* __restric
 }  // namespace warpag
 
 size_t ag_state_bytes() { return sizeof(AgState); }
+size_t ag_state_rpos_offset() { return offsetof(AgState, rpos); }
 
 int launch_ag_state_init(const fz_ctx* ctx, void* state, const unsigned long long* agg_off, size_t n_aggs, cudaStream_t st) {
     if (n_aggs == 0) return 0;
@@ -1207,15 +1213,13 @@ int launch_ag_state_init(const fz_ctx* ctx, void* state, const unsigned long lon
     return check(cudaGetLastError(), "hash_ag state init launch");
 }
 
-static int warp_smem_attr() {
-    static bool attr = false;
+static int warp_smem_attr(const fz_ctx* ctx) {
     const int smem = warpag::WARPS * warpag::SMEM_PER_WARP;
-    if (!attr) {
+    if (attr_needed(ctx, ATTR_WARP_HASH)) {
         if (check(cudaFuncSetAttribute(warpag::hash_ag_absorb_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "hash_ag absorb smem attr"))
             return -2;
         if (check(cudaFuncSetAttribute(warpag::hash_ag_squeeze_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "hash_ag squeeze smem attr"))
             return -2;
-        attr = true;
     }
     return 0;
 }
@@ -1229,7 +1233,7 @@ int launch_hash_ag_absorb(const fz_ctx* ctx, void* state, const int32_t* vk_l_s,
     if (n_aggs == 0) return 0;
     const int level = ctx->secpar == 256 ? 1 : 0;
     if (use_warp(ctx, n_aggs)) {
-        if (warp_smem_attr()) return -2;
+        if (warp_smem_attr(ctx)) return -2;
         warpag::hash_ag_absorb_warp_kernel<<<(int)((n_aggs + warpag::WARPS - 1) / warpag::WARPS), warpag::WARPS * 32, warpag::WARPS * warpag::SMEM_PER_WARP,
                                              st>>>((AgState*)state, vk_l_s, vk_r_s, dg_s, c_hat_s, win_off, n_aggs, level, ctx->d);
     } else {
@@ -1242,7 +1246,7 @@ int launch_hash_ag_absorb(const fz_ctx* ctx, void* state, const int32_t* vk_l_s,
 int launch_hash_ag_squeeze(const fz_ctx* ctx, void* state, const unsigned long long* win_off, size_t n_aggs, int32_t* coef_out, cudaStream_t st) {
     if (n_aggs == 0) return 0;
     if (use_warp(ctx, n_aggs)) {
-        if (warp_smem_attr()) return -2;
+        if (warp_smem_attr(ctx)) return -2;
         warpag::hash_ag_squeeze_warp_kernel<<<(int)((n_aggs + warpag::WARPS - 1) / warpag::WARPS), warpag::WARPS * 32, warpag::WARPS * warpag::SMEM_PER_WARP,
                                               st>>>((AgState*)state, win_off, n_aggs, ctx->d, ctx->omega_ag, ctx->bytes_coef, ctx->bytes_idx,
                                                     (uint32_t)ctx->n_ag, coef_out);
@@ -1257,22 +1261,20 @@ int launch_hash_ag_squeeze(const fz_ctx* ctx, void* state, const unsigned long l
 // carve-out -- and an SM cannot change its carve-out while CTAs are resident: every kernel of the side stream that needs shared
 // memory (torch's scans, hash_ch, the text formatter) then waits until a whole SM has drained, i.e. almost to the end of the
 // chain kernel (44 of 52 ms, found with tools/agg_host_probe.py).  Asking for the largest carve-out keeps the SMs hospitable.
-static int chain_carveout() {
-    static bool done = false;
-    if (done) return 0;
+static int chain_carveout(const fz_ctx* ctx) {
+    if (!attr_needed(ctx, ATTR_CHAIN_CARVEOUT)) return 0;
     const void* ks[] = {(const void*)agw_absorb_thread_kernel,          (const void*)agw_squeeze_thread_kernel,
                         (const void*)warpag::agw_absorb_warp_kernel<24>, (const void*)warpag::agw_squeeze_warp_kernel<24>,
                         (const void*)warpag::agw_absorb_sliced_kernel<24>};
     for (const void* k : ks)
         if (check(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "chain kernel carve-out")) return -2;
-    done = true;
     return 0;
 }
 
 int launch_agw_absorb(const fz_ctx* ctx, void* state, const uint8_t* ring, size_t ring_cap, const unsigned long long* wend,
                       const unsigned long long* win_off, size_t n_aggs, cudaStream_t st) {
     if (n_aggs == 0) return 0;
-    if (chain_carveout()) return -2;
+    if (chain_carveout(ctx)) return -2;
     if (use_warp(ctx, n_aggs))
         warpag::agw_absorb_warp_kernel<24><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
     else
@@ -1283,8 +1285,7 @@ int launch_agw_absorb(const fz_ctx* ctx, void* state, const uint8_t* ring, size_
 int launch_agw_absorb_sliced(const fz_ctx* ctx, void* state, const uint8_t* ring, size_t ring_cap, const unsigned long long* wend, size_t n_aggs,
                              size_t first_active, size_t n_active, unsigned long long budget_blocks, cudaStream_t st) {
     if (n_aggs == 0 || n_active == 0) return 0;
-    (void)ctx;
-    if (chain_carveout()) return -2;
+    if (chain_carveout(ctx)) return -2;
     warpag::agw_absorb_sliced_kernel<24><<<(unsigned)((n_active + 3) / 4), 128, 0, st>>>((AgState*)state, ring, ring_cap, wend, n_aggs, first_active, n_active,
                                                                                         budget_blocks);
     return check(cudaGetLastError(), "agw_absorb_sliced launch");
@@ -1293,7 +1294,7 @@ int launch_agw_absorb_sliced(const fz_ctx* ctx, void* state, const uint8_t* ring
 int launch_agw_squeeze(const fz_ctx* ctx, void* state, const unsigned long long* win_off, size_t n_aggs, uint8_t* xof, size_t xof_cap, uint32_t* bpos_out,
                        cudaStream_t st) {
     if (n_aggs == 0) return 0;
-    if (chain_carveout()) return -2;
+    if (chain_carveout(ctx)) return -2;
     if (use_warp(ctx, n_aggs))
         warpag::agw_squeeze_warp_kernel<24><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
     else

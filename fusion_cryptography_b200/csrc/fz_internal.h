@@ -18,6 +18,7 @@ struct fz_ctx {
     // scratch owned by the context (grown on demand, never per call when large enough)
     void* scratch;
     size_t scratch_bytes;
+    int sort_smem_max;  // dynamic shared memory sort_kernel may use on this device (opt-in made in scheme_init)
     int hash_ag_impl;   // 0 auto (warp per aggregate below 2816 aggregates, thread per aggregate above), 2 thread, 3 warp
     int buffered_hash;  // 1: format text into HBM scratch first (fz_hash.cu); 0 (default): streaming generator (fz_hashstream.cu)
 };
@@ -26,6 +27,10 @@ namespace fz {
 
 void set_error(const char* fmt, ...);
 int check(cudaError_t e, const char* what);
+// Kernel attributes (dynamic shared-memory opt-in, carve-out) are PER DEVICE: true the first time `slot` is asked about on the context's device.
+// Setting an attribute twice is harmless, so two host threads racing here only repeat the call.
+enum AttrSlot { ATTR_FORMAT = 0, ATTR_AGW_FORMAT = 1, ATTR_WARP_HASH = 2, ATTR_CHAIN_CARVEOUT = 3 };
+bool attr_needed(const fz_ctx* ctx, int slot);
 
 // fz_ntt.cu
 int ntt_init_tables(fz_ctx* ctx);
@@ -78,11 +83,17 @@ int launch_agw_squeeze(const fz_ctx* ctx, void* state, const unsigned long long*
                        cudaStream_t st);
 // bit 63 of the per-aggregate message length written by the text stage: the text is complete
 constexpr unsigned long long AGW_TEXT_COMPLETE = 1ULL << 63;
+// bit 62: the text writer found that this window's text would overwrite ring bytes the aggregate's sponge has not absorbed yet (ring too small
+// for the backlog): the absorb kernels poison the sponge (phase 0xDEAD) instead of hashing overwritten bytes
+constexpr unsigned long long AGW_TEXT_OVERRUN = 1ULL << 62;
+constexpr unsigned long long AGW_TEXT_FLAGS = AGW_TEXT_COMPLETE | AGW_TEXT_OVERRUN;
+size_t ag_state_rpos_offset();
 // fz_hash.cu (windowed text / decode)
 size_t agw_max_piece();
 int launch_agw_text(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, const int32_t* c_hat, const unsigned long long* win_off,
                     const uint32_t* agg_of, const unsigned long long* agg_off, size_t n_aggs, size_t n_win, uint32_t w0, unsigned long long* text_pos,
-                    uint32_t* piece_len, unsigned long long* piece_off, unsigned long long* wend, uint8_t* ring, size_t ring_cap, cudaStream_t st);
+                    uint32_t* piece_len, unsigned long long* piece_off, unsigned long long* wend, uint8_t* ring, size_t ring_cap, const void* state,
+                    cudaStream_t st);
 int launch_agw_decode(const fz_ctx* ctx, const uint8_t* xof, size_t xof_cap, const uint32_t* bpos, const unsigned long long* win_off, const uint32_t* agg_of,
                       size_t n_win, int32_t* coef_out, cudaStream_t st);
 
@@ -97,6 +108,7 @@ int launch_row_seeds_to_keys(const fz_ctx* ctx, const unsigned long long* seeds,
 int launch_replicate_rows(const fz_ctx* ctx, const int32_t* src, int32_t* dst, size_t batch, int rows, size_t src_batch_stride, cudaStream_t st);
 
 // fz_scheme.cu
+int scheme_init(fz_ctx* ctx);
 int launch_sort(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint32_t* sel, const unsigned long long* agg_off, size_t n_aggs,
                 size_t max_keys, uint32_t* perm, cudaStream_t st);
 int launch_gather_sorted(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, const uint32_t* sel, const uint32_t* perm,

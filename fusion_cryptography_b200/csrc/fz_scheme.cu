@@ -45,9 +45,9 @@ __device__ int repr_cmp(const int32_t* al, const int32_t* ar, const int32_t* bl,
 // Rank sort, one CTA column per aggregate.  sel[p] = key index of position p (NULL: identity).
 // perm[agg_off[j] + rank] = p  (sorted position -> original position), stable.
 __global__ void __launch_bounds__(256) sort_kernel(const int32_t* __restrict__ vk_l, const int32_t* __restrict__ vk_r, const uint32_t* __restrict__ sel,
-                                                    const unsigned long long* __restrict__ agg_off, int d, uint32_t* __restrict__ perm) {
+                                                    const unsigned long long* __restrict__ agg_off, size_t j0, int d, uint32_t* __restrict__ perm) {
     extern __shared__ unsigned long long skeys[];
-    const size_t j = blockIdx.y;
+    const size_t j = j0 + blockIdx.y;
     const size_t lo = agg_off[j], hi = agg_off[j + 1];
     const int n = (int)(hi - lo);
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
@@ -94,13 +94,13 @@ __global__ void __launch_bounds__(128) gather_sorted_kernel(const int32_t* __res
 // part[j][s][c] = cent( sum_{p in split s of aggregate j} sig[perm[p]][c] * alpha[p][c mod d] ),  c over ell*d
 // grid = (col blocks, split, n_aggs); thread <-> 4 consecutive coefficients.
 __global__ void __launch_bounds__(256) aggregate_kernel(const int4* __restrict__ sigs, const uint32_t* __restrict__ perm, const int4* __restrict__ alpha,
-                                                          const unsigned long long* __restrict__ agg_off, int ell, int d4, int split,
+                                                          const unsigned long long* __restrict__ agg_off, size_t j0, int ell, int d4, int split,
                                                           int4* __restrict__ part) {
     const int cols = ell * d4;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
     const int s = blockIdx.y;
-    const size_t j = blockIdx.z;
+    const size_t j = j0 + blockIdx.z;
     const size_t lo = agg_off[j], hi = agg_off[j + 1];
     const size_t n = hi - lo, per = (n + split - 1) / split;
     size_t p0 = lo + (size_t)s * per, p1 = p0 + per;
@@ -214,14 +214,26 @@ int launch_sort(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, con
                 size_t max_keys, uint32_t* perm, cudaStream_t st) {
     if (n_aggs == 0 || max_keys == 0) return 0;
     const size_t smem = max_keys * sizeof(unsigned long long);
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        if (check(cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sort smem attr")) return -2;
-        attr = smem;
+    if (smem > (size_t)ctx->sort_smem_max) {   // the opt-in was made for this context's device in scheme_init
+        set_error("fz_sort_keys: %zu keys in one aggregate need %zu bytes of shared memory, the device allows %d", max_keys, smem, ctx->sort_smem_max);
+        return -1;
     }
-    dim3 grid((unsigned)((max_keys + 255) / 256), (unsigned)n_aggs);
-    sort_kernel<<<grid, 256, smem, st>>>(vk_l, vk_r, sel, agg_off, ctx->d, perm);
-    return check(cudaGetLastError(), "sort launch");
+    for (size_t j0 = 0; j0 < n_aggs; j0 += 65535) {   // gridDim.y is limited to 65,535
+        const size_t nj = n_aggs - j0 < 65535 ? n_aggs - j0 : 65535;
+        dim3 grid((unsigned)((max_keys + 255) / 256), (unsigned)nj);
+        sort_kernel<<<grid, 256, smem, st>>>(vk_l, vk_r, sel, agg_off, j0, ctx->d, perm);
+        if (check(cudaGetLastError(), "sort launch")) return -2;
+    }
+    return 0;
+}
+
+// per-device kernel attributes of this translation unit (called from fz_init with the context's device current)
+int scheme_init(fz_ctx* ctx) {
+    int optin = 0;
+    if (check(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device), "shared-memory opt-in query")) return -2;
+    if (check(cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin), "sort smem attr")) return -2;
+    ctx->sort_smem_max = optin;
+    return 0;
 }
 
 int launch_gather_sorted(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, const uint32_t* sel, const uint32_t* perm,
@@ -245,9 +257,12 @@ int launch_aggregate(const fz_ctx* ctx, const int32_t* sigs, const uint32_t* per
                      int split, int32_t* part, int32_t* out, cudaStream_t st) {
     if (n_aggs == 0) return 0;
     const int d4 = ctx->d / 4, cols = ctx->ell * d4;
-    dim3 grid((unsigned)((cols + 255) / 256), (unsigned)split, (unsigned)n_aggs);
-    aggregate_kernel<<<grid, 256, 0, st>>>((const int4*)sigs, perm, (const int4*)alpha, agg_off, ctx->ell, d4, split, (int4*)(split == 1 ? out : part));
-    if (check(cudaGetLastError(), "aggregate launch")) return -2;
+    for (size_t j0 = 0; j0 < n_aggs; j0 += 65535) {   // gridDim.z is limited to 65,535
+        const size_t nj = n_aggs - j0 < 65535 ? n_aggs - j0 : 65535;
+        dim3 grid((unsigned)((cols + 255) / 256), (unsigned)split, (unsigned)nj);
+        aggregate_kernel<<<grid, 256, 0, st>>>((const int4*)sigs, perm, (const int4*)alpha, agg_off, j0, ctx->ell, d4, split, (int4*)(split == 1 ? out : part));
+        if (check(cudaGetLastError(), "aggregate launch")) return -2;
+    }
     if (split > 1) {
         size_t blocks = (n_aggs * cols + 255) / 256;
         const size_t cap = (size_t)ctx->sm_count * 8;

@@ -644,13 +644,14 @@ def hash_ag_xof_buffer(self, n_aggs: int, max_window: int):
     return torch.empty(max(n_aggs, 1) * cap, dtype=torch.uint8, device=self.device), cap
 
 
-def hash_ag_text(self, vk_l_w, vk_r_w, dg_w, c_hat_w, win_off, agg_of, agg_off, n_aggs: int, n_window: int, w0: int, text_pos, ring, ring_cap: int):
-    """Writes the text window w0 adds to every aggregate's message into the rings; returns the message lengths after it."""
+def hash_ag_text(self, vk_l_w, vk_r_w, dg_w, c_hat_w, win_off, agg_of, agg_off, n_aggs: int, n_window: int, w0: int, text_pos, ring, ring_cap: int, state=None):
+    """Writes the text window w0 adds to every aggregate's message into the rings; returns the message lengths after it (bit 63: text complete;
+    bit 62, only with `state`: the text overran bytes the aggregate's sponge had not absorbed -- the absorb calls then poison that sponge)."""
     self.lib.fz_hash_ag_text_workspace.restype = C.c_size_t
     ws = self._ws(self.lib.fz_hash_ag_text_workspace(self._h, C.c_size_t(n_window)))
     wend = torch.empty(max(n_aggs, 1), dtype=torch.int64, device=self.device)
     self._chk(self.lib.fz_hash_ag_text(self._h, _ptr(vk_l_w), _ptr(vk_r_w), _ptr(dg_w), _ptr(c_hat_w), _ptr(win_off), _ptr(agg_of), _ptr(agg_off),
-                                       C.c_size_t(n_aggs), C.c_size_t(n_window), C.c_uint32(w0), _ptr(text_pos), _ptr(ring), C.c_size_t(ring_cap), _ptr(wend),
+                                       C.c_size_t(n_aggs), C.c_size_t(n_window), C.c_uint32(w0), _ptr(text_pos), _ptr(ring), C.c_size_t(ring_cap), _ptr(state), _ptr(wend),
                                        _ptr(ws), C.c_size_t(ws.numel()), self._stream()))
     return wend
 

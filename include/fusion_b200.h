@@ -107,13 +107,16 @@ int fz_hash_ag_squeeze(fz_ctx* ctx, void* state, const uint64_t* win_off, size_t
  * counts, zero-initialised; wend_out: n_aggs message lengths after this window); the chain absorbs ring blocks up to wend;
  * squeezed blocks go to a per-aggregate XOF buffer (xof_cap = fz_hash_ag_xof_bytes(P)) which fz_hash_ag_decode turns into
  * the window's coefficients (fusion.py:594-629 + NTT).  Window w0 holds the sorted positions w0.. of every aggregate;
- * agg_of[i] is the aggregate of window entry i.  Text of window w+2 may only be written once window w has been absorbed. */
+ * agg_of[i] is the aggregate of window entry i.  Text of window w+2 may only be written once window w has been absorbed.
+ * `state` (optional, the sponge records of fz_hash_ag_begin) lets the writer check that discipline itself: if the new text would reach
+ * back over bytes an aggregate's sponge has not absorbed yet, bit 62 of wend_out is set and the absorb calls poison that sponge
+ * (it never closes; fz_hash_ag_squeeze_xof produces nothing for it) instead of hashing overwritten bytes. */
 size_t fz_hash_ag_ring_bytes(const fz_ctx* ctx, size_t max_window);
 size_t fz_hash_ag_xof_bytes(const fz_ctx* ctx, size_t max_window);
 size_t fz_hash_ag_text_workspace(const fz_ctx* ctx, size_t n_window);
 int fz_hash_ag_text(fz_ctx* ctx, const int32_t* vk_l_w, const int32_t* vk_r_w, const uint8_t* dg_w, const int32_t* c_hat_w, const uint64_t* win_off,
                     const uint32_t* agg_of, const uint64_t* agg_off, size_t n_aggs, size_t n_window, uint32_t w0, uint64_t* text_pos, uint8_t* ring,
-                    size_t ring_cap, uint64_t* wend_out, void* ws, size_t ws_bytes, void* stream);
+                    size_t ring_cap, const void* state, uint64_t* wend_out, void* ws, size_t ws_bytes, void* stream);
 int fz_hash_ag_absorb_ring(fz_ctx* ctx, void* state, const uint8_t* ring, size_t ring_cap, const uint64_t* wend, const uint64_t* win_off, size_t n_aggs,
                            void* stream);
 /* time-sliced absorb (same sponge, fusion.py:591): one launch advances n_active aggregates, first_active.. modulo n_aggs, by at

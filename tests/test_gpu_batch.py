@@ -85,14 +85,14 @@ def test_aggregate_verify_batch(engines, oracle, scheme_golden, secpar):
         eng.ctx.set_option("hash_ag_impl", 0)
     # the time-sliced absorb (batches a little above 8 warp-chains per SM): pretend the GPU has room for 6 chains, so that 6 of the 8
     # aggregates advance per launch with a block budget while the resting pair rotates
-    os.environ["FZ_AGG_SLOTS"] = "6"
+    eng.tuning.agg_slots = 6
     try:
         for max_pos in (1 << 17, 40, 16):
             aggs = eng.aggregate(kb.vk_l, kb.vk_r, msgs, sigs, counts, sel=sel_t, max_positions=max_pos)
             assert torch.equal(aggs, ref_aggs), ("sliced", max_pos)
             assert host(eng.verify(kb.vk_l, kb.vk_r, msgs, aggs, counts, sel=sel_t, max_positions=max_pos)).tolist() == [0] * len(counts)
     finally:
-        del os.environ["FZ_AGG_SLOTS"]
+        eng.tuning.agg_slots = None
     hvl, hvr, hs = host(kb.vk_l), host(kb.vk_r), host(sigs)
     oracle.set_threads(oracle.max_threads())
     off = 0

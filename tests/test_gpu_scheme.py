@@ -388,3 +388,32 @@ def test_hash_pipeline_stays_inside_its_byte_buffers(ctxs, secpar, impl):
         assert torch.equal(out, want)
     finally:
         ctx.set_option("hash_ag_impl", 0)
+
+
+def test_text_ring_overrun_is_detected_not_hashed(ctxs):
+    """Ring discipline of the windowed aggregation hash (advisor finding): when a window's text would overwrite bytes a sponge has not absorbed
+    yet, the writer flags the aggregate (bit 62 of wend), the absorb call poisons its sponge and the host sees a sponge that never closed --
+    the hash of overwritten bytes is never produced.  Provoked with a ring of the minimum size against a window of several signers."""
+    ctx = ctxs[256]
+    d = ctx.d
+    rng = np.random.default_rng(11)
+    counts = [6, 1]
+    n, n_aggs = sum(counts), len(counts)
+    vl, vr = dev(rng.integers(-H, H + 1, size=(n, d)).astype(np.int32)), dev(rng.integers(-H, H + 1, size=(n, d)).astype(np.int32))
+    dg = dev(rng.integers(0, 256, size=(n, 32)).astype(np.uint8), np.uint8)
+    c = ctx.hash_ch(vl, vr, dg)
+    agg_off, n_total, max_keys = ctx._agg_off(counts)
+    agg_of = torch.repeat_interleave(torch.arange(n_aggs, dtype=torch.int32, device="cuda"), torch.tensor(counts, device="cuda"))
+    cap = 272 * 80                                   # 21,760 bytes: room for two signers' text (about 9.5 KB each), not for six
+    ring = torch.zeros(n_aggs * cap, dtype=torch.uint8, device="cuda")
+    text_pos = torch.zeros(n_aggs, dtype=torch.int64, device="cuda")
+    state = ctx.hash_ag_begin(agg_off, n_aggs)
+    wend = ctx.hash_ag_text(vl, vr, dg, c, agg_off, agg_of, agg_off, n_aggs, n_total, 0, text_pos, ring, cap, state=state)
+    flags = (wend.cpu().numpy().astype(np.uint64) >> np.uint64(62)) & np.uint64(3)
+    assert flags.tolist() == [3, 2], flags           # aggregate 0: complete + overrun; aggregate 1 (one signer): complete, fits
+    ctx.hash_ag_absorb_ring(state, ring, cap, wend, agg_off, n_aggs)
+    assert ctx.hash_ag_open_sponges(state, n_aggs) == 1
+    # without the state the writer cannot know (the caller's discipline, as before): no flag
+    text_pos.zero_()
+    wend2 = ctx.hash_ag_text(vl, vr, dg, c, agg_off, agg_of, agg_off, n_aggs, n_total, 0, text_pos, ring, cap)
+    assert ((wend2.cpu().numpy().astype(np.uint64) >> np.uint64(62)) & np.uint64(1)).tolist() == [0, 0]
