@@ -643,6 +643,23 @@ def leg_ntt(dv: Dev, ctx):
         hout = torch.empty((n, D), dtype=torch.int32, pin_memory=True)
         hout.zero_()
     e2e_steps = max(3, min(args.steps, 10))
+    # the ceiling of that leg on this box: the bare pinned copies (1 GiB up and 1 GiB down, concurrently, nothing computed), every rank at once
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def bare_copies():
+        with torch.cuda.stream(s_up):
+            a.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            hout.copy_(c, non_blocking=True)
+
+    bare_copies()
+    torch.cuda.synchronize()
+    dv.barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        bare_copies()
+    torch.cuda.synchronize()
+    bare_s = dv.allmax(time.perf_counter() - t0) / 3
     ctx.pass_host(hin, bhat, hout)
     dv.barrier()
     t0 = time.perf_counter()
@@ -681,7 +698,11 @@ def leg_ntt(dv: Dev, ctx):
         "metric": METRIC["ntt"], "value": n * world * args.steps / (elapsed_ms / 1000.0), "unit": UNIT["ntt"], "ms_per_step": elapsed_ms / args.steps,
         "scaling": "weak", "dtype": "u32", "gpu_launches": args.steps, "clocks": clocks, "roofline": roofline,
         "e2e": {"value": n * world * e2e_steps / e2e_s, "unit": UNIT["ntt"], "h2d_bytes_per_step": n * D * 4, "d2h_bytes_per_step": n * D * 4,
-                "ms_per_step": 1000 * e2e_s / e2e_steps, "matches_device_path": same, "host_buffers": numa_note["note"]},
+                "ms_per_step": 1000 * e2e_s / e2e_steps, "matches_device_path": same, "host_buffers": numa_note["note"],
+                "pcie_ceiling": {"ms_per_step": 1000 * bare_s, "GB/s_per_direction_all_ranks": world * n * D * 4 / bare_s / 1e9,
+                                 "frac": bare_s / (e2e_s / e2e_steps),
+                                 "note": "the same pinned buffers copied up and down concurrently with nothing computed, all ranks at once (max over ranks): what the box's "
+                                         "host links give this leg; frac = that time / the pipeline's time"}},
     }
 
 
