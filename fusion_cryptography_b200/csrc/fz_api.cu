@@ -130,6 +130,7 @@ int fz_set_option(fz_ctx* c, const char* name, long long value) {
     FZ_REQUIRE(c && name, "fz_set_option: NULL argument");
     if (!strcmp(name, "buffered_hash")) { c->buffered_hash = value ? 1 : 0; return 0; }
     if (!strcmp(name, "hash_ag_impl")) { c->hash_ag_impl = (int)value; return 0; }
+    if (!strcmp(name, "sample_impl")) { fz::set_sample_impl((int)value); return 0; }
     fz::set_error("fz_set_option: unknown option %s", name);
     return -1;
 }

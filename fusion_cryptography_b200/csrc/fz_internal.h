@@ -99,6 +99,7 @@ int launch_agw_decode(const fz_ctx* ctx, const uint8_t* xof, size_t xof_cap, con
 
 // fz_sample.cu
 int sample_init_tables(fz_ctx* ctx);
+void set_sample_impl(int v);   // 0 general kernel, 1 dense kernel with the byte tile, 2 dense kernel with 16-byte stores (default)
 int launch_sample(const fz_ctx* ctx, int mode, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, uint32_t bound, int weight,
                   int32_t* out, cudaStream_t st);
 int launch_sample_ring(int d, uint32_t q, int mode, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, uint32_t bound, int weight,

@@ -114,6 +114,22 @@ def test_samplers(ctxs, oracle, scheme_golden, kat_golden, secpar):
     for s, g in zip(seeds, got):
         random.seed(s)  # algebra/polynomials.py:448-453
         assert g.tolist() == [(1 + random.randrange(52)) * (1 - 2 * random.randrange(2)) for _ in range(d)], s
+    # the dense secret-key kernel seeds a warp from two registers when every seed of the warp has at most two 32-bit limbs: one- and two-limb
+    # seeds mixed, more generators than one CTA holds, each of the three kernels that can serve the call (fz_set_option "sample_impl")
+    seeds2 = [2**33 + 17 * i for i in range(100)] + list(range(5000, 5100)) + [2**64 - 1 - i for i in range(30)] + [2**32 - 1, 2**32, 2**32 + 1]
+    want2 = []
+    for s in seeds2:
+        random.seed(s)
+        want2.append([(1 + random.randrange(52)) * (1 - 2 * random.randrange(2)) for _ in range(d)])
+    for impl in (1, 2, 0, 1):
+        ctx.set_option("sample_impl", impl)
+        assert host(ctx.sample_coef(seeds2)).tolist() == want2, impl
+        assert host(ctx.sample_coef(seeds))[:11].tolist() == got[:11].tolist(), impl
+    for bound in (1, 2, 100, 127, 128, 300):   # 128 and above fall back to the general kernel (magnitudes no longer fit the byte tile)
+        g2 = host(ctx.sample_coef(seeds2[:40] + seeds[:11], norm_bound=bound))
+        for s, g in zip(seeds2[:40] + seeds[:11], g2):
+            random.seed(s)
+            assert g.tolist() == [(1 + random.randrange(bound)) * (1 - 2 * random.randrange(2)) for _ in range(d)], (s, bound)
     got = host(ctx.sample_ntt(seeds))
     for s, g in zip(seeds, got):
         random.seed(s)  # algebra/polynomials.py:479-480

@@ -83,6 +83,44 @@ int main(int argc, char** argv) {
         printf("mode %d: probe %zu generators: %.3f ms (%.1f M gen/s); per warp: seed %.0f cycles, draws %.0f cycles (%.1f trips of %d)\n", it % 3, n, ms, n / ms / 1e3, a / m, b / m,
                t / m, SMP_TRIP);
     }
+    // the dense kernels (sample_dense_kernel<STAGE>): time, cycle split and equality with the general kernel's output
+    {
+        int32_t* d_ref; cudaMalloc(&d_ref, n * 1024);
+        std::vector<int32_t> kl(n, 1);
+        int32_t* d_kl; cudaMalloc(&d_kl, n * 4); cudaMemcpy(d_kl, kl.data(), n * 4, cudaMemcpyHostToDevice);
+        sample_kernel<<<grid, SMP_THREADS, SMP_SMEM>>>(0, d_keys, 8, d_kl, n, 256, Q, 52u, 256, d_ref);
+        cudaDeviceSynchronize();
+        std::vector<int32_t> ref(n * 256), got(n * 256);
+        cudaMemcpy(ref.data(), d_ref, n * 1024, cudaMemcpyDeviceToHost);
+        for (int stage = 1; stage >= 0; --stage) {
+            const int G = stage ? SdCfg<1>::G : SdCfg<0>::G;
+            const unsigned dgrid = (unsigned)((n + G - 1) / G);
+            long long* d_c2; cudaMalloc(&d_c2, (size_t)dgrid * 4 * 16);
+            for (int it = 0; it < 4; ++it) {
+                cudaMemset(d_out, 0xff, n * 1024);
+                long long* cp = it >= 2 ? d_c2 : nullptr;
+                cudaEventRecord(e0);
+                if (stage) sample_dense_kernel<1><<<dgrid, SD_THREADS, SdCfg<1>::SMEM>>>(d_keys, 8, d_kl, n, 256, 52u, d_out, cp);
+                else sample_dense_kernel<0><<<dgrid, SD_THREADS, SdCfg<0>::SMEM>>>(d_keys, 8, d_kl, n, 256, 52u, d_out, cp);
+                cudaEventRecord(e1); cudaDeviceSynchronize();
+                float ms; cudaEventElapsedTime(&ms, e0, e1);
+                cudaMemcpy(got.data(), d_out, n * 1024, cudaMemcpyDeviceToHost);
+                size_t bad = 0;
+                for (size_t i = 0; i < n * 256; ++i) bad += got[i] != ref[i];
+                double a = 0, b = 0;
+                if (cp) {
+                    std::vector<long long> c((size_t)dgrid * 8);
+                    cudaMemcpy(c.data(), d_c2, c.size() * 8, cudaMemcpyDeviceToHost);
+                    for (size_t w = 0; w < (size_t)dgrid * 4; ++w) { a += c[w * 2]; b += c[w * 2 + 1]; }
+                    a /= dgrid * 4.0; b /= dgrid * 4.0;
+                }
+                printf("dense STAGE=%d (%d generators per CTA): %zu generators: %.3f ms (%.1f M gen/s), mismatching coefficients vs the general kernel: %zu", stage, G, n, ms,
+                       n / ms / 1e3, bad);
+                if (cp) printf("; per warp: seed %.0f cycles, draws + write-out %.0f cycles", a, b);
+                printf("\n");
+            }
+        }
+    }
     printf("err %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
