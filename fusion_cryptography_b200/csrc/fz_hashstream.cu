@@ -635,6 +635,246 @@ __global__ void __launch_bounds__(32) agw_squeeze_thread_kernel(AgState* __restr
 }
 
 // ---------------------------------------------------------------------------------- host
+// ---------------------------------------------------------------------------------- ring-fed chain (TWO lanes per aggregate)
+// Between about 1,800 and 40,000 aggregates per GPU neither of the two layouts above fits: a warp per chain puts three and more warps on a
+// sub-partition and their 18 shuffles per round saturate its shuffle port (247 cycles per round at three chains, 350 at four), a thread per chain
+// leaves half of the sub-partitions without a warp below 19,000 chains while each warp is bound by its own ALU pipe (180 instructions x 2 cycles
+// per round: 370-400 cycles).  Here the even lane of a pair holds the LOW 32 bits of every Keccak lane and the odd lane the HIGH 32 bits: XOR and
+// AND-NOT need no communication, a 64-bit rotation is one SHFL.BFLY for the partner's half and one funnel shift, i.e. 90 ALU instructions and 28
+// shuffles per thread and round and 16 chains per warp.  tools/keccak_lab2.cu (profiles/r02_keccak_lab2_v23.txt): 246-255 cycles per round up to
+// 9,472 chains (a warp per sub-partition), 351 at 18,944, 545 at 37,888 (3.94 G Keccak-f/s against 4.27 G of the thread layout at saturation); the
+// even / odd bit-interleaved split (V22, 17 shuffles) measures 230 but needs every message word interleaved and every squeezed word
+// de-interleaved (about 40 instructions per 64-bit word), which costs more than the 8 % it saves.  Message bytes and squeezed bytes need no
+// conversion here: each lane loads / stores its own 4 bytes of every 8.
+// Shuffles with a mask narrower than the warp compile to WARPSYNC.COLLECTIVE sequences (4x the instructions), so every shuffle is full-mask and the
+// control flow is warp-uniform: all 16 pairs run as many permutations as the busiest pair of the warp and a pair snapshots its state after its own
+// last one (25 predicated moves per block, about 1 %).
+namespace pairag {
+
+template <int N>
+__device__ __forceinline__ uint32_t rot(uint32_t v) {
+    if constexpr (N == 0) return v;
+    const uint32_t p = __shfl_xor_sync(0xffffffffu, v, 1);
+    if constexpr (N == 32) return p;
+    // n < 32: lo' = (lo << n) | (hi >> (32 - n)), hi' = (hi << n) | (lo >> (32 - n)): funnel(partner, mine, n) on both lanes; 32 + n swaps the halves first
+    constexpr int n = N & 31;
+    if constexpr (N < 32) return __funnelshift_l(p, v, n);
+    else return __funnelshift_l(v, p, n);
+}
+__device__ __forceinline__ uint32_t x5(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e) { return a ^ b ^ c ^ d ^ e; }
+__device__ __forceinline__ uint32_t ch(uint32_t a, uint32_t b, uint32_t c) { return a ^ (~b & c); }
+
+__device__ __forceinline__ void round(uint32_t (&a)[25], uint32_t rc) {
+    const uint32_t c0 = x5(a[0], a[5], a[10], a[15], a[20]);
+    const uint32_t c1 = x5(a[1], a[6], a[11], a[16], a[21]);
+    const uint32_t c2 = x5(a[2], a[7], a[12], a[17], a[22]);
+    const uint32_t c3 = x5(a[3], a[8], a[13], a[18], a[23]);
+    const uint32_t c4 = x5(a[4], a[9], a[14], a[19], a[24]);
+    const uint32_t r0 = rot<1>(c0), r1 = rot<1>(c1), r2 = rot<1>(c2), r3 = rot<1>(c3), r4 = rot<1>(c4);
+#define TH0(v) ((v) ^ c4 ^ r1)
+#define TH1(v) ((v) ^ c0 ^ r2)
+#define TH2(v) ((v) ^ c1 ^ r3)
+#define TH3(v) ((v) ^ c2 ^ r4)
+#define TH4(v) ((v) ^ c3 ^ r0)
+    const uint32_t b0 = TH0(a[0]);
+    const uint32_t b10 = rot<1>(TH1(a[1]));
+    const uint32_t b20 = rot<62>(TH2(a[2]));
+    const uint32_t b5 = rot<28>(TH3(a[3]));
+    const uint32_t b15 = rot<27>(TH4(a[4]));
+    const uint32_t b16 = rot<36>(TH0(a[5]));
+    const uint32_t b1 = rot<44>(TH1(a[6]));
+    const uint32_t b11 = rot<6>(TH2(a[7]));
+    const uint32_t b21 = rot<55>(TH3(a[8]));
+    const uint32_t b6 = rot<20>(TH4(a[9]));
+    const uint32_t b7 = rot<3>(TH0(a[10]));
+    const uint32_t b17 = rot<10>(TH1(a[11]));
+    const uint32_t b2 = rot<43>(TH2(a[12]));
+    const uint32_t b12 = rot<25>(TH3(a[13]));
+    const uint32_t b22 = rot<39>(TH4(a[14]));
+    const uint32_t b23 = rot<41>(TH0(a[15]));
+    const uint32_t b8 = rot<45>(TH1(a[16]));
+    const uint32_t b18 = rot<15>(TH2(a[17]));
+    const uint32_t b3 = rot<21>(TH3(a[18]));
+    const uint32_t b13 = rot<8>(TH4(a[19]));
+    const uint32_t b14 = rot<18>(TH0(a[20]));
+    const uint32_t b24 = rot<2>(TH1(a[21]));
+    const uint32_t b9 = rot<61>(TH2(a[22]));
+    const uint32_t b19 = rot<56>(TH3(a[23]));
+    const uint32_t b4 = rot<14>(TH4(a[24]));
+#undef TH0
+#undef TH1
+#undef TH2
+#undef TH3
+#undef TH4
+    a[0] = ch(b0, b1, b2) ^ rc; a[1] = ch(b1, b2, b3); a[2] = ch(b2, b3, b4); a[3] = ch(b3, b4, b0); a[4] = ch(b4, b0, b1);
+    a[5] = ch(b5, b6, b7); a[6] = ch(b6, b7, b8); a[7] = ch(b7, b8, b9); a[8] = ch(b8, b9, b5); a[9] = ch(b9, b5, b6);
+    a[10] = ch(b10, b11, b12); a[11] = ch(b11, b12, b13); a[12] = ch(b12, b13, b14); a[13] = ch(b13, b14, b10); a[14] = ch(b14, b10, b11);
+    a[15] = ch(b15, b16, b17); a[16] = ch(b16, b17, b18); a[17] = ch(b17, b18, b19); a[18] = ch(b18, b19, b15); a[19] = ch(b19, b15, b16);
+    a[20] = ch(b20, b21, b22); a[21] = ch(b21, b22, b23); a[22] = ch(b22, b23, b24); a[23] = ch(b23, b24, b20); a[24] = ch(b24, b20, b21);
+}
+
+// Keccak-f[1600] on the half of the state this lane holds (hi = 0 / 1); must be executed by all 32 lanes of the warp
+__device__ __forceinline__ void keccak_f_pair(uint32_t (&a)[25], uint32_t hi) {
+    const uint32_t* rc = reinterpret_cast<const uint32_t*>(c_keccak_rc) + hi;
+#pragma unroll 4
+    for (int r = 0; r < 24; ++r) round(a, rc[2 * r]);
+}
+
+__device__ __forceinline__ uint32_t warp_max(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w > v ? w : v;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(32) agw_absorb_pair_kernel(AgState* __restrict__ st, const uint8_t* __restrict__ ring, size_t ring_cap,
+                                                              const unsigned long long* __restrict__ wend, const unsigned long long* __restrict__ win_off,
+                                                              size_t n_aggs) {
+    // word k of lane t of the next block at stage[buf][k][t] (cp.async while the current block is permuted, as in the thread kernel)
+    __shared__ __align__(4) uint32_t stage[2][KECCAK_RATE_LANES][32];
+    const int t = threadIdx.x;
+    const uint32_t hi = (uint32_t)(t & 1);
+    const size_t j = (size_t)blockIdx.x * 16 + (size_t)(t >> 1);
+    const bool valid = j < n_aggs;
+    AgState* s = st + (valid ? j : 0);
+    bool act = valid && s->phase == 0;
+    unsigned long long rpos = 0, end = 0;
+    bool closing = false;
+    if (act) {
+        const unsigned long long we = wend[j];
+        if (we & AGW_TEXT_OVERRUN) {   // the writer overwrote bytes this sponge had not absorbed: never hash them
+            act = false;
+        } else {
+            const uint32_t absorbed = s->absorbed + (uint32_t)(win_off[j + 1] - win_off[j]);
+            closing = absorbed == s->total;
+            rpos = s->rpos;
+            end = we & ~AGW_TEXT_FLAGS;
+        }
+    }
+    const uint32_t nblk = act ? (uint32_t)((end - rpos) / KECCAK_RATE) : 0u;
+    const bool work = act && (nblk > 0 || closing);
+    uint32_t a[25], sv[25];
+    const uint32_t* sa = reinterpret_cast<const uint32_t*>(s->a) + hi;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) { a[k] = work ? sa[2 * k] : 0u; sv[k] = a[k]; }
+    const uint8_t* base = ring + (valid ? j : 0) * ring_cap + 4 * hi;
+    auto fetch = [&](unsigned long long pos, int buf) {   // this lane's 4 bytes of each of the 17 words of the block at message offset pos
+        const uint8_t* src = base + (pos % ring_cap);
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&stage[buf][k][t]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + 8 * k) : "memory");
+        }
+    };
+    const uint32_t maxblk = warp_max(nblk);
+    int buf = 0;
+    if (nblk > 0) fetch(rpos, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (uint32_t b = 0; b < maxblk; ++b) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const bool mine = b < nblk;
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) a[k] ^= mine ? stage[buf][k][t] : 0u;
+        buf ^= 1;
+        if (b + 1 < nblk) fetch(rpos + (unsigned long long)(b + 1) * KECCAK_RATE, buf);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        keccak_f_pair(a, hi);
+        if (b + 1 == nblk) {
+#pragma unroll
+            for (int k = 0; k < 25; ++k) sv[k] = a[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 25; ++k) a[k] = sv[k];
+    rpos += (unsigned long long)nblk * KECCAK_RATE;
+    if (__any_sync(0xffffffffu, closing)) {   // last (partial) block with SHAKE padding; rem < 136
+        if (closing) {
+            const uint32_t rem = (uint32_t)(end - rpos);
+            const uint32_t* bw = reinterpret_cast<const uint32_t*>(base + (rpos % ring_cap));
+#pragma unroll
+            for (int k = 0; k < KECCAK_RATE_LANES; ++k) {
+                const uint32_t off = 8u * k + 4u * hi;   // byte offset of this lane's half of word k
+                uint32_t w = 0;
+                if (off < rem) {
+                    w = bw[2 * k];
+                    const uint32_t vb = rem - off;
+                    if (vb < 4) w &= (1u << (8 * vb)) - 1u;
+                }
+                if (rem >= off && rem < off + 4) w ^= 0x1Fu << (8 * (rem - off));
+                if (k == 16 && hi) w ^= 0x80000000u;
+                a[k] ^= w;
+            }
+        }
+        keccak_f_pair(a, hi);
+        if (!closing) {
+#pragma unroll
+            for (int k = 0; k < 25; ++k) a[k] = sv[k];
+        }
+    }
+    if (valid && s->phase == 0 && !act) { if (!hi) s->phase = 0xDEAD; return; }   // overrun (act was cleared above)
+    if (!act) return;
+    if (work) {
+        uint32_t* da = reinterpret_cast<uint32_t*>(s->a) + hi;
+#pragma unroll
+        for (int k = 0; k < 25; ++k) da[2 * k] = a[k];
+    }
+    if (!hi) {
+        s->absorbed += (uint32_t)(win_off[j + 1] - win_off[j]);
+        if (closing) { s->rpos = end; s->phase = 1; s->bpos = 0; }
+        else s->rpos = rpos;
+    }
+}
+
+// squeezes whole blocks into the aggregate's XOF buffer (same layout as agw_squeeze_thread_kernel)
+__global__ void __launch_bounds__(32) agw_squeeze_pair_kernel(AgState* __restrict__ st, const unsigned long long* __restrict__ win_off, size_t n_aggs,
+                                                               uint32_t n_ag, uint8_t* __restrict__ xof, size_t xof_cap, uint32_t* __restrict__ bpos_out) {
+    const int t = threadIdx.x;
+    const uint32_t hi = (uint32_t)(t & 1);
+    const size_t j = (size_t)blockIdx.x * 16 + (size_t)(t >> 1);
+    const bool valid = j < n_aggs;
+    AgState* s = st + (valid ? j : 0);
+    const unsigned long long cnt = valid ? win_off[j + 1] - win_off[j] : 0ULL;
+    const bool act = valid && cnt != 0 && s->phase == 1;
+    const uint32_t bpos = act ? s->bpos : 0u;
+    const unsigned long long need = (unsigned long long)bpos + cnt * n_ag;   // bytes counted from the start of the current block
+    const uint32_t nperm = act && need > 0 ? (uint32_t)((need - 1) / KECCAK_RATE) : 0u;   // trips of `while (o + 136 < need)`
+    uint32_t a[25], sv[25];
+    const uint32_t* sa = reinterpret_cast<const uint32_t*>(s->a) + hi;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) { a[k] = act ? sa[2 * k] : 0u; sv[k] = a[k]; }
+    uint32_t* out = reinterpret_cast<uint32_t*>(xof + (valid ? j : 0) * xof_cap) + hi;
+    if (act) {
+#pragma unroll
+        for (int k = 0; k < KECCAK_RATE_LANES; ++k) __stcs(out + 2 * k, a[k]);
+    }
+    const uint32_t maxperm = warp_max(nperm);
+    for (uint32_t it = 0; it < maxperm; ++it) {
+        keccak_f_pair(a, hi);
+        if (it < nperm) {
+            uint32_t* ob = out + (size_t)(it + 1) * (KECCAK_RATE / 4);
+#pragma unroll
+            for (int k = 0; k < KECCAK_RATE_LANES; ++k) __stcs(ob + 2 * k, a[k]);
+        }
+        if (it + 1 == nperm) {
+#pragma unroll
+            for (int k = 0; k < 25; ++k) sv[k] = a[k];
+        }
+    }
+    if (!act) return;
+    uint32_t* da = reinterpret_cast<uint32_t*>(s->a) + hi;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) da[2 * k] = sv[k];
+    if (!hi) {
+        bpos_out[j] = bpos;
+        s->bpos = (uint32_t)(need - (unsigned long long)nperm * KECCAK_RATE);
+        s->produced += (uint32_t)cnt;
+    }
+}
+
+}  // namespace pairag
+
 static void add_seg(std::vector<uint8_t>& pool, SegTable& t, int id, const std::string& s) {
     while (pool.size() % 16) pool.push_back(0);
     t.off[id] = (uint32_t)pool.size();
@@ -1226,7 +1466,15 @@ static int warp_smem_attr(const fz_ctx* ctx) {
 
 // one serial sponge per aggregate: a warp per aggregate minimises the chain latency, a thread per aggregate maximises
 // throughput once there are enough aggregates to fill the machine
-static bool use_warp(const fz_ctx* ctx, size_t n_aggs) { return ctx->hash_ag_impl == 3 || (ctx->hash_ag_impl == 0 && n_aggs < 2816); }
+// ... and two lanes per aggregate in between (ring-fed kernels only; the one-shot hash_ag_* kernels keep the two-way choice)
+static bool use_warp(const fz_ctx* ctx, size_t n_aggs) { return ctx->hash_ag_impl == 3 || ((ctx->hash_ag_impl == 0 || ctx->hash_ag_impl == 4) && n_aggs < 2816); }
+// measured crossovers (profiles/r02_keccak_lab2_v23.txt, r01_keccak_lab_v3.txt): a warp per chain runs 197 cycles per round at two chains per
+// sub-partition (1,184 chains; the time-sliced absorb keeps that up to 1,776) and 247 at three; the pair layout 250 up to 9,472 chains, 351 at
+// 18,944, 545 at 37,888; a thread per chain 370-400 up to 18,944 chains, 554 at 37,888 and wins from there on (4.27 against 3.94 G Keccak-f/s)
+static int chain_layout(const fz_ctx* ctx, size_t n_aggs) {   // 2 thread, 3 warp, 4 pair
+    if (ctx->hash_ag_impl == 2 || ctx->hash_ag_impl == 3 || ctx->hash_ag_impl == 4) return ctx->hash_ag_impl;
+    return n_aggs <= 1776 ? 3 : n_aggs < 40960 ? 4 : 2;
+}
 
 int launch_hash_ag_absorb(const fz_ctx* ctx, void* state, const int32_t* vk_l_s, const int32_t* vk_r_s, const uint8_t* dg_s, const int32_t* c_hat_s,
                           const unsigned long long* win_off, size_t n_aggs, cudaStream_t st) {
@@ -1265,7 +1513,8 @@ static int chain_carveout(const fz_ctx* ctx) {
     if (!attr_needed(ctx, ATTR_CHAIN_CARVEOUT)) return 0;
     const void* ks[] = {(const void*)agw_absorb_thread_kernel,          (const void*)agw_squeeze_thread_kernel,
                         (const void*)warpag::agw_absorb_warp_kernel<24>, (const void*)warpag::agw_squeeze_warp_kernel<24>,
-                        (const void*)warpag::agw_absorb_sliced_kernel<24>};
+                        (const void*)warpag::agw_absorb_sliced_kernel<24>, (const void*)pairag::agw_absorb_pair_kernel,
+                        (const void*)pairag::agw_squeeze_pair_kernel};
     for (const void* k : ks)
         if (check(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "chain kernel carve-out")) return -2;
     return 0;
@@ -1275,8 +1524,11 @@ int launch_agw_absorb(const fz_ctx* ctx, void* state, const uint8_t* ring, size_
                       const unsigned long long* win_off, size_t n_aggs, cudaStream_t st) {
     if (n_aggs == 0) return 0;
     if (chain_carveout(ctx)) return -2;
-    if (use_warp(ctx, n_aggs))
+    const int layout = chain_layout(ctx, n_aggs);
+    if (layout == 3)
         warpag::agw_absorb_warp_kernel<24><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
+    else if (layout == 4)
+        pairag::agw_absorb_pair_kernel<<<(unsigned)((n_aggs + 15) / 16), 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
     else
         agw_absorb_thread_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
     return check(cudaGetLastError(), "agw_absorb launch");
@@ -1295,8 +1547,12 @@ int launch_agw_squeeze(const fz_ctx* ctx, void* state, const unsigned long long*
                        cudaStream_t st) {
     if (n_aggs == 0) return 0;
     if (chain_carveout(ctx)) return -2;
-    if (use_warp(ctx, n_aggs))
+    const int layout = chain_layout(ctx, n_aggs);
+    if (layout == 3)
         warpag::agw_squeeze_warp_kernel<24><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
+    else if (layout == 4)
+        pairag::agw_squeeze_pair_kernel<<<(unsigned)((n_aggs + 15) / 16), 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap,
+                                                                                     bpos_out);
     else
         agw_squeeze_thread_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
     return check(cudaGetLastError(), "agw_squeeze launch");

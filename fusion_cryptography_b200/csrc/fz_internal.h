@@ -19,7 +19,7 @@ struct fz_ctx {
     void* scratch;
     size_t scratch_bytes;
     int sort_smem_max;  // dynamic shared memory sort_kernel may use on this device (opt-in made in scheme_init)
-    int hash_ag_impl;   // 0 auto (warp per aggregate below 2816 aggregates, thread per aggregate above), 2 thread, 3 warp
+    int hash_ag_impl;   // 0 auto (ring-fed chains: a warp per aggregate up to 1,776 aggregates, two lanes per aggregate up to 40,960, a thread per aggregate above), 2 thread, 3 warp, 4 pair
     int buffered_hash;  // 1: format text into HBM scratch first (fz_hash.cu); 0 (default): streaming generator (fz_hashstream.cu)
 };
 
@@ -99,7 +99,7 @@ int launch_agw_decode(const fz_ctx* ctx, const uint8_t* xof, size_t xof_cap, con
 
 // fz_sample.cu
 int sample_init_tables(fz_ctx* ctx);
-void set_sample_impl(int v);   // 0 general kernel, 1 dense kernel with the byte tile, 2 dense kernel with 16-byte stores (default)
+void set_sample_impl(int v);   // 0 general kernel, 1 dense kernel with the byte tile (default), 2 dense kernel with 16-byte stores
 int launch_sample(const fz_ctx* ctx, int mode, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, uint32_t bound, int weight,
                   int32_t* out, cudaStream_t st);
 int launch_sample_ring(int d, uint32_t q, int mode, const uint32_t* keys, int key_stride, const int32_t* klen, size_t n, uint32_t bound, int weight,

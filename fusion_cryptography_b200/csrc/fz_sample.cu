@@ -428,9 +428,11 @@ int sample_init_tables(fz_ctx* ctx) {
     return check(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMP_SMEM), "sample_kernel smem attr");
 }
 
-// which kernel serves the dense secret-key case (fz_set_option "sample_impl"): 0 the general kernel, 1 sample_dense_kernel<1> (byte tile), 2 sample_dense_kernel<0>
-// (16-byte stores; the default: 1.079 ms against 1.100 ms and 1.473 ms for 262,144 generators, profiles/r02_sample_lab_v2.txt)
-static int g_sample_impl = 2;
+// which kernel serves the dense secret-key case (fz_set_option "sample_impl"): 0 the general kernel, 1 sample_dense_kernel<1> (byte tile, the default),
+// 2 sample_dense_kernel<0> (16-byte stores).  262,144 generators through fz_sample_coef into a buffer that is not in L2: 1.098 ms (1), 1.428 ms (2),
+// 1.520 ms (0); the 16-byte stores only look as good as the tile (1.079 ms, profiles/r02_sample_lab_v2.txt) when the output still sits in L2 from a
+// memset -- half-sector writes to lines that are not resident cost a fill each, the tile's 128-byte coalesced stores do not.
+static int g_sample_impl = 1;
 void set_sample_impl(int v) { g_sample_impl = v; }
 
 // true when the dense kernel took the launch: dense weights, d <= 256 (the byte tile holds 256 rows), magnitudes that fit seven bits

@@ -69,10 +69,10 @@ def test_aggregate_verify_batch(engines, oracle, scheme_golden, secpar):
     kpos = KeyBatch(sk_hat=kb.sk_hat[idx].contiguous(), vk_l=kb.vk_l[idx].contiguous(), vk_r=kb.vk_r[idx].contiguous())
     sigs = eng.sign(kpos, msgs)
     # one window / windows of 5 and of 1 sorted positions per aggregate (the resumable sponge of hash_ag), with a warp
-    # per aggregate (impl 3) and a thread per aggregate (impl 2): all bit-identical
+    # per aggregate (impl 3), a thread per aggregate (impl 2) and a lane pair per aggregate (impl 4): all bit-identical
     ref_aggs = None
     try:
-        for impl in (3, 2):
+        for impl in (3, 2, 4):
             eng.ctx.set_option("hash_ag_impl", impl)
             for max_pos in (1 << 17, 40, 8):
                 aggs = eng.aggregate(kb.vk_l, kb.vk_r, msgs, sigs, counts, sel=sel_t, max_positions=max_pos)
@@ -115,6 +115,48 @@ def test_aggregate_verify_batch(engines, oracle, scheme_golden, secpar):
     assert codes == [0, 0, 3, 0, 0, 0, 0, 0]
     with pytest.raises(IndexError):
         eng.aggregate(kb.vk_l, kb.vk_r, [], sigs, [0])
+
+
+@pytest.mark.parametrize("secpar", [128, 256])
+def test_pair_layout_many_ragged_aggregates(engines, secpar):
+    """The lane-pair chain kernels (fz_hashstream.cu pairag::, 16 aggregates per warp, warp-uniform trip counts with per-pair snapshots): 45 aggregates
+    of 1..13 signers -- three warps, the last one partly empty, every warp with pairs that finish at different blocks -- over windows of all, 64 and
+    16 sorted positions, bit-identical with the warp-per-aggregate kernels; verify accepts all and rejects a tampered one."""
+    eng = engines[secpar]
+    pool = 64
+    seeds = (3 * 10**6 + 2 * np.arange(pool)).astype(np.uint64)
+    kb = eng.keygen(seeds)
+    rng = np.random.default_rng(secpar)
+    counts = [int(c) for c in rng.integers(1, 14, size=45)]
+    sel, msgs = [], []
+    for j, c in enumerate(counts):
+        start = (11 * j) % pool
+        for i in range(c):
+            sel.append((start + i) % pool)
+            msgs.append(f"a{j}-m{i}".encode())
+    sel_t = torch.tensor(sel, dtype=torch.int32)
+    from fusion_cryptography_b200.batch import KeyBatch
+    idx = sel_t.cuda().long()
+    kpos = KeyBatch(sk_hat=kb.sk_hat[idx].contiguous(), vk_l=kb.vk_l[idx].contiguous(), vk_r=kb.vk_r[idx].contiguous())
+    sigs = eng.sign(kpos, msgs)
+    out = {}
+    try:
+        for impl in (3, 4):
+            eng.ctx.set_option("hash_ag_impl", impl)
+            for max_pos in (1 << 17, 64, 16):
+                aggs = eng.aggregate(kb.vk_l, kb.vk_r, msgs, sigs, counts, sel=sel_t, max_positions=max_pos)
+                codes = host(eng.verify(kb.vk_l, kb.vk_r, msgs, aggs, counts, sel=sel_t, max_positions=max_pos))
+                assert codes.tolist() == [0] * len(counts), (impl, max_pos)
+                out[(impl, max_pos)] = aggs.clone()
+        bad = out[(4, 16)].clone()
+        bad[17, 0, 3] += 1
+        codes = host(eng.verify(kb.vk_l, kb.vk_r, msgs, bad, counts, sel=sel_t, max_positions=16)).tolist()
+        assert codes == [3 if j == 17 else 0 for j in range(len(counts))]
+    finally:
+        eng.ctx.set_option("hash_ag_impl", 0)
+    ref = out[(3, 1 << 17)]
+    for k, v in out.items():
+        assert torch.equal(v, ref), k
 
 
 def test_single_aggregate_sharded_world1(engines, oracle):

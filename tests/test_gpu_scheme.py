@@ -333,9 +333,9 @@ def test_buffered_and_streaming_hash_agree(ctxs, oracle, secpar):
         ctx.set_option("buffered_hash", 0)
         ctx.set_option("hash_ag_impl", 0)
     # fourth implementation: the ring-fed kernels (text by a warp per signer, chains that only permute, parallel decode), with a warp
-    # and with a thread per aggregate
+    # with a thread and with two lanes (a lane pair) per aggregate
     try:
-        for impl in (3, 2):
+        for impl in (3, 2, 4):
             ctx.set_option("hash_ag_impl", impl)
             c = ctx.hash_ch(dev(vl), dev(vr), dev(dg, np.uint8))
             out[("ring", impl)] = (host(c), host(ctx.hash_ag_fast(dev(vl), dev(vr), dev(dg, np.uint8), c, counts)))
@@ -353,7 +353,7 @@ def test_buffered_and_streaming_hash_agree(ctxs, oracle, secpar):
 
 
 @pytest.mark.parametrize("secpar", [128, 256])
-@pytest.mark.parametrize("impl", [3, 2])
+@pytest.mark.parametrize("impl", [3, 2, 4])
 def test_hash_pipeline_stays_inside_its_byte_buffers(ctxs, secpar, impl):
     """compute-sanitizer is not available on this pool, so the byte rings and XOF buffers of the ring-fed aggregation hash (fz_hash_ag_text,
     fz_hash_ag_absorb_ring, fz_hash_ag_squeeze_xof, fz_hash_ag_decode) are carved out of the middle of larger buffers whose head and tail hold
@@ -406,7 +406,8 @@ def test_hash_pipeline_stays_inside_its_byte_buffers(ctxs, secpar, impl):
         ctx.set_option("hash_ag_impl", 0)
 
 
-def test_text_ring_overrun_is_detected_not_hashed(ctxs):
+@pytest.mark.parametrize("impl", [0, 2, 4])
+def test_text_ring_overrun_is_detected_not_hashed(ctxs, impl):
     """Ring discipline of the windowed aggregation hash (advisor finding): when a window's text would overwrite bytes a sponge has not absorbed
     yet, the writer flags the aggregate (bit 62 of wend), the absorb call poisons its sponge and the host sees a sponge that never closed --
     the hash of overwritten bytes is never produced.  Provoked with a ring of the minimum size against a window of several signers."""
@@ -427,7 +428,11 @@ def test_text_ring_overrun_is_detected_not_hashed(ctxs):
     wend = ctx.hash_ag_text(vl, vr, dg, c, agg_off, agg_of, agg_off, n_aggs, n_total, 0, text_pos, ring, cap, state=state)
     flags = (wend.cpu().numpy().astype(np.uint64) >> np.uint64(62)) & np.uint64(3)
     assert flags.tolist() == [3, 2], flags           # aggregate 0: complete + overrun; aggregate 1 (one signer): complete, fits
-    ctx.hash_ag_absorb_ring(state, ring, cap, wend, agg_off, n_aggs)
+    try:
+        ctx.set_option("hash_ag_impl", impl)      # a warp, a thread, a lane pair per aggregate: each must refuse the overrun ring
+        ctx.hash_ag_absorb_ring(state, ring, cap, wend, agg_off, n_aggs)
+    finally:
+        ctx.set_option("hash_ag_impl", 0)
     assert ctx.hash_ag_open_sponges(state, n_aggs) == 1
     # without the state the writer cannot know (the caller's discipline, as before): no flag
     text_pos.zero_()

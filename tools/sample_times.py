@@ -12,6 +12,8 @@ kd = torch.from_numpy(keys.view(np.int32)).cuda(); kl = torch.ones(n, dtype=torc
 out = torch.empty((n, 256), dtype=torch.int32, device="cuda")
 def run():
     ctx._chk(ctx.lib.fz_sample_coef(ctx._h, _ptr(kd), C.c_int(8), _ptr(kl), C.c_size_t(n), C.c_int(52), C.c_int(256), _ptr(out), ctx._stream()))
+impl = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+ctx.set_option("sample_impl", impl)   # 0 general kernel, 1 dense kernel with the byte tile, 2 dense kernel with 16-byte stores
 for _ in range(5): run()
 torch.cuda.synchronize()
 best = 1e9
@@ -19,4 +21,4 @@ for _ in range(10):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); run(); b.record(); torch.cuda.synchronize()
     best = min(best, a.elapsed_time(b))
-print(f"{os.environ.get('FUSION_B200_LIB', 'default')}: sample_coef {n} generators: {best:.3f} ms  checksum {int(out.sum().item())}")
+print(f"{os.environ.get('FUSION_B200_LIB', 'default')} sample_impl {impl}: sample_coef {n} generators: {best:.3f} ms  checksum {int(out.sum().item())}")
