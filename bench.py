@@ -953,17 +953,21 @@ def leg_verify(dv: Dev, ctx, eng, secpar=256, full=True):
     perms = args.verify_aggs * cap * perms_per_signer / t_ver
     gbs = n_dis * cap * (ell + 1) * d * 4 / t_sum / 1e9
     rec = ncu_record("aggregate_kernel")
-    thread_kernels = na >= 2816
+    # the chain layout launch_agw_absorb / launch_agw_squeeze pick for this many aggregates on one GPU (fz_hashstream.cu chain_layout)
+    layout = "warp" if na <= 1776 else ("pair" if na < 40960 else "thread")
+    thread_kernels = layout != "warp"
+    chain_kernel = {"warp": "warpag::agw_absorb/squeeze_warp_kernel (a warp per aggregate)", "pair": "pairag::agw_absorb/squeeze_pair_kernel (two lanes per aggregate)",
+                    "thread": "agw_absorb/squeeze_thread_kernel (a thread per aggregate)"}[layout]
     out.update({
         "metric": METRIC["verify"], "scaling": "strong", "dtype": "u32 / u64 (Keccak lanes)", "tampered_1pct_rejected": tamper_ok,
         "single_capacity_aggregate": single, "one_aggregate_sharded": sharded,
         "roofline": {
             "bound": "int32 alu pipe (LOP3 / SHF)" if thread_kernels else "latency of the serial SHAKE256 chains (one warp per aggregate)",
-            "kernel": "hash_ch_stream_kernel + agw_absorb/squeeze_thread_kernel" if thread_kernels else "hash_ch_stream_kernel + warpag::agw_absorb/squeeze_warp_kernel",
+            "kernel": "hash_ch_stream_kernel + " + chain_kernel, "chain_layout": layout,
             "achieved": perms, "peak": alu_peak, "unit": "Keccak-f[1600]/s", "frac": perms / alu_peak, "traffic": None, "sm_mhz_used": mhz,
             "how": f"whole leg: {perms_per_signer:.1f} permutations per verified signature (hash_ch {PERMS_CH[secpar]:.0f} + hash_ag {PERMS_AG[secpar]:.1f}) / leg time, against the ALU-pipe "
-                   "peak at the sampled clock (see the sign leg); with fewer than 2,816 aggregates per GPU the aggregation hash runs a warp per chain and the leg is bound by "
-                   "chain latency instead",
+                   "peak at the sampled clock (see the sign leg; a permutation in the pair layout costs 1.31 x the ALU-pipe instructions of the thread layout the peak "
+                   "is counted in); with at most 1,776 aggregates per GPU the aggregation hash runs a warp per chain and the leg is bound by chain latency instead",
             "chain_latency": {"cycles_per_round_single_chain": t_one_v * mhz * 1e6 / (chain_perms * 24.0), "lab_floor_cycles_per_round": 168,
                               "note": "single capacity aggregate: verify seconds * SM clock / (chain permutations * 24 rounds), includes sort, challenges and the weighted sum; "
                                       "lab floor = tools/keccak_lab.cu V17 alone on a sub-partition (profiles/r01_keccak_lab_v3.txt); the five-lanes-per-chain layout "

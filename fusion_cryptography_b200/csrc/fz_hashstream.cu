@@ -729,14 +729,20 @@ __device__ __forceinline__ uint32_t warp_max(uint32_t v) {
     return v;
 }
 
-__global__ void __launch_bounds__(32) agw_absorb_pair_kernel(AgState* __restrict__ st, const uint8_t* __restrict__ ring, size_t ring_cap,
-                                                              const unsigned long long* __restrict__ wend, const unsigned long long* __restrict__ win_off,
-                                                              size_t n_aggs) {
+// CTAs of four warps (64 aggregates): the four warps of a CTA sit on the four sub-partitions of its SM whatever else is resident, single-warp CTAs
+// do not spread evenly (measured: 592 single-warp CTAs ran like two warps per sub-partition).  No CTA-wide barrier anywhere.
+constexpr int PAIR_WARPS = 4;
+__global__ void __launch_bounds__(PAIR_WARPS * 32) agw_absorb_pair_kernel(AgState* __restrict__ st, const uint8_t* __restrict__ ring, size_t ring_cap,
+                                                                          const unsigned long long* __restrict__ wend,
+                                                                          const unsigned long long* __restrict__ win_off, size_t n_aggs) {
     // word k of lane t of the next block at stage[buf][k][t] (cp.async while the current block is permuted, as in the thread kernel)
-    __shared__ __align__(4) uint32_t stage[2][KECCAK_RATE_LANES][32];
-    const int t = threadIdx.x;
+    __shared__ __align__(4) uint32_t stage_all[PAIR_WARPS][2][KECCAK_RATE_LANES][32];
+    uint32_t (*stage)[KECCAK_RATE_LANES][32] = stage_all[threadIdx.x >> 5];
+    const int t = threadIdx.x & 31;
     const uint32_t hi = (uint32_t)(t & 1);
-    const size_t j = (size_t)blockIdx.x * 16 + (size_t)(t >> 1);
+    const size_t grp = (size_t)blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
+    if (grp * 16 >= n_aggs) return;   // warp-uniform
+    const size_t j = grp * 16 + (size_t)(t >> 1);
     const bool valid = j < n_aggs;
     AgState* s = st + (valid ? j : 0);
     bool act = valid && s->phase == 0;
@@ -827,12 +833,19 @@ __global__ void __launch_bounds__(32) agw_absorb_pair_kernel(AgState* __restrict
     }
 }
 
-// squeezes whole blocks into the aggregate's XOF buffer (same layout as agw_squeeze_thread_kernel)
-__global__ void __launch_bounds__(32) agw_squeeze_pair_kernel(AgState* __restrict__ st, const unsigned long long* __restrict__ win_off, size_t n_aggs,
-                                                               uint32_t n_ag, uint8_t* __restrict__ xof, size_t xof_cap, uint32_t* __restrict__ bpos_out) {
-    const int t = threadIdx.x;
+// squeezes whole blocks into the aggregate's XOF buffer (same layout as agw_squeeze_thread_kernel).
+// A time-sliced form (launches of at most 592 warps with a block budget, the resting groups rotating, for the 625 warps of 10^4 aggregates) was built
+// and measured: 458 ms against 465 ms of squeeze kernels over the 109 windows of the configs[4] batch, i.e. nothing -- the squeeze phase is not paced by
+// the 33 sub-partitions that carry two warps but by the decode / gather / target kernels of the previous window sharing the issue slots (4.2 ms per
+// window = 2.7 ms of bare chain + 1.5 ms of side-stream work; 2.7 ms per window at 2,500 aggregates, where that work is four times smaller).  Not kept.
+__global__ void __launch_bounds__(PAIR_WARPS * 32) agw_squeeze_pair_kernel(AgState* __restrict__ st, const unsigned long long* __restrict__ win_off,
+                                                                           size_t n_aggs, uint32_t n_ag, uint8_t* __restrict__ xof, size_t xof_cap,
+                                                                           uint32_t* __restrict__ bpos_out) {
+    const int t = threadIdx.x & 31;
     const uint32_t hi = (uint32_t)(t & 1);
-    const size_t j = (size_t)blockIdx.x * 16 + (size_t)(t >> 1);
+    const size_t grp = (size_t)blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
+    if (grp * 16 >= n_aggs) return;   // warp-uniform
+    const size_t j = grp * 16 + (size_t)(t >> 1);
     const bool valid = j < n_aggs;
     AgState* s = st + (valid ? j : 0);
     const unsigned long long cnt = valid ? win_off[j + 1] - win_off[j] : 0ULL;
@@ -1528,7 +1541,7 @@ int launch_agw_absorb(const fz_ctx* ctx, void* state, const uint8_t* ring, size_
     if (layout == 3)
         warpag::agw_absorb_warp_kernel<24><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
     else if (layout == 4)
-        pairag::agw_absorb_pair_kernel<<<(unsigned)((n_aggs + 15) / 16), 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
+        pairag::agw_absorb_pair_kernel<<<(unsigned)((n_aggs + 63) / 64), pairag::PAIR_WARPS * 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
     else
         agw_absorb_thread_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
     return check(cudaGetLastError(), "agw_absorb launch");
@@ -1551,8 +1564,8 @@ int launch_agw_squeeze(const fz_ctx* ctx, void* state, const unsigned long long*
     if (layout == 3)
         warpag::agw_squeeze_warp_kernel<24><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
     else if (layout == 4)
-        pairag::agw_squeeze_pair_kernel<<<(unsigned)((n_aggs + 15) / 16), 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap,
-                                                                                     bpos_out);
+        pairag::agw_squeeze_pair_kernel<<<(unsigned)((n_aggs + 63) / 64), pairag::PAIR_WARPS * 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag,
+                                                                                                          xof, xof_cap, bpos_out);
     else
         agw_squeeze_thread_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
     return check(cudaGetLastError(), "agw_squeeze launch");

@@ -81,6 +81,7 @@ int launch_agw_absorb_sliced(const fz_ctx* ctx, void* state, const uint8_t* ring
                              size_t first_active, size_t n_active, unsigned long long budget_blocks, cudaStream_t st);
 int launch_agw_squeeze(const fz_ctx* ctx, void* state, const unsigned long long* win_off, size_t n_aggs, uint8_t* xof, size_t xof_cap, uint32_t* bpos_out,
                        cudaStream_t st);
+
 // bit 63 of the per-aggregate message length written by the text stage: the text is complete
 constexpr unsigned long long AGW_TEXT_COMPLETE = 1ULL << 63;
 // bit 62: the text writer found that this window's text would overwrite ring bytes the aggregate's sponge has not absorbed yet (ring too small
