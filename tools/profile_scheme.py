@@ -21,9 +21,9 @@ msgs = ctx.pack_messages([f"msg-{i:07d}".encode() for i in range(nk)])
 # keygen (sample_kernel, ntt_fwd, matvec) + sign (sponge_bytes, hash_ch_stream, ntt_fwd, sign_mac)
 vk_l, vk_r, sigs = eng.keygen_sign(seeds, msgs, chunk=nk)
 torch.cuda.synchronize()
-# windowed aggregate / verify: a warp per aggregate (few aggregates) and a thread per aggregate (many)
+# windowed aggregate / verify: a warp per aggregate (few aggregates), a lane pair per aggregate (the middle range) and a thread per aggregate (many)
 dg = ctx.hash_msg(msgs)
-for impl, na, ns in ((3, 1184, 96), (2, 9472, 12)):
+for impl, na, ns in ((3, 1184, 96), (4, 9472, 12), (2, 9472, 12)):
     ctx.set_option("hash_ag_impl", impl)
     base = (np.arange(na)[:, None] * 97 + np.arange(ns)[None, :]) % nk
     sel = torch.from_numpy(base.reshape(-1).astype(np.int32)).to(dev)

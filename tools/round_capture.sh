@@ -13,7 +13,7 @@ $NCU --set full --import-source on -k regex:ntt_pass_kernel -s 3 -c 2 -f -o gpur
 $SCHEME > gpurun_out/${TAG}_plain_scheme.log 2>&1 &&
 $NCU --metrics gpu__time_duration.sum -c 4000 --csv --log-file gpurun_out/${TAG}_launches_scheme.csv $SCHEME > gpurun_out/${TAG}_ncu_l2.log 2>&1
 $SCHEME > /dev/null 2>&1 &&
-$NCU --set full --import-source on -k regex:'sample_kernel|hash_ch_stream_kernel|sign_rows_kernel|aggregate_kernel|agw_absorb|agw_squeeze|verify_' -c 40 -f -o gpurun_out/prof_${TAG}_scheme $SCHEME > gpurun_out/${TAG}_ncu_f2.log 2>&1
+$NCU --set full --import-source on -k regex:'sample_dense_kernel|hash_ch_stream_kernel|sign_rows_kernel|aggregate_kernel|agw_absorb|agw_squeeze|agw_format|agw_decode|verify_' -c 48 -f -o gpurun_out/prof_${TAG}_scheme $SCHEME > gpurun_out/${TAG}_ncu_f2.log 2>&1
 for f in gpurun_out/prof_${TAG}_*.ncu-rep; do
   ncu -i $f --page raw --csv > ${f%.ncu-rep}_raw.csv 2> /dev/null
   # gpurun merges at most 64 MiB back: keep the raw page, drop reports above 8 MiB
