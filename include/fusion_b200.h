@@ -39,7 +39,11 @@ const char* fz_last_error(void);
 int fz_version(void);
 /* named integer parameter of the level ("d", "ell", "capacity", "n_ch", "n_ag", ...); -1 if unknown */
 long long fz_param(const fz_ctx* ctx, const char* name);
-/* named integer option; "buffered_hash" = 1 selects the HBM-scratch hashing pipeline instead of the streaming one (same results) */
+/* named integer option (every choice gives the same results; the options exist for the cross-checking tests and the measurements):
+ *   "buffered_hash" = 1   the HBM-scratch hashing pipeline instead of the streaming one
+ *   "hash_ag_impl"        layout of the serial SHAKE256 chains of hash_ag: 0 chosen by the number of aggregates (default), 2 a thread,
+ *                         3 a warp, 4 a lane pair per aggregate
+ *   "sample_impl"         kernel serving the dense secret-key sampler: 1 byte-tile kernel (default), 2 16-byte-store kernel, 0 the general kernel */
 int fz_set_option(fz_ctx* ctx, const char* name, long long value);
 
 /* algebra/polynomials.py:394-411 transform(coefficient -> NTT) == algebra/ntt.py:216-291
