@@ -720,7 +720,7 @@ def leg_sign(dv: Dev, ctx, eng):
     idx = np.arange(lo, hi)
     seeds = (10**6 + 2 * idx).astype(np.uint64)
     msgs = [f"msg-{i:07d}".encode() for i in idx]
-    chunk = 65536
+    chunk = 2 * 640 * int(ctx.param("sm_count"))                    # Engine.keygen_sign's default: two full waves of the challenge-hash kernel
     eng.keygen_sign(seeds[:256], msgs[:256])                        # warm-up
     pm = ctx.pack_messages(msgs)                                    # messages resident in HBM before the timed region
     eng.keygen_sign(seeds, pm, chunk=chunk, keep_sigs=False)        # first full-size call pays cudaMalloc; the timed one reuses the buffers
@@ -734,7 +734,7 @@ def leg_sign(dv: Dev, ctx, eng):
     if cs:
         cs.mark(w0, w1)
         clocks = cs.stop()
-    launches_per_chunk = 9   # seeds->keys, sampler, NTT, 2 x (A-sum, product), prehash, challenge hash + decode, NTT, signature rows
+    launches_per_chunk = 9   # seeds->keys, sampler, NTT, 2 x (A-sum, product), prehash, challenge hash + decode, NTT, signature rows (the rows on a second stream)
     # kernels of the leg, one by one, on a resident chunk
     nc = min(nk, chunk)
     kb = eng.keygen(seeds[:nc])

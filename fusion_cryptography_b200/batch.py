@@ -31,6 +31,7 @@ VERIFY_REASONS = {
 class Tuning:
     """Knobs of the windowed aggregate / verify pipeline (measured defaults; the tests use them to reach every code path with small batches)."""
     agg_slots: Optional[int] = None   # warp-chains served per time-sliced absorb launch; None = 8 per SM (two per sub-partition)
+    sign_overlap: bool = True         # keygen_sign: signature rows of chunk k on the side stream beside the challenge hash of chunk k + 1
     sliced: bool = True               # time-slice the absorb phase for batches a little above agg_slots chains
     sliced_window_div: int = 2        # sliced mode: windows are this many times shorter (the byte rings hold the backlog of the resting chains)
     sliced_budget: float = 1.01       # sliced mode: blocks per launch = expected blocks of one window x this
@@ -72,10 +73,17 @@ class Engine:
             return self.ctx.sign_mac(keys.sk_l, keys.sk_r, c_hat, out=out)   # general: ell distinct rows
         return self.ctx.sign_mac_rows(keys.sk_hat, c_hat, out=out)
 
-    def keygen_sign(self, seeds, msgs: Sequence[bytes], chunk: int = 65536, keep_sigs: bool = True):
+    def keygen_sign(self, seeds, msgs: Sequence[bytes], chunk: Optional[int] = None, keep_sigs: bool = True):
         """BASELINE config[2]: keygen + sign of many one-time keys; secret keys never reach HBM as ell rows.
-        Returns (vk_l, vk_r, sigs or None); with keep_sigs=False signatures of each chunk overwrite one buffer."""
+        Returns (vk_l, vk_r, sigs or None); with keep_sigs=False signatures of each chunk overwrite one buffer.
+        chunk defaults to two full waves of the challenge-hash kernel (a thread per signer, 64-thread CTAs, ten resident per SM = 640 signers
+        per SM and wave: 189,440 keys on a B200): half of the leg is that ALU-bound kernel, and a chunk that fills only part of a wave leaves the
+        same part of the pipes idle.  10^6 keys on one stream: 66.9 ms in chunks of 65,536 (0.69 waves), 60.9 ms at 94,720, 58.7 ms at 189,440;
+        with the two-stream pipeline below 57.8 / 54.7 / 52.9-53.9 ms (tools/sign_chunk_probe.py)."""
         import numpy as np
+
+        if chunk is None:
+            chunk = 2 * 640 * int(self.ctx.param("sm_count"))
 
         seeds = np.asarray(seeds, dtype=np.uint64)
         n = len(seeds)
@@ -86,9 +94,51 @@ class Engine:
         vk_l = torch.empty((n, self.d), dtype=torch.int32, device=dev)
         vk_r = torch.empty((n, self.d), dtype=torch.int32, device=dev)
         sigs = torch.empty((n if keep_sigs else min(chunk, n), self.ell, self.d), dtype=torch.int32, device=dev)
-        for lo in range(0, n, chunk):
+        ctx = self.ctx
+        if not self.tuning.sign_overlap or n <= chunk:
+            for lo in range(0, n, chunk):
+                hi = min(n, lo + chunk)
+                ctx.keygen_sign(self.A, seeds_d[lo:hi], msgs[lo:hi], vk_l[lo:hi], vk_r[lo:hi], sigs[lo:hi] if keep_sigs else sigs[: hi - lo])
+            return vk_l, vk_r, (sigs if keep_sigs else None)
+        # Two streams.  The signature rows of chunk k (HBM writes, 87 KB per key) run on the side stream beside the challenge hash of chunk k + 1
+        # (ALU pipe) -- NOT beside its sampler: a sampler CTA owns the whole shared memory of its SM, so nothing co-resides with it and rows launched
+        # then would simply run first.  Measured: 10^6 keys in 52.5 ms against 58.1 ms (tools/sign_overlap_probe.py).  With keep_sigs=False two
+        # signature buffers alternate.
+        main, side = torch.cuda.current_stream(dev), self._side_stream()
+        sig2 = None if keep_sigs else torch.empty_like(sigs)
+        sk_hat = [torch.empty((min(chunk, n), 2, self.d), dtype=torch.int32, device=dev) for _ in range(2)]
+        side.wait_stream(main)
+        prev = None
+
+        def rows(p):
+            k, lo, hi, c_hat = p
+            out = sigs[lo:hi] if keep_sigs else (sigs if k & 1 == 0 else sig2)[: hi - lo]
+            ctx.sign_mac_rows(sk_hat[k & 1][: hi - lo], c_hat, out=out)
+
+        done = [None, None]
+        for k, lo in enumerate(range(0, n, chunk)):
             hi = min(n, lo + chunk)
-            self.ctx.keygen_sign(self.A, seeds_d[lo:hi], msgs[lo:hi], vk_l[lo:hi], vk_r[lo:hi], sigs[lo:hi] if keep_sigs else sigs[: hi - lo])
+            if done[k & 1] is not None:
+                main.wait_event(done[k & 1])          # rows of chunk k - 2 have read this secret-key buffer
+            ctx.keygen(self.A, seeds_d[lo:hi], want_sk=False, out=(sk_hat[k & 1][: hi - lo], vk_l[lo:hi], vk_r[lo:hi]))
+            dg = ctx.hash_msg(msgs[lo:hi])
+            if prev is not None:
+                sampled = torch.cuda.Event()
+                sampled.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(sampled)
+                    rows(prev)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                done[prev[0] & 1] = ev
+                prev[3].record_stream(side)
+            c_hat = ctx.hash_ch(vk_l[lo:hi], vk_r[lo:hi], dg)
+            prev = (k, lo, hi, c_hat)
+        rows(prev)
+        main.wait_stream(side)
+        for t in (sigs, sig2, sk_hat[0], sk_hat[1]):
+            if t is not None:
+                t.record_stream(side)
         return vk_l, vk_r, (sigs if keep_sigs else None)
 
     def keygen_rows(self, row_seeds) -> KeyBatch:

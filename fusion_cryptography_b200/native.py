@@ -744,8 +744,9 @@ def sample_ntt(self, seeds) -> torch.Tensor:
     return out
 
 
-def keygen(self, A, seeds, want_sk: bool = True):
-    """fusion.py:338-373 for u64 seeds.  Returns (sk_l, sk_r, sk_hat, vk_l, vk_r); sk_l / sk_r are None unless want_sk."""
+def keygen(self, A, seeds, want_sk: bool = True, out=None):
+    """fusion.py:338-373 for u64 seeds.  Returns (sk_l, sk_r, sk_hat, vk_l, vk_r); sk_l / sk_r are None unless want_sk.
+    `out` may supply (sk_hat [n, 2, d], vk_l [n, d], vk_r [n, d]) buffers to write into."""
     A = self._dev(A)
     if not isinstance(seeds, torch.Tensor):
         import numpy as np
@@ -756,9 +757,15 @@ def keygen(self, A, seeds, want_sk: bool = True):
     ws = self._ws(self.lib.fz_keygen_workspace(self._h, C.c_size_t(n)))
     sk_l = torch.empty((n, self.ell, self.d), dtype=torch.int32, device=self.device) if want_sk else None
     sk_r = torch.empty((n, self.ell, self.d), dtype=torch.int32, device=self.device) if want_sk else None
-    sk_hat = torch.empty((n, 2, self.d), dtype=torch.int32, device=self.device)
-    vk_l = torch.empty((n, self.d), dtype=torch.int32, device=self.device)
-    vk_r = torch.empty((n, self.d), dtype=torch.int32, device=self.device)
+    if out is not None:
+        sk_hat, vk_l, vk_r = out
+        for t, shape in ((sk_hat, (n, 2, self.d)), (vk_l, (n, self.d)), (vk_r, (n, self.d))):
+            if tuple(t.shape) != shape or t.dtype != torch.int32 or not t.is_contiguous() or t.device != self.device:
+                raise ValueError("keygen: out buffers must be contiguous int32 device tensors of shapes [n, 2, d], [n, d], [n, d]")
+    else:
+        sk_hat = torch.empty((n, 2, self.d), dtype=torch.int32, device=self.device)
+        vk_l = torch.empty((n, self.d), dtype=torch.int32, device=self.device)
+        vk_r = torch.empty((n, self.d), dtype=torch.int32, device=self.device)
     self._chk(self.lib.fz_keygen(self._h, _ptr(A), _ptr(seeds), C.c_size_t(n), _ptr(sk_l), _ptr(sk_r), _ptr(sk_hat), _ptr(vk_l), _ptr(vk_r), _ptr(ws),
                                  C.c_size_t(ws.numel()), self._stream()))
     return sk_l, sk_r, sk_hat, vk_l, vk_r

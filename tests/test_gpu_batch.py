@@ -32,7 +32,19 @@ def test_keygen_sign_batch_vs_oracle(engines, oracle, scheme_golden, secpar):
     n = 300
     seeds = (10**6 + 2 * np.arange(n)).astype(np.uint64)      # SURVEY C3 seeds (stride 2, quirk Q2)
     msgs = [f"msg-{i:07d}".encode() for i in range(n)]
-    vk_l, vk_r, sigs = eng.keygen_sign(seeds, msgs, chunk=128)   # 3 chunks, last one ragged
+    vk_l, vk_r, sigs = eng.keygen_sign(seeds, msgs, chunk=128)   # 3 chunks, last one ragged; two-stream pipeline (signature rows beside the next chunk's hash)
+    # the same on one stream, chunk sizes that leave 1 / 2 / 5 chunks, and with the signatures of each chunk overwriting alternating buffers
+    eng.tuning.sign_overlap = False
+    try:
+        v2l, v2r, s2 = eng.keygen_sign(seeds, msgs, chunk=128)
+    finally:
+        eng.tuning.sign_overlap = True
+    assert torch.equal(v2l, vk_l) and torch.equal(v2r, vk_r) and torch.equal(s2, sigs)
+    for ch in (300, 150, 64, None):
+        v3l, v3r, s3 = eng.keygen_sign(seeds, msgs, chunk=ch)
+        assert torch.equal(v3l, vk_l) and torch.equal(v3r, vk_r) and torch.equal(s3, sigs), ch
+        v4l, v4r, none = eng.keygen_sign(seeds, msgs, chunk=ch, keep_sigs=False)
+        assert none is None and torch.equal(v4l, vk_l) and torch.equal(v4r, vk_r), ch
     oracle.set_threads(oracle.max_threads())
     sk_l, sk_r, ovl, ovr = oracle.keygen_batch(secpar, A, seeds)
     assert np.array_equal(host(vk_l), ovl) and np.array_equal(host(vk_r), ovr)
