@@ -264,6 +264,9 @@ class Engine:
     # the sorted signer positions: window w holds positions [w*P, (w+1)*P) of every aggregate.  All chains advance
     # together (latency-bound chains need every aggregate in flight), memory is O(n_aggs * P) instead of O(positions),
     # and the per-signer work of window w+1 (gather, hash_ch) runs on a second stream while window w is absorbed.
+    def _window_positions(self, max_positions: Optional[int]) -> int:
+        return int(max_positions) if max_positions is not None else 3 * 640 * int(self.ctx.param("sm_count"))
+
     def _side_stream(self):
         if getattr(self, "_side", None) is None:
             self._side = torch.cuda.Stream(device=self.ctx.device)
@@ -397,10 +400,11 @@ class Engine:
             main.wait_stream(side)
 
     def aggregate(self, vk_l, vk_r, msgs: Optional[Sequence[bytes]], sigs, counts: Sequence[int], sel: Optional[torch.Tensor] = None,
-                  sig_sel: Optional[torch.Tensor] = None, max_positions: int = 1 << 18, digests: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  sig_sel: Optional[torch.Tensor] = None, max_positions: Optional[int] = None, digests: Optional[torch.Tensor] = None) -> torch.Tensor:
         """counts[j] signers per aggregate; position p (0 <= p < sum(counts)) signs msgs[p] with key row sel[p] and
         signature row sig_sel[p] (both default to p).  `digests` ([positions, 32] prehashes from hash_msg) may replace msgs.
-        `max_positions` bounds the signer positions resident per window.  Returns [n_aggs, ell, d]."""
+        `max_positions` bounds the signer positions resident per window (default: three full waves of the challenge-hash kernel, 284,160 on a B200:
+        a window's hash_ch launch then leaves no partly filled wave).  Returns [n_aggs, ell, d]."""
         total = int(sum(counts))
         if any(c <= 0 for c in counts):
             raise IndexError("list index out of range")  # the reference indexes sorted_signatures[0] (fusion.py:670)
@@ -409,7 +413,7 @@ class Engine:
         ctx, dev = self.ctx, self.ctx.device
         n_aggs = len(counts)
         dg_all = digests if digests is not None else ctx.hash_msg(msgs)
-        state, wins, sel_d, side, P = self._hash_windows(vk_l, vk_r, dg_all, counts, sel, max_positions, keep_c=False)
+        state, wins, sel_d, side, P = self._hash_windows(vk_l, vk_r, dg_all, counts, sel, self._window_positions(max_positions), keep_c=False)
         zsel = sig_sel.to(dev, dtype=torch.int32).contiguous() if sig_sel is not None else None
         acc = {"out": None}
 
@@ -424,7 +428,7 @@ class Engine:
         return out.reshape(n_aggs, self.ell, self.d)
 
     def verify(self, vk_l, vk_r, msgs: Optional[Sequence[bytes]], aggs, counts: Sequence[int], sel: Optional[torch.Tensor] = None,
-               n_msgs: Optional[Sequence[int]] = None, max_positions: int = 1 << 18, digests: Optional[torch.Tensor] = None) -> torch.Tensor:
+               n_msgs: Optional[Sequence[int]] = None, max_positions: Optional[int] = None, digests: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Returns uint8 codes per aggregate (0 = (True, ""), else VERIFY_REASONS[code])."""
         ctx, dev = self.ctx, self.ctx.device
         cap = ctx.capacity
@@ -439,7 +443,7 @@ class Engine:
         if n_aggs == 0:
             return torch.zeros(0, dtype=torch.uint8, device=dev)
         dg_all = digests if digests is not None else ctx.hash_msg(msgs)
-        state, wins, sel_d, side, P = self._hash_windows(vk_l, vk_r, dg_all, counts, sel, max_positions, keep_c=True)
+        state, wins, sel_d, side, P = self._hash_windows(vk_l, vk_r, dg_all, counts, sel, self._window_positions(max_positions), keep_c=True)
         acc = {"target": None}
 
         def consume(wd, alpha_w):     # fusion.py:706-714 over this window's signers
