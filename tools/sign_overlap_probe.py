@@ -62,3 +62,4 @@ for hp in (0, 1):
     print(f"piped, high-priority rows stream {hp}: {tm:.2f} ms = {n / tm / 1e3:.2f} M sign/s  same={ok}", flush=True)
 # measured on B200, 10^6 keys, chunk 189,440: serial 58.1 ms; piped 52.5 ms; with the rows kernel capped at 1 / 2 / 4 CTAs per SM 51.6 / 52.8 / 52.8 ms;
 # with the hash kernel capped at 9 / 8 / 7 CTAs per SM (dynamic shared-memory padding) 55.1 / 57.1 / 58.5 ms; a high-priority stream for the rows: no change
+# the rows kernel as 1-4 CTAs of 32-128 threads per SM (so that it fits beside ten resident hash CTAs from the start): 53.5-61.5 ms, never better than 52.8 ms
