@@ -171,6 +171,29 @@ def test_pair_layout_many_ragged_aggregates(engines, secpar):
         assert torch.equal(v, ref), k
 
 
+def test_chain_layout_is_chosen_by_the_number_of_aggregates(engines):
+    """No option set: 1,800 aggregates take the lane-pair chain kernels, 41,000 the thread-per-aggregate ones (fz_hashstream.cu chain_layout); both must
+    give what the warp-per-aggregate kernels give.  Aggregates of one and two signers keep the batches small."""
+    eng = engines[128]
+    pool = 64
+    kb = eng.keygen((4 * 10**6 + 2 * np.arange(pool)).astype(np.uint64))
+    for n_aggs, per in ((1800, 2), (41000, 1)):
+        counts = [per] * n_aggs
+        sel = torch.tensor([(5 * j + i) % pool for j in range(n_aggs) for i in range(per)], dtype=torch.int32)
+        msgs = [b"m%d" % (p % 97) for p in range(n_aggs * per)]
+        from fusion_cryptography_b200.batch import KeyBatch
+        idx = sel.cuda().long()
+        sigs = eng.sign(KeyBatch(sk_hat=kb.sk_hat[idx].contiguous(), vk_l=kb.vk_l[idx].contiguous(), vk_r=kb.vk_r[idx].contiguous()), msgs)
+        auto = eng.aggregate(kb.vk_l, kb.vk_r, msgs, sigs, counts, sel=sel)
+        assert bool((eng.verify(kb.vk_l, kb.vk_r, msgs, auto, counts, sel=sel) == 0).all())
+        try:
+            eng.ctx.set_option("hash_ag_impl", 3)
+            ref = eng.aggregate(kb.vk_l, kb.vk_r, msgs, sigs, counts, sel=sel)
+        finally:
+            eng.ctx.set_option("hash_ag_impl", 0)
+        assert torch.equal(auto, ref), n_aggs
+
+
 def test_single_aggregate_sharded_world1(engines, oracle):
     from fusion_cryptography_b200 import parallel
 
