@@ -397,7 +397,10 @@ size_t fz_hash_ag_ring_bytes(const fz_ctx* ctx, size_t max_window) {   // per ag
     return (need + 271) / 272 * 272;
 }
 size_t fz_hash_ag_xof_bytes(const fz_ctx* ctx, size_t max_window) { return ((max_window * (size_t)ctx->n_ag + 2 * 136 + 32) + 15) & ~(size_t)15; }
-size_t fz_hash_ag_text_workspace(const fz_ctx* ctx, size_t n_window) { (void)ctx; return r256(n_window * 4) + r256(n_window * 8) + 256; }
+size_t fz_hash_ag_text_workspace(const fz_ctx* ctx, size_t n_window) {
+    (void)ctx;
+    return r256(n_window * 4) + r256(n_window * 8) + r256(n_window * agw_int_text_stride()) + r256(n_window * 4) + 256;
+}
 
 int fz_hash_ag_text(fz_ctx* ctx, const int32_t* vk_l_w, const int32_t* vk_r_w, const uint8_t* dg_w, const int32_t* c_hat_w, const uint64_t* win_off,
                     const uint32_t* agg_of, const uint64_t* agg_off, size_t n_aggs, size_t n_window, uint32_t w0, uint64_t* text_pos, uint8_t* ring,
@@ -408,10 +411,12 @@ int fz_hash_ag_text(fz_ctx* ctx, const int32_t* vk_l_w, const int32_t* vk_r_w, c
     Carver cv(ws, ws_bytes);
     uint32_t* piece_len = cv.take<uint32_t>(n_window);
     unsigned long long* piece_off = cv.take<unsigned long long>(n_window);
+    uint8_t* int_text = cv.take<uint8_t>(n_window * agw_int_text_stride());   // the decimal prehash of every signer of the window, 80-byte slots
+    uint32_t* int_len = cv.take<uint32_t>(n_window);
     FZ_REQUIRE(cv.ok, "fz_hash_ag_text: workspace too small (see fz_hash_ag_text_workspace)");
     return launch_agw_text(ctx, vk_l_w, vk_r_w, dg_w, c_hat_w, (const unsigned long long*)win_off, agg_of, (const unsigned long long*)agg_off, n_aggs,
-                           n_window, w0, (unsigned long long*)text_pos, piece_len, piece_off, (unsigned long long*)wend_out, ring, ring_cap, state,
-                           (cudaStream_t)stream);
+                           n_window, w0, (unsigned long long*)text_pos, piece_len, piece_off, int_text, int_len, (unsigned long long*)wend_out, ring, ring_cap,
+                           state, (cudaStream_t)stream);
 }
 
 int fz_hash_ag_absorb_ring(fz_ctx* ctx, void* state, const uint8_t* ring, size_t ring_cap, const uint64_t* wend, const uint64_t* win_off, size_t n_aggs,

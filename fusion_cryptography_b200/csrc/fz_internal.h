@@ -93,8 +93,9 @@ size_t ag_state_rpos_offset();
 size_t agw_max_piece();
 int launch_agw_text(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, const int32_t* c_hat, const unsigned long long* win_off,
                     const uint32_t* agg_of, const unsigned long long* agg_off, size_t n_aggs, size_t n_win, uint32_t w0, unsigned long long* text_pos,
-                    uint32_t* piece_len, unsigned long long* piece_off, unsigned long long* wend, uint8_t* ring, size_t ring_cap, const void* state,
-                    cudaStream_t st);
+                    uint32_t* piece_len, unsigned long long* piece_off, uint8_t* int_text, uint32_t* int_len, unsigned long long* wend, uint8_t* ring,
+                    size_t ring_cap, const void* state, cudaStream_t st);
+size_t agw_int_text_stride();
 int launch_agw_decode(const fz_ctx* ctx, const uint8_t* xof, size_t xof_cap, const uint32_t* bpos, const unsigned long long* win_off, const uint32_t* agg_of,
                       size_t n_win, int32_t* coef_out, cudaStream_t st);
 
