@@ -729,14 +729,33 @@ __global__ void __launch_bounds__(128) agw_decode_kernel(const uint8_t* __restri
         jdraw[t] = (int)acc;
     }
     __syncwarp();
-    if (L == 0) {
-        for (int t = 0; t < n_swaps; ++t) {
-            const int idx = d - 1 - t;
-            const int jj = t < n_draw ? jdraw[t] : 0;
+    if (L == 0) {   // the draws that have bytes: a data-dependent sequence of swaps, one lane
+        for (int t = 0; t < n_draw; ++t) {
+            const int idx = d - 1 - t, jj = jdraw[t];
             const int8_t tmp = cf[idx]; cf[idx] = cf[jj]; cf[jj] = tmp;
         }
     }
     __syncwarp();
+    // the draws past the end of the squeezed bytes all see b"" -> 0 (quirk Q4): swap(cf[idx], cf[0]) for idx = a, a - 1, ..., b is the rotation
+    // cf[a] <- cf[0], cf[k] <- cf[k + 1] (b <= k < a), cf[0] <- cf[b]: done by the whole warp (about as many steps as there are real draws at secpar 256)
+    const int a = d - 1 - n_draw, b = d - n_swaps;
+    if (n_draw < n_swaps && a >= b) {
+        int8_t v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int k = b + L + 32 * r;
+            v[r] = k < a ? cf[k + 1] : (k == a ? cf[0] : (int8_t)0);
+        }
+        const int8_t vb = cf[b];
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int k = b + L + 32 * r;
+            if (k <= a) cf[k] = v[r];
+        }
+        if (L == 0) cf[0] = vb;
+        __syncwarp();
+    }
     int32_t* o = coef_out + i * d;
     for (int k = L; k < d; k += 32) o[k] = (int32_t)cf[k];
 }
