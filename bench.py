@@ -53,8 +53,12 @@ WORKLOAD = {
 }
 # algorithmic HBM bytes per polynomial: NTT/INTT 1 KiB in + 1 KiB out, pointwise 3 KiB; the fused pass reads a and b_hat, writes the result
 BYTES = {"ntt_pass": 3072, "ntt_fwd": 2048, "pointwise_mul": 3072, "ntt_inv": 2048}
-# Keccak-f[1600] per signer (secpar 256): hash_ch 48 absorb + 77 squeeze; hash_ag about 70 absorb + 29.2 squeeze
-PERMS_CH = {256: 125.0, 128: 27.0}
+# Keccak-f[1600] EXECUTED per signer.  hash_ch at secpar 256: 48 absorb (the text is 6.4 KB) + 61 squeeze -- the reference asks SHAKE256 for 10,436 bytes
+# = 77 blocks (fusion.py:520-524, the figure of SURVEY 8d), but its decoder reads only the first 8,423 (fusion.py:436-438, 473: signums, omega magnitudes,
+# d - 1 - omega index draws), so the kernel stops after the 62nd block (ctx.n_ch_used); at 128: 15 + 7 (1,075 of 1,551 bytes are read).  The roofline
+# counts the permutations that run, not the ones the reference's digest() call computes and throws away.  hash_ag: about 70 absorb + 29.2 squeeze, all read.
+PERMS_CH = {256: 109.0, 128: 22.0}
+PERMS_CH_REFERENCE = {256: 125.0, 128: 27.0}
 PERMS_AG = {256: 99.2, 128: 30.0}
 # thread-per-sponge permutation: 179 ALU-pipe (LOP3 / SHF / IADD3) instructions per round once theta is folded into three-input LOP3s (cuobjdump of
 # hash_ch_stream_kernel, tools/keccak_lab.cu V4); an SM sub-partition issues one ALU-pipe warp instruction every 2 cycles (tools/ubench_int.cu)
@@ -805,7 +809,8 @@ def leg_sign(dv: Dev, ctx, eng):
                          "keygen_rows_ms_per_chunk": 1000 * t_kgr, "chunk": ngm, "generators_per_sec": 2 * ell * ngm / t_kgr},
         "roofline": {"bound": "int32 alu pipe (LOP3 / SHF)", "kernel": "hash_ch_stream_kernel", "achieved": perms, "peak": alu_peak, "unit": "Keccak-f[1600]/s",
                      "frac": perms / alu_peak, "traffic": None,
-                     "how": f"{PERMS_CH[SECPAR]:.0f} permutations per challenge; peak = SMs * 4 sub-partitions * SM clock / (24 rounds * {KECCAK_ALU_INSTR_PER_ROUND} ALU-pipe instructions "
+                     "how": f"{PERMS_CH[SECPAR]:.0f} permutations executed per challenge (48 absorb + 61 squeeze; the reference's digest() call computes {PERMS_CH_REFERENCE[SECPAR]:.0f}, "
+                            f"the last 15 squeezed blocks are never read by its decoder and are not computed here); peak = SMs * 4 sub-partitions * SM clock / (24 rounds * {KECCAK_ALU_INSTR_PER_ROUND} ALU-pipe instructions "
                             f"* {ALU_CYCLES_PER_WARP_INSTR} issue cycles / 32 lanes) at the sampled clock",
                      "sm_mhz_used": mhz, "ncu_alu_pipe_pct": rec.get("ncu_alu_pct"), "ncu_issue_active_pct": rec.get("ncu_issue_active_pct"),
                      "share_of_leg": t_hash * (nk / nc) / t_ks,
