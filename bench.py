@@ -818,7 +818,9 @@ def leg_sign(dv: Dev, ctx, eng):
                          "sign_rows_kernel": {"bound": "hbm (writes)", "GB/s": nc * ell * d * 4 / t_rows / 1e9, "frac": nc * ell * d * 4 / t_rows / 1e9 / peak, "ms": 1000 * t_rows,
                                               "bytes": "ell KiB written per key"},
                          "sign_mac_kernel (general rows)": {"bound": "hbm", "GB/s": ngm * 3 * ell * d * 4 / t_macg / 1e9, "frac": ngm * 3 * ell * d * 4 / t_macg / 1e9 / peak,
-                                                            "ms": 1000 * t_macg, "bytes": "3 * ell KiB per key (SURVEY 8d: 257,024 B)"},
+                                                            "ms": 1000 * t_macg, "bytes": "3 * ell KiB per key (SURVEY 8d: 257,024 B)",
+                                                            "note": "the peak is a 1:1 read / write copy (torch copy_); this kernel reads two bytes per byte it writes, and "
+                                                                    "HBM reads are faster than writes, so a fraction slightly above 1 of THAT peak is possible (nominal HBM3e: 8 TB/s)"},
                          "keygen (sampler + NTT + A.sk)": {"ms_per_chunk": 1000 * t_kg, "keys": nc}},
                      "hbm_peak": peak, "hbm_peak_source": peak_src},
         "e2e": {"value": e2e_n * world / e2e_s, "unit": UNIT["sign"], "h2d_bytes_per_step": moved["h2d_bytes"], "d2h_bytes_per_step": moved["d2h_bytes"],

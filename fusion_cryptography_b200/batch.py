@@ -37,6 +37,9 @@ class Tuning:
     sliced_budget: float = 1.01       # sliced mode: blocks per launch = expected blocks of one window x this
     sliced_extra_launches: int = 2    # sliced mode: rotating launches after the last window, before the one that closes everything
     overlap: bool = True              # per-signer work of window w+1 on a side stream beside the sponge chains of window w
+    side_priority: int = 0            # CUDA priority of that side stream (-1 = scheduled ahead of the main stream's kernels; measured: no effect)
+    text_stream: bool = False         # the message text of window w on a stream of its own, so that hash_ch of window w + 1 runs beside it (measured: slower)
+    lookahead: int = 2                # windows the host may enqueue ahead of the sponge chains (each holds about 3.1 KB per signer position)
 
 
 @dataclass
@@ -269,8 +272,13 @@ class Engine:
 
     def _side_stream(self):
         if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(device=self.ctx.device)
+            self._side = torch.cuda.Stream(device=self.ctx.device, priority=self.tuning.side_priority)
         return self._side
+
+    def _text_stream(self):
+        if getattr(self, "_side2", None) is None:
+            self._side2 = torch.cuda.Stream(device=self.ctx.device)
+        return self._side2
 
     def _sorted_hash(self, vk_l, vk_r, digests_pos, counts, sel):
         """One-shot sort -> gather -> hash_ch -> hash_ag with every position resident (small batches, kernel timing)."""
@@ -315,8 +323,17 @@ class Engine:
         # against 1.18 s, of 10,000 aggregates 2.80 s against 3.10 s.
         overlap = tn.overlap
         prep = self._side_stream() if overlap else main   # one side stream per engine: the caching allocator pools blocks per stream
+        # Tuning.text_stream puts the message text (a warp per signer, half of the ALU pipe idle) on a stream of its own, so that hash_ch of window
+        # w + 1 -- the ALU-saturating kernel -- also runs beside the text and the whole chain step of window w instead of starting after the text
+        # (at 10^4 capacity aggregates a window is 17.3 ms: chains beside hash_ch 10.7, hash_ch alone 3.8, text alone 2.7).  Measured, bit-identical,
+        # and SLOWER: verify 2.43 s against 2.25 s (5,000 aggregates: 1.42 against 1.27 s) -- the chain kernels, whose warps then share their
+        # sub-partitions with hash_ch for their whole run, take 1.57 s instead of 1.08 s, which costs more than the 0.32 s of waiting it removes
+        # (profiles/r02_agg_probe_text_stream.txt).  Off by default; a higher CUDA priority for the side stream changed nothing either.
+        txt = self._text_stream() if (overlap and tn.text_stream) else prep
         if overlap:
             prep.wait_stream(main)
+            if txt is not prep:
+                txt.wait_stream(main)
         wins = []
         for w in range(0, max(max_count, 1), P):
             cnt = np.clip(cnp - w, 0, P)
@@ -325,8 +342,9 @@ class Engine:
             np.cumsum(cnt, out=woff_np[1:])
             if len(wins) >= 2:
                 if overlap:
-                    prep.wait_event(wins[-2]["absorbed"])    # ring space of window w - 2 is free once its chain step is done
-                wins[-2]["absorbed"].synchronize()           # and the host stays at most two windows ahead
+                    txt.wait_event(wins[-2]["absorbed"])     # ring space of window w - 2 is free once its chain step is done
+            if len(wins) >= max(2, tn.lookahead):
+                wins[-max(2, tn.lookahead)]["absorbed"].synchronize()   # the host stays at most `lookahead` windows ahead
             with torch.cuda.stream(prep):
                 win_off = torch.from_numpy(woff_np).to(dev, non_blocking=True)
                 cnt_d = torch.from_numpy(cnt).to(dev, non_blocking=True)
@@ -336,9 +354,17 @@ class Engine:
                 pos = perm.index_select(0, idx)
                 vl_w, vr_w, dg_w = ctx.gather_sorted(vk_l, vk_r, dg_all, pos, sel=sel_d)
                 c_w = ctx.hash_ch(vl_w, vr_w, dg_w)
+                if txt is not prep:
+                    hashed = torch.cuda.Event()
+                    hashed.record(prep)
+            with torch.cuda.stream(txt):
+                if txt is not prep:
+                    txt.wait_event(hashed)
+                    for t in (vl_w, vr_w, dg_w, c_w, win_off, agg_of):
+                        t.record_stream(txt)                 # allocated on the side stream, read by the text kernels
                 wend = ctx.hash_ag_text(vl_w, vr_w, dg_w, c_w, win_off, agg_of, agg_off, n_aggs, n_win, w, text_pos, ring, ring_cap, state=state)
                 ready = torch.cuda.Event()
-                ready.record(prep)
+                ready.record(txt)
             if overlap:
                 for t in (win_off, wend, pos, agg_of, c_w):
                     t.record_stream(main)                # allocated on the side stream, read on the main stream
@@ -366,6 +392,8 @@ class Engine:
         if overlap:
             for t in (ring, text_pos, agg_ids, agg_off, perm, sel_d):
                 t.record_stream(prep)
+                if txt is not prep:
+                    t.record_stream(txt)
         return state, wins, sel_d, prep, P
 
     def _squeeze_windows(self, state, wins, n_aggs, P, side, consume):

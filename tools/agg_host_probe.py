@@ -5,7 +5,9 @@ import numpy as np, torch
 from fusion_cryptography_b200.batch import Engine
 
 na = int(sys.argv[1]) if len(sys.argv) > 1 else 1250
-eng = Engine(256, seed=42); ctx = eng.ctx; dev = ctx.device
+from fusion_cryptography_b200.batch import Tuning
+eng = Engine(256, seed=42, tuning=Tuning(side_priority=int(os.environ.get("FZ_SIDE_PRIO", "0")), text_stream=os.environ.get("FZ_TEXT_STREAM", "1") != "0",
+                                            lookahead=int(os.environ.get("FZ_LOOKAHEAD", "2")))); ctx = eng.ctx; dev = ctx.device
 if os.environ.get("FZ_AG_IMPL"): ctx.set_option("hash_ag_impl", int(os.environ["FZ_AG_IMPL"]))
 cap = ctx.capacity; nk = 65536
 seeds = (10**6 + 2 * np.arange(nk)).astype(np.uint64)
