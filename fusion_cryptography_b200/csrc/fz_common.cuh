@@ -72,7 +72,11 @@ __device__ __forceinline__ uint32_t mont_mul(uint32_t yr, int32_t b) {
 // any int32 -> lazy unsigned residue in [0, 2q)
 __device__ __forceinline__ uint32_t to_lazy(int32_t x) {
     uint32_t v = (uint32_t)x;
+#ifdef __CUDA_ARCH__
     asm("{ .reg .pred p; setp.lt.s32 p, %1, 0; @p add.u32 %0, %0, %2; }" : "+r"(v) : "r"(x), "r"(Q2));
+#else   // host build of the arithmetic unit tests (tests/test_modarith_host.py); never part of the library
+    if (x < 0) v += Q2;
+#endif
     return v;
 }
 
@@ -106,11 +110,19 @@ __device__ __forceinline__ int32_t mul_cent(int32_t a, int32_t b) { return cent_
 
 __device__ __forceinline__ int4 ld_stream(const int4* p) {
     int4 r;
+#ifdef __CUDA_ARCH__
     asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#else
+    r = *p;
+#endif
     return r;
 }
 __device__ __forceinline__ void st_stream(int4* p, const int4& v) {
+#ifdef __CUDA_ARCH__
     asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#else
+    *p = v;
+#endif
 }
 
 }  // namespace fz
