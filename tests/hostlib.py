@@ -1,0 +1,71 @@
+"""Builds and loads the host harnesses of tests/host/*.cpp -- the product's device headers (csrc/*.cuh) compiled with g++ for the CPU suite -- and the
+small call helpers the host tests share.  Test infrastructure only."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+import tempfile
+from math import ceil, log2
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUDA_INC = "/usr/local/cuda/include"
+Q = 2147465729
+_cache = {}
+_dir = None
+
+
+def load(name: str, cuda_headers: bool = False, pthread: bool = False) -> C.CDLL:
+    """tests/host/<name>.cpp -> shared library (built once per process); skips the calling test when the toolchain is missing."""
+    global _dir
+    if name in _cache:
+        return _cache[name]
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    if cuda_headers and not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("needs the CUDA headers")
+    if _dir is None:
+        _dir = tempfile.mkdtemp(prefix="fz_host_")
+    out = os.path.join(_dir, name + ".so")
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w"] + (["-pthread"] if pthread else []) + (["-I" + CUDA_INC] if cuda_headers else [])
+    subprocess.run(cmd + ["-o", out, os.path.join(ROOT, "tests", "host", name + ".cpp")], check=True)
+    _cache[name] = C.CDLL(out)
+    return _cache[name]
+
+
+def i32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int64).astype(np.int32))
+
+
+def ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ---- fz_format.cuh on the emulated warp
+def fmt_vk(lib, secpar, vl, vr) -> str:
+    buf = C.create_string_buffer(11264)
+    a, b = i32(vl), i32(vr)
+    n = lib.h_format_vk(C.c_int(1 if secpar == 256 else 0), C.c_int(len(a)), ptr(a), ptr(b), buf)
+    return buf.raw[:n].decode()
+
+
+def fmt_ch(lib, secpar, c) -> str:
+    buf = C.create_string_buffer(11264)
+    a = i32(c)
+    n = lib.h_format_ch(C.c_int(1 if secpar == 256 else 0), C.c_int(len(a)), ptr(a), buf)
+    return buf.raw[:n].decode()
+
+
+# ---- fz_decoder.cuh
+def byte_budget(log2_bias, d, norm_bound):
+    bound = max(1, min(Q // 2, norm_bound))                               # fusion.py:432
+    return bound, ceil((log2(bound) + 1 + log2_bias) / 8), ceil((log2(d) + log2_bias) / 8)     # fusion.py:433-434
+
+
+def host_decode(lib, b: bytes, log2_bias, d, norm_bound, weight):
+    bound, bpc, bpi = byte_budget(log2_bias, d, norm_bound)
+    out = np.full(d, 99, dtype=np.int32)
+    lib.h_decode(b, C.c_uint32(len(b)), C.c_int(d), C.c_int(weight), C.c_uint32(bound), C.c_int(bpc), C.c_int(bpi), ptr(out))
+    return out.tolist()

@@ -5,36 +5,23 @@ parameters.  No GPU needed."""
 import ctypes as C
 import json
 import os
-import shutil
-import subprocess
 from math import ceil, log2
 
 import numpy as np
 import pytest
+
+import hostlib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 Q = 2147465729
 
 
 @pytest.fixture(scope="module")
-def lib(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("needs g++")
-    out = str(tmp_path_factory.mktemp("decoder") / "decoder_host.so")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w", "-o", out, os.path.join(ROOT, "tests", "host", "decoder_host.cpp")], check=True)
-    return C.CDLL(out)
+def lib():
+    return hostlib.load("decoder_host")
 
 
-def byte_budget(log2_bias, d, norm_bound):
-    bound = max(1, min(Q // 2, norm_bound))                               # fusion.py:432
-    return bound, ceil((log2(bound) + 1 + log2_bias) / 8), ceil((log2(d) + log2_bias) / 8)     # fusion.py:433-434
-
-
-def host_decode(lib, b: bytes, log2_bias, d, norm_bound, weight):
-    bound, bpc, bpi = byte_budget(log2_bias, d, norm_bound)
-    out = np.full(d, 99, dtype=np.int32)
-    lib.h_decode(b, C.c_uint32(len(b)), C.c_int(d), C.c_int(weight), C.c_uint32(bound), C.c_int(bpc), C.c_int(bpi), out.ctypes.data_as(C.c_void_p))
-    return out.tolist()
+byte_budget, host_decode = hostlib.byte_budget, hostlib.host_decode
 
 
 def reference_decode(b: bytes, log2_bias, d, norm_bound, weight):

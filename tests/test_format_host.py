@@ -6,24 +6,19 @@ import ctypes as C
 import json
 import os
 import re
-import shutil
-import subprocess
 
 import numpy as np
 import pytest
+
+import hostlib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 Q = 2147465729
 
 
 @pytest.fixture(scope="module")
-def lib(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("needs g++")
-    out = str(tmp_path_factory.mktemp("format") / "format_host.so")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w", "-pthread", "-o", out, os.path.join(ROOT, "tests", "host", "format_host.cpp")],
-                   check=True)
-    return C.CDLL(out)
+def lib():
+    return hostlib.load("format_host", pthread=True)
 
 
 @pytest.fixture(scope="module")
@@ -31,18 +26,7 @@ def gold():
     return json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json"))), np.load(os.path.join(ROOT, "tests", "golden", "scheme_golden.npz"))
 
 
-def fmt_vk(lib, secpar, vl, vr):
-    buf = C.create_string_buffer(11264)
-    a = np.ascontiguousarray(np.asarray(vl, dtype=np.int64).astype(np.int32)); b = np.ascontiguousarray(np.asarray(vr, dtype=np.int64).astype(np.int32))
-    n = lib.h_format_vk(C.c_int(1 if secpar == 256 else 0), C.c_int(len(a)), a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), buf)
-    return buf.raw[:n].decode()
-
-
-def fmt_ch(lib, secpar, c):
-    buf = C.create_string_buffer(11264)
-    a = np.ascontiguousarray(np.asarray(c, dtype=np.int64).astype(np.int32))
-    n = lib.h_format_ch(C.c_int(1 if secpar == 256 else 0), C.c_int(len(a)), a.ctypes.data_as(C.c_void_p), buf)
-    return buf.raw[:n].decode()
+fmt_vk, fmt_ch = hostlib.fmt_vk, hostlib.fmt_ch
 
 
 @pytest.mark.parametrize("secpar", [128, 256])

@@ -6,12 +6,12 @@ import ctypes as C
 import hashlib
 import json
 import os
-import shutil
-import subprocess
 from math import ceil, log2
 
 import numpy as np
 import pytest
+
+import hostlib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -21,13 +21,8 @@ LEVEL = {128: (64, 27), 256: (256, 60)}      # secpar -> (degree, omega_ch)   (f
 
 
 @pytest.fixture(scope="module")
-def lib(tmp_path_factory):
-    if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
-        pytest.skip("needs g++ and the CUDA headers")
-    out = str(tmp_path_factory.mktemp("hashch") / "hashch_host.so")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w", "-I" + CUDA_INC, "-o", out, os.path.join(ROOT, "tests", "host", "hashch_host.cpp")],
-                   check=True)
-    return C.CDLL(out)
+def lib():
+    return hostlib.load("hashch_host", cuda_headers=True)
 
 
 def host_hash_ch(lib, secpar, vk_l, vk_r, digests):

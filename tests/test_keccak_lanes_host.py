@@ -4,23 +4,18 @@ publish / barrier / read / barrier, tests/host/keccak_lanes_host.cpp) and compar
 tests/test_modarith_host.py pins against hashlib.  No GPU needed."""
 import ctypes as C
 import os
-import shutil
-import subprocess
 
 import numpy as np
 import pytest
+
+import hostlib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
-def lib(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("needs g++")
-    out = str(tmp_path_factory.mktemp("lanes") / "keccak_lanes_host.so")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w", "-pthread", "-o", out, os.path.join(ROOT, "tests", "host", "keccak_lanes_host.cpp")],
-                   check=True)
-    return C.CDLL(out)
+def lib():
+    return hostlib.load("keccak_lanes_host", pthread=True)
 
 
 def reference(lib, states, times):

@@ -5,11 +5,11 @@ without a GPU.  tests/host/modarith_host.cpp only supplies the device intrinsics
 import ctypes as C
 import hashlib
 import os
-import shutil
-import subprocess
 
 import numpy as np
 import pytest
+
+import hostlib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 Q = 2147465729
@@ -23,13 +23,8 @@ def cent(v: int) -> int:
 
 
 @pytest.fixture(scope="module")
-def lib(tmp_path_factory):
-    if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
-        pytest.skip("needs g++ and the CUDA headers")
-    out = str(tmp_path_factory.mktemp("modarith") / "modarith_host.so")
-    src = os.path.join(ROOT, "tests", "host", "modarith_host.cpp")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w", "-I" + CUDA_INC, "-o", out, src], check=True)
-    lib = C.CDLL(out)
+def lib():
+    lib = hostlib.load("modarith_host", cuda_headers=True)
     lib.h_q.restype = C.c_uint32
     assert lib.h_q() == Q
     return lib

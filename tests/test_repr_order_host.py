@@ -6,23 +6,19 @@ import ctypes as C
 import json
 import os
 import re
-import shutil
-import subprocess
 
 import numpy as np
 import pytest
+
+import hostlib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 Q = 2147465729
 
 
 @pytest.fixture(scope="module")
-def lib(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("needs g++")
-    out = str(tmp_path_factory.mktemp("repr") / "repr_order_host.so")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w", "-o", out, os.path.join(ROOT, "tests", "host", "repr_order_host.cpp")], check=True)
-    return C.CDLL(out)
+def lib():
+    return hostlib.load("repr_order_host")
 
 
 def template(secpar):

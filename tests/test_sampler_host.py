@@ -4,11 +4,11 @@ and public-matrix samplers of the reference).  Seeds of one, two and more 32-bit
 import ctypes as C
 import os
 import random
-import shutil
-import subprocess
 
 import numpy as np
 import pytest
+
+import hostlib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 Q = 2147465729
@@ -16,13 +16,8 @@ CUDA_INC = "/usr/local/cuda/include"
 
 
 @pytest.fixture(scope="module")
-def lib(tmp_path_factory):
-    if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
-        pytest.skip("needs g++ and the CUDA headers")
-    out = str(tmp_path_factory.mktemp("sampler") / "sampler_host.so")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w", "-I" + CUDA_INC, "-o", out, os.path.join(ROOT, "tests", "host", "sampler_host.cpp")],
-                   check=True)
-    return C.CDLL(out)
+def lib():
+    return hostlib.load("sampler_host", cuda_headers=True)
 
 
 def limbs(seeds):

@@ -7,23 +7,19 @@ import hashlib
 import json
 import os
 import re
-import shutil
-import subprocess
 
 import numpy as np
 import pytest
+
+import hostlib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
 @pytest.fixture(scope="module")
-def lib(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("needs g++")
-    out = str(tmp_path_factory.mktemp("text") / "text_host.so")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w", "-o", out, os.path.join(ROOT, "tests", "host", "text_host.cpp")], check=True)
-    return C.CDLL(out)
+def lib():
+    return hostlib.load("text_host")
 
 
 def test_decimal_formatter_equals_str(lib):
