@@ -14,22 +14,11 @@
 // library) is canonical (|x| <= (q-1)/2 < 2^30); the streamed operand may be any int32.
 #include "fz_common.cuh"
 #include "fz_internal.h"
+#include "fz_mac.cuh"
 
 namespace fz {
 
-__device__ __forceinline__ void mac4(long long (&acc)[4], const int4& a, const int4& b) {
-    acc[0] += (long long)a.x * b.x;
-    acc[1] += (long long)a.y * b.y;
-    acc[2] += (long long)a.z * b.z;
-    acc[3] += (long long)a.w * b.w;
-}
-__device__ __forceinline__ void fold4(long long (&acc)[4]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i] = fold_i64(acc[i]);
-}
-__device__ __forceinline__ int4 cent4(const long long (&acc)[4]) {
-    return make_int4(cent_i64(acc[0]), cent_i64(acc[1]), cent_i64(acc[2]), cent_i64(acc[3]));
-}
+// mac4 / fold4 / cent4: fz_mac.cuh
 
 // out[b][k] = cent( sum_r A[r][k] * s[b][r][k] ).  A: [ell][d] canonical, s: [batch][ell][d], out: [batch][d].
 // thread <-> (b, 4 consecutive k); the ell rows of s[b] are streamed with 4 loads in flight.
