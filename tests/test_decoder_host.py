@@ -16,9 +16,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 Q = 2147465729
 
 
-@pytest.fixture(scope="module")
-def lib():
-    return hostlib.load("decoder_host")
+@pytest.fixture(scope="module", params=["decoder_host", "dec_stream_host"])      # fz_decoder.cuh, and its twin of the one-shot aggregation-hash kernels
+def lib(request):
+    return hostlib.load(request.param, cuda_headers=request.param == "dec_stream_host")
 
 
 byte_budget, host_decode = hostlib.byte_budget, hostlib.host_decode
