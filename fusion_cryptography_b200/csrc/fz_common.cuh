@@ -15,6 +15,12 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// the dynamic shared memory of a kernel: `FZ_DYN_SHARED __align__(16) uint8_t name[];` (the CPU test suite's emulator, tests/host/cuda_emu.h, gives the
+// arrays static storage and defines this macro itself)
+#ifndef FZ_DYN_SHARED
+#define FZ_DYN_SHARED extern __shared__
+#endif
+
 namespace fz {
 
 constexpr uint32_t Q = 2147465729u;

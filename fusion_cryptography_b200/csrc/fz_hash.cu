@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(FMT_WARPS * 32) format_kernel(int mode, int le
                                                                  const int32_t* __restrict__ vk_r, const uint8_t* __restrict__ digests,
                                                                  const int32_t* __restrict__ c_hat, size_t n, uint8_t* __restrict__ out, size_t out_stride,
                                                                  uint32_t* __restrict__ out_len) {
-    extern __shared__ __align__(16) uint8_t fsm[];
+    FZ_DYN_SHARED __align__(16) uint8_t fsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t* buf = fsm + (size_t)warp * FMT_SMEM_PER_WARP;
     const FmtConst& fc = c_fmt[level];
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(FMT_WARPS * 32) agw_format_kernel(int level, i
                                                                      const uint32_t* __restrict__ agg_of, const unsigned long long* __restrict__ agg_off,
                                                                      size_t n_win, uint32_t w0, const unsigned long long* __restrict__ piece_off,
                                                                      const uint32_t* __restrict__ piece_len, uint8_t* __restrict__ ring, size_t ring_cap) {
-    extern __shared__ __align__(16) uint8_t fsm[];
+    FZ_DYN_SHARED __align__(16) uint8_t fsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const FmtConst& fc = c_fmt[level];
     for (size_t i = (size_t)blockIdx.x * FMT_WARPS + warp; i < n_win; i += (size_t)gridDim.x * FMT_WARPS) {
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(FMT_WARPS * 32) agw_format_kernel(int level, i
 __global__ void __launch_bounds__(128) agw_decode_kernel(const uint8_t* __restrict__ xof, size_t xof_cap, const uint32_t* __restrict__ bpos,
                                                           const unsigned long long* __restrict__ win_off, const uint32_t* __restrict__ agg_of, size_t n_win,
                                                           int d, int weight, int bpc, int bpi, uint32_t n_ag, int32_t* __restrict__ coef_out) {
-    extern __shared__ __align__(16) uint8_t dsm[];
+    FZ_DYN_SHARED __align__(16) uint8_t dsm[];
     const int L = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t i = (size_t)blockIdx.x * 4 + warp;
     if (i >= n_win) return;
@@ -580,7 +580,7 @@ static int grid_for(size_t n, int per_block) { return (int)((n + per_block - 1) 
 int launch_sponge_bytes(const fz_ctx* ctx, const uint8_t* data, const unsigned long long* offs, size_t n, uint32_t prefix, int prefix_len,
                         uint8_t suffix, uint8_t* out, size_t out_stride, uint32_t out_len, cudaStream_t st) {
     if (n == 0) return 0;
-    sponge_bytes_kernel<<<grid_for(n, 128), 128, 0, st>>>(data, offs, n, prefix, prefix_len, suffix, out, out_stride, out_len);
+    FZ_LAUNCH(sponge_bytes_kernel, grid_for(n, 128), 128, 0, st, data, offs, n, prefix, prefix_len, suffix, out, out_stride, out_len);
     (void)ctx;
     return check(cudaGetLastError(), "sponge_bytes launch");
 }
@@ -594,14 +594,14 @@ int launch_format(const fz_ctx* ctx, int mode, const int32_t* vk_l, const int32_
     size_t blocks = (n + FMT_WARPS - 1) / FMT_WARPS;
     const size_t cap = (size_t)ctx->sm_count * 5;
     if (blocks > cap) blocks = cap;
-    format_kernel<<<(int)blocks, FMT_WARPS * 32, smem, st>>>(mode, ctx->secpar == 256 ? 1 : 0, ctx->d, (uint8_t)(ctx->secpar == 256 ? 3 : 1), vk_l, vk_r,
+    FZ_LAUNCH(format_kernel, (int)blocks, FMT_WARPS * 32, smem, st, mode, ctx->secpar == 256 ? 1 : 0, ctx->d, (uint8_t)(ctx->secpar == 256 ? 3 : 1), vk_l, vk_r,
                                                               digests, c_hat, n, out, out_stride, out_len);
     return check(cudaGetLastError(), "format launch");
 }
 
 int launch_shake_decode(const fz_ctx* ctx, const uint8_t* msg, size_t stride, const uint32_t* len, size_t n, int32_t* coef_out, cudaStream_t st) {
     if (n == 0) return 0;
-    shake_decode_kernel<<<grid_for(n, HC_THREADS), HC_THREADS, 0, st>>>(msg, stride, len, n, ctx->d, ctx->omega_ch, 1u, ctx->bytes_coef, ctx->bytes_idx,
+    FZ_LAUNCH(shake_decode_kernel, grid_for(n, HC_THREADS), HC_THREADS, 0, st, msg, stride, len, n, ctx->d, ctx->omega_ch, 1u, ctx->bytes_coef, ctx->bytes_idx,
                                                                            (uint32_t)ctx->n_ch_used, coef_out);
     return check(cudaGetLastError(), "shake_decode launch");
 }
@@ -609,7 +609,7 @@ int launch_shake_decode(const fz_ctx* ctx, const uint8_t* msg, size_t stride, co
 int launch_decode(const fz_ctx* ctx, const uint8_t* bytes, size_t stride, uint32_t blen, size_t n, int weight, uint32_t bound, int bpc, int bpi,
                   int32_t* coef_out, cudaStream_t st) {
     if (n == 0) return 0;
-    decode_kernel<<<grid_for(n, HC_THREADS), HC_THREADS, 0, st>>>(bytes, stride, blen, n, ctx->d, weight, bound, bpc, bpi, coef_out);
+    FZ_LAUNCH(decode_kernel, grid_for(n, HC_THREADS), HC_THREADS, 0, st, bytes, stride, blen, n, ctx->d, weight, bound, bpc, bpi, coef_out);
     return check(cudaGetLastError(), "decode launch");
 }
 
@@ -617,9 +617,9 @@ int launch_ag_message(const fz_ctx* ctx, const uint8_t* pieces, size_t piece_str
                       const unsigned long long* agg_off, size_t n_aggs, size_t n_total, unsigned long long* piece_pos, uint8_t* msgs, size_t msg_stride,
                       uint32_t* msg_len, cudaStream_t st) {
     if (n_aggs == 0) return 0;
-    ag_layout_kernel<<<(int)n_aggs, 256, 0, st>>>(piece_len, order, agg_off, msg_stride, piece_pos, msg_len);
+    FZ_LAUNCH(ag_layout_kernel, (int)n_aggs, 256, 0, st, piece_len, order, agg_off, msg_stride, piece_pos, msg_len);
     if (check(cudaGetLastError(), "ag_layout launch")) return -2;
-    ag_pack_kernel<<<(int)(n_total + n_aggs), 128, 0, st>>>(pieces, piece_stride, piece_len, order, agg_off, piece_pos, msg_stride,
+    FZ_LAUNCH(ag_pack_kernel, (int)(n_total + n_aggs), 128, 0, st, pieces, piece_stride, piece_len, order, agg_off, piece_pos, msg_stride,
                                                             (uint8_t)(ctx->secpar == 256 ? 3 : 1), msgs, msg_len, n_aggs, n_total);
     return check(cudaGetLastError(), "ag_pack launch");
 }
@@ -627,7 +627,7 @@ int launch_ag_message(const fz_ctx* ctx, const uint8_t* pieces, size_t piece_str
 int launch_shake_ag(const fz_ctx* ctx, const uint8_t* msgs, size_t msg_stride, const uint32_t* msg_len, const unsigned long long* agg_off, uint8_t* xof,
                     size_t n_aggs, cudaStream_t st) {
     if (n_aggs == 0) return 0;
-    shake_ag_kernel<<<grid_for(n_aggs, 32), 32, 0, st>>>(msgs, msg_stride, msg_len, agg_off, (uint32_t)ctx->n_ag, xof, n_aggs);
+    FZ_LAUNCH(shake_ag_kernel, grid_for(n_aggs, 32), 32, 0, st, msgs, msg_stride, msg_len, agg_off, (uint32_t)ctx->n_ag, xof, n_aggs);
     return check(cudaGetLastError(), "shake_ag launch");
 }
 
@@ -642,12 +642,12 @@ int launch_agw_text(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r,
     const int level = ctx->secpar == 256 ? 1 : 0;
     const uint8_t dst0 = (uint8_t)(ctx->secpar == 256 ? 3 : 1);
     if (n_win) {
-        agw_int_text_kernel<<<(unsigned)((n_win + 127) / 128), 128, 0, st>>>(digests, n_win, int_text, int_len);
+        FZ_LAUNCH(agw_int_text_kernel, (unsigned)((n_win + 127) / 128), 128, 0, st, digests, n_win, int_text, int_len);
         if (check(cudaGetLastError(), "agw_int_text launch")) return -2;
-        agw_len_kernel<<<(unsigned)((n_win + 3) / 4), 128, 0, st>>>(level, ctx->d, vk_l, vk_r, int_len, c_hat, win_off, agg_of, agg_off, n_win, w0, piece_len);
+        FZ_LAUNCH(agw_len_kernel, (unsigned)((n_win + 3) / 4), 128, 0, st, level, ctx->d, vk_l, vk_r, int_len, c_hat, win_off, agg_of, agg_off, n_win, w0, piece_len);
         if (check(cudaGetLastError(), "agw_len launch")) return -2;
     }
-    agw_layout_kernel<<<(unsigned)((n_aggs + 3) / 4), 128, 0, st>>>(piece_len, win_off, agg_off, n_aggs, dst0, text_pos, piece_off, wend, ring, ring_cap, w0,
+    FZ_LAUNCH(agw_layout_kernel, (unsigned)((n_aggs + 3) / 4), 128, 0, st, piece_len, win_off, agg_off, n_aggs, dst0, text_pos, piece_off, wend, ring, ring_cap, w0,
                                                                     state ? (const unsigned long long*)((const uint8_t*)state + ag_state_rpos_offset()) : nullptr,
                                                                     ag_state_bytes() / 8);
     if (check(cudaGetLastError(), "agw_layout launch")) return -2;
@@ -658,7 +658,7 @@ int launch_agw_text(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r,
         size_t blocks = (n_win + FMT_WARPS - 1) / FMT_WARPS;
         const size_t cap = (size_t)ctx->sm_count * 16;
         if (blocks > cap) blocks = cap;
-        agw_format_kernel<<<(unsigned)blocks, FMT_WARPS * 32, smem, st>>>(level, ctx->d, dst0, vk_l, vk_r, int_text, int_len, c_hat, win_off, agg_of, agg_off, n_win, w0,
+        FZ_LAUNCH(agw_format_kernel, (unsigned)blocks, FMT_WARPS * 32, smem, st, level, ctx->d, dst0, vk_l, vk_r, int_text, int_len, c_hat, win_off, agg_of, agg_off, n_win, w0,
                                                                           piece_off, piece_len, ring, ring_cap);
         if (check(cudaGetLastError(), "agw_format launch")) return -2;
     }
@@ -670,7 +670,7 @@ int launch_agw_decode(const fz_ctx* ctx, const uint8_t* xof, size_t xof_cap, con
     if (n_win == 0) return 0;
     const int per_warp = ((ctx->n_ag + 32 + 15) & ~15) + 256 + 256;
     const int smem = 4 * per_warp;   // <= 18 KiB at either level: below the default dynamic shared memory limit
-    agw_decode_kernel<<<(unsigned)((n_win + 3) / 4), 128, smem, st>>>(xof, xof_cap, bpos, win_off, agg_of, n_win, ctx->d, ctx->omega_ag, ctx->bytes_coef,
+    FZ_LAUNCH(agw_decode_kernel, (unsigned)((n_win + 3) / 4), 128, smem, st, xof, xof_cap, bpos, win_off, agg_of, n_win, ctx->d, ctx->omega_ag, ctx->bytes_coef,
                                                                       ctx->bytes_idx, (uint32_t)ctx->n_ag, coef_out);
     return check(cudaGetLastError(), "agw_decode launch");
 }

@@ -232,16 +232,24 @@ __global__ void __launch_bounds__(32) agw_absorb_thread_kernel(AgState* __restri
         const uint8_t* src = base + (pos % ring_cap);
 #pragma unroll
         for (int k = 0; k < KECCAK_RATE_LANES; ++k) {
+#ifdef __CUDA_ARCH__
             const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&stage[buf][k][t]);
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + 8 * k) : "memory");
+#else   // CPU test suite (tests/host/cuda_emu.h): the copy is synchronous
+            memcpy(&stage[buf][k][t], src + 8 * k, 8);
+#endif
         }
+#ifdef __CUDA_ARCH__
         asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
     };
     bool have = rpos + KECCAK_RATE <= end;
     int buf = 0;
     if (have) fetch(rpos, 0);
     while (have) {
+#ifdef __CUDA_ARCH__
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
 #pragma unroll
         for (int k = 0; k < KECCAK_RATE_LANES; ++k) a[k] ^= stage[buf][k][t];
         rpos += KECCAK_RATE;
@@ -376,22 +384,32 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) agw_absorb_pair_kernel(AgStat
         const uint8_t* src = base + (pos % ring_cap);
 #pragma unroll
         for (int k = 0; k < KECCAK_RATE_LANES; ++k) {
+#ifdef __CUDA_ARCH__
             const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&stage[buf][k][t]);
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + 8 * k) : "memory");
+#else
+            memcpy(&stage[buf][k][t], src + 8 * k, 4);
+#endif
         }
     };
     const uint32_t maxblk = warp_max(nblk);
     int buf = 0;
     if (nblk > 0) fetch(rpos, 0);
+#ifdef __CUDA_ARCH__
     asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
     for (uint32_t b = 0; b < maxblk; ++b) {
+#ifdef __CUDA_ARCH__
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
         const bool mine = b < nblk;
 #pragma unroll
         for (int k = 0; k < KECCAK_RATE_LANES; ++k) a[k] ^= mine ? stage[buf][k][t] : 0u;
         buf ^= 1;
         if (b + 1 < nblk) fetch(rpos + (unsigned long long)(b + 1) * KECCAK_RATE, buf);
+#ifdef __CUDA_ARCH__
         asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
         keccak_f_pair(a, hi);
         if (b + 1 == nblk) {
 #pragma unroll
@@ -509,7 +527,7 @@ int hashstream_init_tables(fz_ctx* ctx) {
 int launch_hash_ch_stream(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, size_t n, int32_t* coef_out,
                           cudaStream_t st) {
     if (n == 0) return 0;
-    hash_ch_stream_kernel<<<(int)((n + HS_THREADS - 1) / HS_THREADS), HS_THREADS, 0, st>>>(vk_l, vk_r, digests, n, ctx->secpar == 256 ? 1 : 0, ctx->d,
+    FZ_LAUNCH(hash_ch_stream_kernel, (int)((n + HS_THREADS - 1) / HS_THREADS), HS_THREADS, 0, st, vk_l, vk_r, digests, n, ctx->secpar == 256 ? 1 : 0, ctx->d,
                                                                                             ctx->omega_ch, ctx->bytes_coef, ctx->bytes_idx,
                                                                                             (uint32_t)ctx->n_ch_used, coef_out);
     return check(cudaGetLastError(), "hash_ch_stream launch");
@@ -606,7 +624,7 @@ __global__ void __launch_bounds__(WARPS * 32) hash_ag_absorb_warp_kernel(AgState
                                                                           const int32_t* __restrict__ vk_r_s, const uint8_t* __restrict__ dg_s,
                                                                           const int32_t* __restrict__ c_hat_s, const unsigned long long* __restrict__ win_off,
                                                                           size_t n_aggs, int level, int d) {
-    extern __shared__ __align__(16) uint8_t wsm[];
+    FZ_DYN_SHARED __align__(16) uint8_t wsm[];
     const int L = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t j = (size_t)blockIdx.x * WARPS + warp;
     if (j >= n_aggs) return;
@@ -698,7 +716,7 @@ __global__ void __launch_bounds__(WARPS * 32) hash_ag_absorb_warp_kernel(AgState
 __global__ void __launch_bounds__(WARPS * 32) hash_ag_squeeze_warp_kernel(AgState* __restrict__ st, const unsigned long long* __restrict__ win_off,
                                                                            size_t n_aggs, int d, int weight, int bpc, int bpi, uint32_t n_ag,
                                                                            int32_t* __restrict__ coef_out) {
-    extern __shared__ __align__(16) uint8_t wsm[];
+    FZ_DYN_SHARED __align__(16) uint8_t wsm[];
     const int L = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t j = (size_t)blockIdx.x * WARPS + warp;
     if (j >= n_aggs) return;
@@ -938,7 +956,7 @@ size_t ag_state_rpos_offset() { return offsetof(AgState, rpos); }
 int launch_ag_state_init(const fz_ctx* ctx, void* state, const unsigned long long* agg_off, size_t n_aggs, cudaStream_t st) {
     if (n_aggs == 0) return 0;
     (void)ctx;
-    ag_state_init_kernel<<<(int)((n_aggs + 127) / 128), 128, 0, st>>>((AgState*)state, agg_off, n_aggs);
+    FZ_LAUNCH(ag_state_init_kernel, (int)((n_aggs + 127) / 128), 128, 0, st, (AgState*)state, agg_off, n_aggs);
     return check(cudaGetLastError(), "hash_ag state init launch");
 }
 
@@ -971,10 +989,9 @@ int launch_hash_ag_absorb(const fz_ctx* ctx, void* state, const int32_t* vk_l_s,
     const int level = ctx->secpar == 256 ? 1 : 0;
     if (use_warp(ctx, n_aggs)) {
         if (warp_smem_attr(ctx)) return -2;
-        warpag::hash_ag_absorb_warp_kernel<<<(int)((n_aggs + warpag::WARPS - 1) / warpag::WARPS), warpag::WARPS * 32, warpag::WARPS * warpag::SMEM_PER_WARP,
-                                             st>>>((AgState*)state, vk_l_s, vk_r_s, dg_s, c_hat_s, win_off, n_aggs, level, ctx->d);
+        FZ_LAUNCH(warpag::hash_ag_absorb_warp_kernel, (int)((n_aggs + warpag::WARPS - 1) / warpag::WARPS), warpag::WARPS * 32, warpag::WARPS * warpag::SMEM_PER_WARP, st, (AgState*)state, vk_l_s, vk_r_s, dg_s, c_hat_s, win_off, n_aggs, level, ctx->d);
     } else {
-        hash_ag_absorb_thread_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>((AgState*)state, vk_l_s, vk_r_s, dg_s, c_hat_s, win_off, n_aggs, level,
+        FZ_LAUNCH(hash_ag_absorb_thread_kernel, (int)((n_aggs + 31) / 32), 32, 0, st, (AgState*)state, vk_l_s, vk_r_s, dg_s, c_hat_s, win_off, n_aggs, level,
                                                                                 ctx->d);
     }
     return check(cudaGetLastError(), "hash_ag absorb launch");
@@ -984,11 +1001,10 @@ int launch_hash_ag_squeeze(const fz_ctx* ctx, void* state, const unsigned long l
     if (n_aggs == 0) return 0;
     if (use_warp(ctx, n_aggs)) {
         if (warp_smem_attr(ctx)) return -2;
-        warpag::hash_ag_squeeze_warp_kernel<<<(int)((n_aggs + warpag::WARPS - 1) / warpag::WARPS), warpag::WARPS * 32, warpag::WARPS * warpag::SMEM_PER_WARP,
-                                              st>>>((AgState*)state, win_off, n_aggs, ctx->d, ctx->omega_ag, ctx->bytes_coef, ctx->bytes_idx,
+        FZ_LAUNCH(warpag::hash_ag_squeeze_warp_kernel, (int)((n_aggs + warpag::WARPS - 1) / warpag::WARPS), warpag::WARPS * 32, warpag::WARPS * warpag::SMEM_PER_WARP, st, (AgState*)state, win_off, n_aggs, ctx->d, ctx->omega_ag, ctx->bytes_coef, ctx->bytes_idx,
                                                     (uint32_t)ctx->n_ag, coef_out);
     } else {
-        hash_ag_squeeze_thread_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>((AgState*)state, win_off, n_aggs, ctx->d, ctx->omega_ag, ctx->bytes_coef,
+        FZ_LAUNCH(hash_ag_squeeze_thread_kernel, (int)((n_aggs + 31) / 32), 32, 0, st, (AgState*)state, win_off, n_aggs, ctx->d, ctx->omega_ag, ctx->bytes_coef,
                                                                                  ctx->bytes_idx, (uint32_t)ctx->n_ag, coef_out);
     }
     return check(cudaGetLastError(), "hash_ag squeeze launch");
@@ -1015,11 +1031,11 @@ int launch_agw_absorb(const fz_ctx* ctx, void* state, const uint8_t* ring, size_
     if (chain_carveout(ctx)) return -2;
     const int layout = chain_layout(ctx, n_aggs);
     if (layout == 3)
-        warpag::agw_absorb_warp_kernel<24><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
+        FZ_LAUNCH(warpag::agw_absorb_warp_kernel<24>, (unsigned)n_aggs, 32, 0, st, (AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
     else if (layout == 4)
-        pairag::agw_absorb_pair_kernel<<<(unsigned)((n_aggs + 63) / 64), pairag::PAIR_WARPS * 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
+        FZ_LAUNCH(pairag::agw_absorb_pair_kernel, (unsigned)((n_aggs + 63) / 64), pairag::PAIR_WARPS * 32, 0, st, (AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
     else
-        agw_absorb_thread_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>((AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
+        FZ_LAUNCH(agw_absorb_thread_kernel, (int)((n_aggs + 31) / 32), 32, 0, st, (AgState*)state, ring, ring_cap, wend, win_off, n_aggs);
     return check(cudaGetLastError(), "agw_absorb launch");
 }
 
@@ -1027,7 +1043,7 @@ int launch_agw_absorb_sliced(const fz_ctx* ctx, void* state, const uint8_t* ring
                              size_t first_active, size_t n_active, unsigned long long budget_blocks, cudaStream_t st) {
     if (n_aggs == 0 || n_active == 0) return 0;
     if (chain_carveout(ctx)) return -2;
-    warpag::agw_absorb_sliced_kernel<24><<<(unsigned)((n_active + 3) / 4), 128, 0, st>>>((AgState*)state, ring, ring_cap, wend, n_aggs, first_active, n_active,
+    FZ_LAUNCH(warpag::agw_absorb_sliced_kernel<24>, (unsigned)((n_active + 3) / 4), 128, 0, st, (AgState*)state, ring, ring_cap, wend, n_aggs, first_active, n_active,
                                                                                         budget_blocks);
     return check(cudaGetLastError(), "agw_absorb_sliced launch");
 }
@@ -1038,12 +1054,12 @@ int launch_agw_squeeze(const fz_ctx* ctx, void* state, const unsigned long long*
     if (chain_carveout(ctx)) return -2;
     const int layout = chain_layout(ctx, n_aggs);
     if (layout == 3)
-        warpag::agw_squeeze_warp_kernel<24><<<(unsigned)n_aggs, 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
+        FZ_LAUNCH(warpag::agw_squeeze_warp_kernel<24>, (unsigned)n_aggs, 32, 0, st, (AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
     else if (layout == 4)
-        pairag::agw_squeeze_pair_kernel<<<(unsigned)((n_aggs + 63) / 64), pairag::PAIR_WARPS * 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag,
+        FZ_LAUNCH(pairag::agw_squeeze_pair_kernel, (unsigned)((n_aggs + 63) / 64), pairag::PAIR_WARPS * 32, 0, st, (AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag,
                                                                                                           xof, xof_cap, bpos_out);
     else
-        agw_squeeze_thread_kernel<<<(int)((n_aggs + 31) / 32), 32, 0, st>>>((AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
+        FZ_LAUNCH(agw_squeeze_thread_kernel, (int)((n_aggs + 31) / 32), 32, 0, st, (AgState*)state, win_off, n_aggs, (uint32_t)ctx->n_ag, xof, xof_cap, bpos_out);
     return check(cudaGetLastError(), "agw_squeeze launch");
 }
 

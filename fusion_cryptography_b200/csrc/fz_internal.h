@@ -23,6 +23,12 @@ struct fz_ctx {
     int buffered_hash;  // 1: format text into HBM scratch first (fz_hash.cu); 0 (default): streaming generator (fz_hashstream.cu)
 };
 
+// A kernel launch of the host code.  The CPU test suite compiles the kernels and this launch code with g++ on a small CUDA-on-CPU emulator
+// (tests/host/cuda_emu.h), which defines FZ_LAUNCH before this header is read; in the library it is the ordinary launch.
+#ifndef FZ_LAUNCH
+#define FZ_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 namespace fz {
 
 void set_error(const char* fmt, ...);

@@ -17,8 +17,9 @@ _cache = {}
 _dir = None
 
 
-def load(name: str, cuda_headers: bool = False, pthread: bool = False) -> C.CDLL:
-    """tests/host/<name>.cpp -> shared library (built once per process); skips the calling test when the toolchain is missing."""
+def load(name: str, cuda_headers: bool = False, pthread: bool = False, sources=None, std: str = "c++17", opt: str = "-O2") -> C.CDLL:
+    """tests/host/<name>.cpp (or the listed sources under tests/host/) -> shared library, built once per process; skips the calling test when the
+    toolchain is missing."""
     global _dir
     if name in _cache:
         return _cache[name]
@@ -29,8 +30,9 @@ def load(name: str, cuda_headers: bool = False, pthread: bool = False) -> C.CDLL
     if _dir is None:
         _dir = tempfile.mkdtemp(prefix="fz_host_")
     out = os.path.join(_dir, name + ".so")
-    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w"] + (["-pthread"] if pthread else []) + (["-I" + CUDA_INC] if cuda_headers else [])
-    subprocess.run(cmd + ["-o", out, os.path.join(ROOT, "tests", "host", name + ".cpp")], check=True)
+    srcs = [os.path.join(ROOT, "tests", "host", f) for f in (sources or [name + ".cpp"])]
+    cmd = ["g++", opt, "-std=" + std, "-shared", "-fPIC", "-w"] + (["-pthread"] if pthread else []) + (["-I" + CUDA_INC] if cuda_headers else [])
+    subprocess.run(cmd + ["-o", out] + srcs, check=True)
     _cache[name] = C.CDLL(out)
     return _cache[name]
 
