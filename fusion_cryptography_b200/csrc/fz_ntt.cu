@@ -347,12 +347,12 @@ int launch_ntt(const fz_ctx* ctx, int inverse, const int32_t* in, int32_t* out, 
     if (n_polys == 0) return 0;
     if (ctx->logd == 8) {
         const size_t items = (n_polys + 7) / 8;
-        if (inverse) ntt_inv_kernel<8><<<persistent_grid(ctx, ntt_inv_kernel<8>, NTT_THREADS, items), NTT_THREADS, 0, st>>>(in, out, n_polys);
-        else ntt_fwd_kernel<8><<<persistent_grid(ctx, ntt_fwd_kernel<8>, NTT_THREADS, items), NTT_THREADS, 0, st>>>(in, out, n_polys);
+        if (inverse) FZ_LAUNCH(ntt_inv_kernel<8>, persistent_grid(ctx, ntt_inv_kernel<8>, NTT_THREADS, items), NTT_THREADS, 0, st, in, out, n_polys);
+        else FZ_LAUNCH(ntt_fwd_kernel<8>, persistent_grid(ctx, ntt_fwd_kernel<8>, NTT_THREADS, items), NTT_THREADS, 0, st, in, out, n_polys);
     } else {
         const size_t items = (n_polys + 31) / 32;
-        if (inverse) ntt_inv_kernel<6><<<persistent_grid(ctx, ntt_inv_kernel<6>, NTT_THREADS, items), NTT_THREADS, 0, st>>>(in, out, n_polys);
-        else ntt_fwd_kernel<6><<<persistent_grid(ctx, ntt_fwd_kernel<6>, NTT_THREADS, items), NTT_THREADS, 0, st>>>(in, out, n_polys);
+        if (inverse) FZ_LAUNCH(ntt_inv_kernel<6>, persistent_grid(ctx, ntt_inv_kernel<6>, NTT_THREADS, items), NTT_THREADS, 0, st, in, out, n_polys);
+        else FZ_LAUNCH(ntt_fwd_kernel<6>, persistent_grid(ctx, ntt_fwd_kernel<6>, NTT_THREADS, items), NTT_THREADS, 0, st, in, out, n_polys);
     }
     return check(cudaGetLastError(), inverse ? "ntt_inv launch" : "ntt_fwd launch");
 }
@@ -360,18 +360,18 @@ int launch_ntt(const fz_ctx* ctx, int inverse, const int32_t* in, int32_t* out, 
 int launch_polymul(const fz_ctx* ctx, const int32_t* a, const int32_t* b, int32_t* out, size_t n_polys, cudaStream_t st) {
     if (n_polys == 0) return 0;
     if (ctx->logd == 8)
-        polymul_kernel<8><<<persistent_grid(ctx, polymul_kernel<8>, NTT_THREADS, (n_polys + 7) / 8), NTT_THREADS, 0, st>>>(a, b, out, n_polys);
+        FZ_LAUNCH(polymul_kernel<8>, persistent_grid(ctx, polymul_kernel<8>, NTT_THREADS, (n_polys + 7) / 8), NTT_THREADS, 0, st, a, b, out, n_polys);
     else
-        polymul_kernel<6><<<persistent_grid(ctx, polymul_kernel<6>, NTT_THREADS, (n_polys + 31) / 32), NTT_THREADS, 0, st>>>(a, b, out, n_polys);
+        FZ_LAUNCH(polymul_kernel<6>, persistent_grid(ctx, polymul_kernel<6>, NTT_THREADS, (n_polys + 31) / 32), NTT_THREADS, 0, st, a, b, out, n_polys);
     return check(cudaGetLastError(), "polymul launch");
 }
 
 int launch_ntt_pass(const fz_ctx* ctx, const int32_t* a, const int32_t* bhat, int32_t* out, size_t n_polys, cudaStream_t st) {
     if (n_polys == 0) return 0;
     if (ctx->logd == 8)
-        ntt_pass_kernel<8><<<persistent_grid(ctx, ntt_pass_kernel<8>, NTT_THREADS, (n_polys + 7) / 8), NTT_THREADS, 0, st>>>(a, bhat, out, n_polys);
+        FZ_LAUNCH(ntt_pass_kernel<8>, persistent_grid(ctx, ntt_pass_kernel<8>, NTT_THREADS, (n_polys + 7) / 8), NTT_THREADS, 0, st, a, bhat, out, n_polys);
     else
-        ntt_pass_kernel<6><<<persistent_grid(ctx, ntt_pass_kernel<6>, NTT_THREADS, (n_polys + 31) / 32), NTT_THREADS, 0, st>>>(a, bhat, out, n_polys);
+        FZ_LAUNCH(ntt_pass_kernel<6>, persistent_grid(ctx, ntt_pass_kernel<6>, NTT_THREADS, (n_polys + 31) / 32), NTT_THREADS, 0, st, a, bhat, out, n_polys);
     return check(cudaGetLastError(), "ntt_pass launch");
 }
 
@@ -381,7 +381,7 @@ int launch_pointwise_add(const fz_ctx* ctx, const int32_t* a, const int32_t* b, 
     size_t blocks = (n4 + 255) / 256;
     const size_t cap = (size_t)ctx->sm_count * 16;
     if (blocks > cap) blocks = cap;
-    pointwise_add_kernel<<<(int)blocks, 256, 0, st>>>((const int4*)a, (const int4*)b, (int4*)out, n4);
+    FZ_LAUNCH(pointwise_add_kernel, (int)blocks, 256, 0, st, (const int4*)a, (const int4*)b, (int4*)out, n4);
     return check(cudaGetLastError(), "pointwise_add launch");
 }
 
@@ -391,8 +391,8 @@ int launch_pointwise(const fz_ctx* ctx, const int32_t* a, const int32_t* b, cons
     size_t blocks = (n4 + 255) / 256;
     const size_t cap = (size_t)ctx->sm_count * 16;
     if (blocks > cap) blocks = cap;
-    if (c) pointwise_kernel<true><<<(int)blocks, 256, 0, st>>>((const int4*)a, (const int4*)b, (const int4*)c, (int4*)out, n4);
-    else pointwise_kernel<false><<<(int)blocks, 256, 0, st>>>((const int4*)a, (const int4*)b, nullptr, (int4*)out, n4);
+    if (c) FZ_LAUNCH(pointwise_kernel<true>, (int)blocks, 256, 0, st, (const int4*)a, (const int4*)b, (const int4*)c, (int4*)out, n4);
+    else FZ_LAUNCH(pointwise_kernel<false>, (int)blocks, 256, 0, st, (const int4*)a, (const int4*)b, nullptr, (int4*)out, n4);
     return check(cudaGetLastError(), "pointwise launch");
 }
 

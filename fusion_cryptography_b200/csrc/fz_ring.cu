@@ -166,7 +166,7 @@ constexpr int RING_WARP_TILE = 512;
 template <bool INVERSE, bool VEC, bool WARP>
 __global__ void __launch_bounds__(RING_THREADS) ring_ntt_kernel(RingK k, const Sh* __restrict__ tw, const int32_t* in, int32_t* out, size_t n_polys,
                                                                  int polys_per_tile, int tile_words, int twc_items) {
-    extern __shared__ __align__(16) uint32_t ring_smem[];
+    FZ_DYN_SHARED __align__(16) uint32_t ring_smem[];
     constexpr int GS = WARP ? 32 : RING_THREADS;
     const int tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
     uint32_t* tile = WARP ? ring_smem + (threadIdx.x >> 5) * tile_words : ring_smem;   // tile_words includes the pad word per 32
@@ -293,7 +293,7 @@ static int upload_table(fz_ring* r, const uint32_t* host_table, Sh** out) {
     }
     int rc = check(cudaMemcpy(raw, host_table, sizeof(uint32_t) * r->d, cudaMemcpyHostToDevice), "ring table upload");
     if (!rc) {
-        ring_table_kernel<<<(r->d + 255) / 256, 256>>>(raw, *out, r->d, r->q);
+        FZ_LAUNCH(ring_table_kernel, (r->d + 255) / 256, 256, 0, 0, raw, *out, r->d, r->q);
         rc = check(cudaGetLastError(), "ring table kernel");
         if (!rc) rc = check(cudaDeviceSynchronize(), "ring table kernel");
     }
@@ -319,7 +319,7 @@ static int launch_ring_ntt_v(fz_ring* r, const int32_t* in, int32_t* out, size_t
     const size_t n_tiles = (n_polys + polys_per_tile - 1) / polys_per_tile;
     const size_t want = WARP ? (n_tiles + RING_THREADS / 32 - 1) / (RING_THREADS / 32) : n_tiles;
     const size_t cap = (size_t)r->sm_count * (per_sm > 0 ? per_sm : 1);
-    kern<<<(unsigned)(want < cap ? want : cap), RING_THREADS, smem, st>>>(ring_k(r), INVERSE ? r->inv : r->fwd, in, out, n_polys, polys_per_tile,
+    FZ_LAUNCH(kern, (unsigned)(want < cap ? want : cap), RING_THREADS, smem, st, ring_k(r), INVERSE ? r->inv : r->fwd, in, out, n_polys, polys_per_tile,
                                                                           (int)tile_words, twc_items);
     return check(cudaGetLastError(), "ring NTT launch");
 }
@@ -342,13 +342,13 @@ static int launch_ring_pointwise(fz_ring* r, const int32_t* a, const int32_t* b,
     size_t done = 0;
     if ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0 && n >= 4) {
         const size_t n4 = n / 4, want = (n4 + 255) / 256;
-        ring_pointwise4_kernel<MUL><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(ring_k(r), (const int4*)a, (const int4*)b, (int4*)out, n4);
+        FZ_LAUNCH(ring_pointwise4_kernel<MUL>, (unsigned)(want < cap ? want : cap), 256, 0, st, ring_k(r), (const int4*)a, (const int4*)b, (int4*)out, n4);
         if (check(cudaGetLastError(), "ring pointwise launch")) return -2;
         done = n4 * 4;
     }
     if (done < n) {
         const size_t rest = n - done, want = (rest + 255) / 256;
-        ring_pointwise_kernel<MUL><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(ring_k(r), a + done, b + done, out + done, rest);
+        FZ_LAUNCH(ring_pointwise_kernel<MUL>, (unsigned)(want < cap ? want : cap), 256, 0, st, ring_k(r), a + done, b + done, out + done, rest);
         if (check(cudaGetLastError(), "ring pointwise launch")) return -2;
     }
     return 0;
@@ -461,7 +461,7 @@ int fz_ring_decode_poly(fz_ring* r, const uint8_t* bytes, size_t stride, size_t 
         return -3;
     }
     if (n == 0) return 0;
-    ring_decode_kernel<<<(unsigned)((n + 63) / 64), 64, 0, (cudaStream_t)stream>>>(bytes, stride, (uint32_t)blen, n, r->d, weight_bound, (uint32_t)bound,
+    FZ_LAUNCH(ring_decode_kernel, (unsigned)((n + 63) / 64), 64, 0, (cudaStream_t)stream, bytes, stride, (uint32_t)blen, n, r->d, weight_bound, (uint32_t)bound,
                                                                                    bytes_per_coefficient, bytes_per_index, out);
     return check(cudaGetLastError(), "ring decode launch");
 }

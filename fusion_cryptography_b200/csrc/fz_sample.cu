@@ -23,7 +23,7 @@ namespace fz {
 // keys: [n][key_stride] 32-bit limbs, klen[n] limbs used (>= 1)
 __global__ void __launch_bounds__(SMP_THREADS) sample_kernel(int mode, const uint32_t* __restrict__ keys, int key_stride, const int32_t* __restrict__ klen,
                                                               size_t n, int d, uint32_t q, uint32_t bound, int weight, int32_t* __restrict__ out) {
-    extern __shared__ __align__(16) uint32_t smp_sm[];
+    FZ_DYN_SHARED __align__(16) uint32_t smp_sm[];
     const size_t i = (size_t)blockIdx.x * SMP_STREAMS + threadIdx.x;
     if (threadIdx.x >= SMP_STREAMS || i >= n) return;   // no block-wide barrier below
     Mt s;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(SD_THREADS) sample_dense_kernel(const uint32_t
                                                                   uint32_t bound, int32_t* __restrict__ out, long long* __restrict__ cyc) {
     using Cfg = SdCfg<STAGE>;
     constexpr int G = Cfg::G, PW = Cfg::PW;
-    extern __shared__ __align__(16) uint32_t smp_sm[];
+    FZ_DYN_SHARED __align__(16) uint32_t smp_sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = warp * PW + lane;
     const size_t base = (size_t)blockIdx.x * G + (size_t)warp * PW;   // first generator of this warp
@@ -156,9 +156,9 @@ static bool launch_sample_dense(int d, int mode, const uint32_t* keys, int key_s
                                 cudaStream_t st) {
     if (g_sample_impl == 0 || mode != 0 || weight < d || d > 256 || d < 4 || (d & 3) || bound < 1 || bound > 127) return false;
     if (g_sample_impl == 2 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
-        sample_dense_kernel<0><<<(unsigned)((n + SdCfg<0>::G - 1) / SdCfg<0>::G), SD_THREADS, SdCfg<0>::SMEM, st>>>(keys, key_stride, klen, n, d, bound, out, nullptr);
+        FZ_LAUNCH(sample_dense_kernel<0>, (unsigned)((n + SdCfg<0>::G - 1) / SdCfg<0>::G), SD_THREADS, SdCfg<0>::SMEM, st, keys, key_stride, klen, n, d, bound, out, nullptr);
     else
-        sample_dense_kernel<1><<<(unsigned)((n + SdCfg<1>::G - 1) / SdCfg<1>::G), SD_THREADS, SdCfg<1>::SMEM, st>>>(keys, key_stride, klen, n, d, bound, out, nullptr);
+        FZ_LAUNCH(sample_dense_kernel<1>, (unsigned)((n + SdCfg<1>::G - 1) / SdCfg<1>::G), SD_THREADS, SdCfg<1>::SMEM, st, keys, key_stride, klen, n, d, bound, out, nullptr);
     return true;
 }
 
@@ -166,7 +166,7 @@ int launch_sample(const fz_ctx* ctx, int mode, const uint32_t* keys, int key_str
                   int32_t* out, cudaStream_t st) {
     if (n == 0) return 0;
     if (launch_sample_dense(ctx->d, mode, keys, key_stride, klen, n, bound, weight, out, st)) return check(cudaGetLastError(), "dense sample launch");
-    sample_kernel<<<(unsigned)((n + SMP_STREAMS - 1) / SMP_STREAMS), SMP_THREADS, SMP_SMEM, st>>>(mode, keys, key_stride, klen, n, ctx->d, Q, bound, weight, out);
+    FZ_LAUNCH(sample_kernel, (unsigned)((n + SMP_STREAMS - 1) / SMP_STREAMS), SMP_THREADS, SMP_SMEM, st, mode, keys, key_stride, klen, n, ctx->d, Q, bound, weight, out);
     return check(cudaGetLastError(), "sample launch");
 }
 
@@ -175,20 +175,20 @@ int launch_sample_ring(int d, uint32_t q, int mode, const uint32_t* keys, int ke
                        int32_t* out, cudaStream_t st) {
     if (n == 0) return 0;
     if (launch_sample_dense(d, mode, keys, key_stride, klen, n, bound, weight, out, st)) return check(cudaGetLastError(), "dense ring sample launch");
-    sample_kernel<<<(unsigned)((n + SMP_STREAMS - 1) / SMP_STREAMS), SMP_THREADS, SMP_SMEM, st>>>(mode, keys, key_stride, klen, n, d, q, bound, weight, out);
+    FZ_LAUNCH(sample_kernel, (unsigned)((n + SMP_STREAMS - 1) / SMP_STREAMS), SMP_THREADS, SMP_SMEM, st, mode, keys, key_stride, klen, n, d, q, bound, weight, out);
     return check(cudaGetLastError(), "ring sample launch");
 }
 
 int launch_seeds_to_keys(const fz_ctx* ctx, const unsigned long long* seeds, size_t n, uint32_t* keys, int32_t* klen, cudaStream_t st) {
     if (n == 0) return 0;
-    seeds_to_keys_kernel<<<(int)((n + 127) / 128), 128, 0, st>>>(seeds, n, keys, klen);
+    FZ_LAUNCH(seeds_to_keys_kernel, (int)((n + 127) / 128), 128, 0, st, seeds, n, keys, klen);
     (void)ctx;
     return check(cudaGetLastError(), "seeds_to_keys launch");
 }
 
 int launch_row_seeds_to_keys(const fz_ctx* ctx, const unsigned long long* seeds, size_t n, int rows, uint32_t* keys, int32_t* klen, cudaStream_t st) {
     if (n == 0) return 0;
-    row_seeds_to_keys_kernel<<<(unsigned)((2 * n * rows + 127) / 128), 128, 0, st>>>(seeds, n, rows, keys, klen);
+    FZ_LAUNCH(row_seeds_to_keys_kernel, (unsigned)((2 * n * rows + 127) / 128), 128, 0, st, seeds, n, rows, keys, klen);
     (void)ctx;
     return check(cudaGetLastError(), "row_seeds_to_keys launch");
 }
@@ -199,7 +199,7 @@ int launch_replicate_rows(const fz_ctx* ctx, const int32_t* src, int32_t* dst, s
     const unsigned gx = (unsigned)((rows * d4 + 255) / 256);
     for (size_t b0 = 0; b0 < batch; b0 += 65535) {
         const size_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
-        replicate_rows_kernel<<<dim3(gx, (unsigned)nb), 256, 0, st>>>((const int4*)src, (int4*)dst, b0, rows, d4, src_batch_stride / 4);
+        FZ_LAUNCH(replicate_rows_kernel, dim3(gx, (unsigned)nb), 256, 0, st, (const int4*)src, (int4*)dst, b0, rows, d4, src_batch_stride / 4);
         if (check(cudaGetLastError(), "replicate_rows launch")) return -2;
     }
     return 0;

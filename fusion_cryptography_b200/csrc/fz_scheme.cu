@@ -19,7 +19,7 @@ namespace fz {
 // perm[agg_off[j] + rank] = p  (sorted position -> original position), stable.
 __global__ void __launch_bounds__(256) sort_kernel(const int32_t* __restrict__ vk_l, const int32_t* __restrict__ vk_r, const uint32_t* __restrict__ sel,
                                                     const unsigned long long* __restrict__ agg_off, size_t j0, int d, uint32_t* __restrict__ perm) {
-    extern __shared__ unsigned long long skeys[];
+    FZ_DYN_SHARED unsigned long long skeys[];
     const size_t j = j0 + blockIdx.y;
     const size_t lo = agg_off[j], hi = agg_off[j + 1];
     const int n = (int)(hi - lo);
@@ -194,7 +194,7 @@ int launch_sort(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, con
     for (size_t j0 = 0; j0 < n_aggs; j0 += 65535) {   // gridDim.y is limited to 65,535
         const size_t nj = n_aggs - j0 < 65535 ? n_aggs - j0 : 65535;
         dim3 grid((unsigned)((max_keys + 255) / 256), (unsigned)nj);
-        sort_kernel<<<grid, 256, smem, st>>>(vk_l, vk_r, sel, agg_off, j0, ctx->d, perm);
+        FZ_LAUNCH(sort_kernel, grid, 256, smem, st, vk_l, vk_r, sel, agg_off, j0, ctx->d, perm);
         if (check(cudaGetLastError(), "sort launch")) return -2;
     }
     return 0;
@@ -212,7 +212,7 @@ int scheme_init(fz_ctx* ctx) {
 int launch_gather_sorted(const fz_ctx* ctx, const int32_t* vk_l, const int32_t* vk_r, const uint8_t* digests, const uint32_t* sel, const uint32_t* perm,
                          size_t n_total, int32_t* vk_l_s, int32_t* vk_r_s, uint8_t* dg_s, cudaStream_t st) {
     if (n_total == 0) return 0;
-    gather_sorted_kernel<<<(int)((n_total + 3) / 4), 128, 0, st>>>(vk_l, vk_r, digests, sel, perm, n_total, ctx->d, vk_l_s, vk_r_s, dg_s);
+    FZ_LAUNCH(gather_sorted_kernel, (int)((n_total + 3) / 4), 128, 0, st, vk_l, vk_r, digests, sel, perm, n_total, ctx->d, vk_l_s, vk_r_s, dg_s);
     return check(cudaGetLastError(), "gather_sorted launch");
 }
 
@@ -233,14 +233,14 @@ int launch_aggregate(const fz_ctx* ctx, const int32_t* sigs, const uint32_t* per
     for (size_t j0 = 0; j0 < n_aggs; j0 += 65535) {   // gridDim.z is limited to 65,535
         const size_t nj = n_aggs - j0 < 65535 ? n_aggs - j0 : 65535;
         dim3 grid((unsigned)((cols + 255) / 256), (unsigned)split, (unsigned)nj);
-        aggregate_kernel<<<grid, 256, 0, st>>>((const int4*)sigs, perm, (const int4*)alpha, agg_off, j0, ctx->ell, d4, split, (int4*)(split == 1 ? out : part));
+        FZ_LAUNCH(aggregate_kernel, grid, 256, 0, st, (const int4*)sigs, perm, (const int4*)alpha, agg_off, j0, ctx->ell, d4, split, (int4*)(split == 1 ? out : part));
         if (check(cudaGetLastError(), "aggregate launch")) return -2;
     }
     if (split > 1) {
         size_t blocks = (n_aggs * cols + 255) / 256;
         const size_t cap = (size_t)ctx->sm_count * 8;
         if (blocks > cap) blocks = cap;
-        fold_partials_kernel<<<(int)blocks, 256, 0, st>>>((const int4*)part, (int4*)out, n_aggs, cols, split);
+        FZ_LAUNCH(fold_partials_kernel, (int)blocks, 256, 0, st, (const int4*)part, (int4*)out, n_aggs, cols, split);
         return check(cudaGetLastError(), "fold_partials launch");
     }
     return 0;
@@ -252,14 +252,14 @@ int launch_fold_partials(const fz_ctx* ctx, const int32_t* part, int32_t* out, s
     size_t blocks = (n_aggs * cols + 255) / 256;
     const size_t cap = (size_t)ctx->sm_count * 8;
     if (blocks > cap) blocks = cap;
-    fold_partials_kernel<<<(int)blocks, 256, 0, st>>>((const int4*)part, (int4*)out, n_aggs, cols, n_parts);
+    FZ_LAUNCH(fold_partials_kernel, (int)blocks, 256, 0, st, (const int4*)part, (int4*)out, n_aggs, cols, n_parts);
     return check(cudaGetLastError(), "fold_partials launch");
 }
 
 int launch_verify_target(const fz_ctx* ctx, const int32_t* vk_l_s, const int32_t* vk_r_s, const int32_t* c_hat, const int32_t* alpha,
                          const unsigned long long* agg_off, size_t n_aggs, int32_t* target, cudaStream_t st) {
     if (n_aggs == 0) return 0;
-    verify_target_kernel<<<(int)n_aggs, 256, 0, st>>>((const int4*)vk_l_s, (const int4*)vk_r_s, (const int4*)c_hat, (const int4*)alpha, agg_off, ctx->d / 4,
+    FZ_LAUNCH(verify_target_kernel, (int)n_aggs, 256, 0, st, (const int4*)vk_l_s, (const int4*)vk_r_s, (const int4*)c_hat, (const int4*)alpha, agg_off, ctx->d / 4,
                                                        (int4*)target);
     return check(cudaGetLastError(), "verify_target launch");
 }
@@ -267,7 +267,7 @@ int launch_verify_target(const fz_ctx* ctx, const int32_t* vk_l_s, const int32_t
 int launch_verify_finalize(const fz_ctx* ctx, const int32_t* target, const int32_t* observed, const int32_t* coef, size_t n_aggs, uint8_t* codes,
                            cudaStream_t st) {
     if (n_aggs == 0) return 0;
-    verify_finalize_kernel<<<(int)n_aggs, 256, 0, st>>>(target, observed, coef, ctx->d, ctx->ell, ctx->beta_vf, codes);
+    FZ_LAUNCH(verify_finalize_kernel, (int)n_aggs, 256, 0, st, target, observed, coef, ctx->d, ctx->ell, ctx->beta_vf, codes);
     return check(cudaGetLastError(), "verify_finalize launch");
 }
 

@@ -133,7 +133,7 @@ int launch_matvec(const fz_ctx* ctx, const int32_t* A, const int32_t* s, size_t 
                   cudaStream_t st) {
     if (batch == 0) return 0;
     const int d4 = ctx->d / 4;
-    matvec_kernel<<<stream_grid(ctx, batch * d4, 256), 256, 0, st>>>((const int4*)A, (const int4*)s, s_row_stride / 4, s_batch_stride / 4, (int4*)out, batch,
+    FZ_LAUNCH(matvec_kernel, stream_grid(ctx, batch * d4, 256), 256, 0, st, (const int4*)A, (const int4*)s, s_row_stride / 4, s_batch_stride / 4, (int4*)out, batch,
                                                                      ctx->ell, d4);
     return check(cudaGetLastError(), "matvec launch");
 }
@@ -145,7 +145,7 @@ int launch_sign_mac(const fz_ctx* ctx, const int32_t* sk_l, const int32_t* sk_r,
     const unsigned gx = (unsigned)((ctx->ell * d4 + 255) / 256);
     for (size_t b0 = 0; b0 < batch; b0 += 65535) {   // gridDim.y limit
         const size_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
-        sign_mac_kernel<<<dim3(gx, (unsigned)nb), 256, 0, st>>>((const int4*)sk_l, (const int4*)sk_r, sk_row_stride / 4, sk_batch_stride / 4, (const int4*)c_hat,
+        FZ_LAUNCH(sign_mac_kernel, dim3(gx, (unsigned)nb), 256, 0, st, (const int4*)sk_l, (const int4*)sk_r, sk_row_stride / 4, sk_batch_stride / 4, (const int4*)c_hat,
                                                                  (int4*)sig, b0, ctx->ell, d4);
         if (check(cudaGetLastError(), "sign_mac launch")) return -2;
     }
@@ -155,7 +155,7 @@ int launch_sign_mac(const fz_ctx* ctx, const int32_t* sk_l, const int32_t* sk_r,
 int launch_sign_rows(const fz_ctx* ctx, const int32_t* sk_hat, const int32_t* c_hat, int32_t* sig, size_t batch, cudaStream_t st) {
     if (batch == 0) return 0;
     const int d4 = ctx->d / 4;
-    sign_rows_kernel<<<stream_grid(ctx, batch * d4, 256), 256, 0, st>>>((const int4*)sk_hat, (const int4*)c_hat, (int4*)sig, batch, ctx->ell, d4);
+    FZ_LAUNCH(sign_rows_kernel, stream_grid(ctx, batch * d4, 256), 256, 0, st, (const int4*)sk_hat, (const int4*)c_hat, (int4*)sig, batch, ctx->ell, d4);
     return check(cudaGetLastError(), "sign_rows launch");
 }
 
@@ -164,9 +164,9 @@ int launch_matvec_rows(const fz_ctx* ctx, const int32_t* A, int32_t* asum, const
                        cudaStream_t st) {
     if (batch == 0) return 0;
     const int d4 = ctx->d / 4;
-    asum_kernel<<<(d4 + 63) / 64, 64, 0, st>>>((const int4*)A, (int4*)asum, ctx->ell, d4);
+    FZ_LAUNCH(asum_kernel, (d4 + 63) / 64, 64, 0, st, (const int4*)A, (int4*)asum, ctx->ell, d4);
     if (check(cudaGetLastError(), "asum launch")) return -2;
-    mul_bcast_kernel<<<stream_grid(ctx, batch * d4, 256), 256, 0, st>>>((const int4*)asum, (const int4*)s, s_batch_stride / 4, (int4*)out, batch, d4);
+    FZ_LAUNCH(mul_bcast_kernel, stream_grid(ctx, batch * d4, 256), 256, 0, st, (const int4*)asum, (const int4*)s, s_batch_stride / 4, (int4*)out, batch, d4);
     return check(cudaGetLastError(), "mul_bcast launch");
 }
 

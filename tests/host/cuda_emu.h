@@ -10,6 +10,7 @@
 #include <barrier>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -150,14 +151,50 @@ static inline long long clock64() { return 0; }
 using std::max;
 using std::min;
 
+// ---- atomics (on shared or global memory alike)
+template <typename T, typename V> static inline T atomicOr(T* p, V v) { return __atomic_fetch_or(p, (T)v, __ATOMIC_SEQ_CST); }
+template <typename T, typename V> static inline T atomicAnd(T* p, V v) { return __atomic_fetch_and(p, (T)v, __ATOMIC_SEQ_CST); }
+template <typename T, typename V> static inline T atomicAdd(T* p, V v) { return __atomic_fetch_add(p, (T)v, __ATOMIC_SEQ_CST); }
+template <typename T, typename V> static inline T atomicMax(T* p, V v) {
+    T old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (old < (T)v && !__atomic_compare_exchange_n(p, &old, (T)v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+
 // ---- memory intrinsics: cache hints mean nothing here
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 template <typename T> static inline T __ldcs(const T* p) { return *p; }
 template <typename T> static inline void __stcs(T* p, const T& v) { *p = v; }
 
-// ---- the few runtime calls the launch code makes
+// ---- the few runtime calls the library makes: there is one "device", its memory is the host's
 #define cudaFuncSetAttribute(...) cudaSuccess
 #define cudaGetLastError() cudaSuccess
+namespace fz_emu {
+constexpr int SM_COUNT = 2;     // small grids: every CTA is a set of host threads
+inline cudaError_t get_device_count(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t get_device_properties(cudaDeviceProp* p, int) { std::memset(p, 0, sizeof(*p)); p->multiProcessorCount = SM_COUNT; p->major = 10; return cudaSuccess; }
+inline cudaError_t device_get_attribute(int* v, cudaDeviceAttr, int) { *v = 227 * 1024; return cudaSuccess; }
+inline cudaError_t dev_malloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+inline cudaError_t dev_free(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t memcpy_async(void* d, const void* s, size_t n) { std::memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t stream_create(cudaStream_t* s) { *s = nullptr; return cudaSuccess; }
+template <typename K> inline cudaError_t occupancy(int* occ, K, int, size_t) { *occ = 1; return cudaSuccess; }
+}  // namespace fz_emu
+#define cudaGetDeviceCount(n) ::fz_emu::get_device_count(n)
+#define cudaSetDevice(d) cudaSuccess
+#define cudaGetDeviceProperties(p, d) ::fz_emu::get_device_properties((p), (d))
+#define cudaDeviceGetAttribute(v, a, d) ::fz_emu::device_get_attribute((v), (a), (d))
+#define cudaMalloc(p, n) ::fz_emu::dev_malloc((void**)(p), (n))
+#define cudaFree(p) ::fz_emu::dev_free((void*)(p))
+#define cudaMemcpyAsync(d, s, n, kind, st) ::fz_emu::memcpy_async((d), (s), (n))
+#define cudaMemcpy(d, s, n, kind) ::fz_emu::memcpy_async((d), (s), (n))
+#define cudaStreamCreateWithFlags(s, f) ::fz_emu::stream_create(s)
+#define cudaStreamCreate(s) ::fz_emu::stream_create(s)
+#define cudaStreamSynchronize(s) cudaSuccess
+#define cudaDeviceSynchronize() cudaSuccess
+#define cudaStreamDestroy(s) cudaSuccess
+#define cudaGetErrorString(e) "emulated CUDA runtime"
+#define cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, t, s) ::fz_emu::occupancy((occ), (k), (t), (s))
 template <typename S> static inline cudaError_t fz_emu_to_symbol(S& symbol, const void* src, size_t count, size_t offset = 0) {
     std::memcpy(reinterpret_cast<char*>(&symbol) + offset, src, count);
     return cudaSuccess;

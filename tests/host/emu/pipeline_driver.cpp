@@ -9,33 +9,14 @@
 #include <cstdio>
 #include <vector>
 
+#include "../../../include/fusion_b200.h"
 #include "../../../fusion_cryptography_b200/csrc/fz_internal.h"
-
-namespace fz {
-static char g_err[512];
-void set_error(const char* fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_err, sizeof(g_err), fmt, ap);
-    va_end(ap);
-}
-int check(cudaError_t e, const char* what) {
-    if (e == cudaSuccess) return 0;
-    set_error("%s failed", what);
-    return -2;
-}
-bool attr_needed(const fz_ctx*, int) { return false; }
-// dynamic shared memory of the kernels (extern __shared__ arrays): one CTA runs at a time
-alignas(16) uint8_t fsm[256 * 1024];
-alignas(16) uint8_t dsm[64 * 1024];
-namespace warpag { alignas(16) uint8_t wsm[256 * 1024]; }
-}  // namespace fz
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 extern "C" {
 
-const char* h_last_error() { return fz::g_err; }
+const char* h_last_error() { return fz_last_error(); }
 
 // Inputs are per SORTED position (agg_off[n_aggs] of them): vk_l_s, vk_r_s, c_hat_s [total][d]; digests_s [total][32].  positions_per_window = P.
 // layout: 2 a thread, 3 a warp, 4 a lane pair per aggregate.  alpha_coef_out: [total][d], the aggregation coefficients before their transform.

@@ -31,8 +31,15 @@ def load(name: str, cuda_headers: bool = False, pthread: bool = False, sources=N
         _dir = tempfile.mkdtemp(prefix="fz_host_")
     out = os.path.join(_dir, name + ".so")
     srcs = [os.path.join(ROOT, "tests", "host", f) for f in (sources or [name + ".cpp"])]
-    cmd = ["g++", opt, "-std=" + std, "-shared", "-fPIC", "-w"] + (["-pthread"] if pthread else []) + (["-I" + CUDA_INC] if cuda_headers else [])
-    subprocess.run(cmd + ["-o", out] + srcs, check=True)
+    flags = [opt, "-std=" + std, "-fPIC", "-w"] + (["-pthread"] if pthread else []) + (["-I" + CUDA_INC] if cuda_headers else [])
+    if len(srcs) == 1:
+        subprocess.run(["g++"] + flags + ["-shared", "-o", out] + srcs, check=True)
+    else:       # one object per source, compiled side by side, then linked
+        objs = [os.path.join(_dir, name + "_" + os.path.basename(f)[:-4] + ".o") for f in srcs]
+        procs = [subprocess.Popen(["g++"] + flags + ["-c", f, "-o", o]) for f, o in zip(srcs, objs)]
+        if any(p.wait() for p in procs):
+            raise RuntimeError("g++ failed building " + name)
+        subprocess.run(["g++", "-shared"] + (["-pthread"] if pthread else []) + ["-o", out] + objs, check=True)
     _cache[name] = C.CDLL(out)
     return _cache[name]
 
@@ -71,3 +78,16 @@ def host_decode(lib, b: bytes, log2_bias, d, norm_bound, weight):
     out = np.full(d, 99, dtype=np.int32)
     lib.h_decode(b, C.c_uint32(len(b)), C.c_int(d), C.c_int(weight), C.c_uint32(bound), C.c_int(bpc), C.c_int(bpi), ptr(out))
     return out.tolist()
+
+
+# ---- the whole library on the CUDA-on-CPU emulator (tests/host/cuda_emu.h)
+EMU_SOURCES = ["emu/api_emu.cpp", "emu/ntt_emu.cpp", "emu/ring_emu.cpp", "emu/sample_emu.cpp", "emu/scheme_emu.cpp", "emu/stream_emu.cpp", "emu/hash_emu.cpp",
+               "emu/hashstream_emu.cpp", "emu/smem_emu.cpp", "emu/pipeline_driver.cpp"]
+
+
+def load_emulated_library() -> C.CDLL:
+    """libfusion_b200 -- every csrc/*.cu, kernels and host code, plus the C ABI of include/fusion_b200.h -- compiled by g++ for the emulator; "device"
+    pointers are host pointers."""
+    lib = load("libfusion_b200_emu", cuda_headers=True, pthread=True, std="c++20", opt="-O1", sources=EMU_SOURCES)
+    lib.fz_last_error.restype = C.c_char_p
+    return lib

@@ -20,8 +20,7 @@ LAYOUTS = {"thread": 2, "warp": 3, "pair": 4}
 
 @pytest.fixture(scope="module")
 def lib():
-    lib = hostlib.load("pipeline_emu", cuda_headers=True, pthread=True, std="c++20", opt="-O1",
-                       sources=["emu/hash_emu.cpp", "emu/hashstream_emu.cpp", "emu/pipeline_driver.cpp"])
+    lib = hostlib.load_emulated_library()
     lib.h_last_error.restype = C.c_char_p
     return lib
 
