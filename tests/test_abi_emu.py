@@ -188,3 +188,150 @@ def test_scheme_end_to_end(lib, orc, secpar):
     c.ok(lib.fz_verify_check(c.h, P(A), P(vl_s), P(vr_s), P(ch_s), P(alpha), P(bad), P(agg_off), SZ(2), P(codes), P(ws), wsn, None))
     assert codes.tolist() == [0, 3]                          # "Target doesn't match image of aggregate signature."
     lib.fz_destroy(c.h)
+
+
+def _root_of_unity(q, order):
+    """a primitive `order`-th root of unity mod the prime q (order a power of two dividing q - 1)"""
+    for g in range(2, q):
+        r = pow(g, (q - 1) // order, q)
+        if pow(r, order // 2, q) == q - 1:
+            return r
+    raise AssertionError
+
+
+def _brv_table(q, d, psi):
+    bits = d.bit_length() - 1
+    return [pow(psi, int(format(i, f"0{bits}b")[::-1], 2) if bits else 0, q) for i in range(d)]
+
+
+@pytest.mark.parametrize("q,d", [(17, 4), (257, 16), (7681, 64), (12289, 512), (2013265921, 1024), (Q, 256)])
+def test_general_rings(lib, orc, q, d):
+    """fz_ring_*: the transforms, pointwise operations and seeded samplers of the reference's algebra layer on rings other than the scheme's
+    (the reference's own unit tests use moduli below 2^17, tests/test_ntt.py:18-50)."""
+    psi = _root_of_unity(q, 2 * d)
+    fwd, inv = _brv_table(q, d, psi), _brv_table(q, d, pow(psi, q - 2, q))
+    tf, ti = np.array(fwd, dtype=np.uint32), np.array(inv, dtype=np.uint32)
+    ring = C.c_void_p()
+    assert lib.fz_ring_create(C.c_int(0), C.c_uint32(q), C.c_int(d.bit_length() - 1), P(tf), P(ti), C.byref(ring)) == 0, lib.fz_last_error()
+    rng = np.random.default_rng(q % 9973 + d)
+    n = 5
+    a = rng.integers(-(1 << 31), 1 << 31, size=(n, d)).astype(np.int32)          # any int32
+    b = rng.integers(-(q // 2), q // 2 + 1, size=(n, d)).astype(np.int32)
+    out = np.full((n, d), 31337, dtype=np.int32)
+    assert lib.fz_ring_ntt_fwd(ring, P(a), P(out), SZ(n), None) == 0, lib.fz_last_error()
+    fa = orc.ring_ntt_fwd(q, fwd, a)
+    assert np.array_equal(out, fa)
+    assert lib.fz_ring_ntt_inv(ring, P(fa), P(out), SZ(n), None) == 0, lib.fz_last_error()
+    assert np.array_equal(out, orc.ring_ntt_inv(q, inv, fa))
+    assert np.array_equal(out.astype(np.int64), (a.astype(np.int64) + q // 2) % q - q // 2)      # INTT(NTT(a)) = cent(a)
+    assert lib.fz_ring_pointwise_mul(ring, P(a), P(b), P(out), SZ(n), None) == 0
+    assert np.array_equal(out, orc.ring_pointwise(q, a, b, True))
+    assert lib.fz_ring_pointwise_add(ring, P(a), P(b), P(out), SZ(n), None) == 0
+    assert np.array_equal(out, orc.ring_pointwise(q, a, b, False))
+    import random
+
+    seeds = [0, 7, 2**40 + 1, 2**70 + 3]
+    keys, klen = seed_keys(seeds)
+    smp = np.full((len(seeds), d), 31337, dtype=np.int32)
+    assert lib.fz_ring_sample_ntt(ring, P(keys), C.c_int(8), P(klen), SZ(len(seeds)), P(smp), None) == 0
+    for s, row in zip(seeds, smp):
+        random.seed(s)
+        assert row.tolist() == [random.randrange(q) - q // 2 for _ in range(d)]                  # algebra/polynomials.py:478-480
+    bound, weight = min(52, q // 2), max(1, d // 3)
+    assert lib.fz_ring_sample_coef(ring, P(keys), C.c_int(8), P(klen), SZ(len(seeds)), C.c_int(bound), C.c_int(weight), P(smp), None) == 0
+    for s, row in zip(seeds, smp):
+        random.seed(s)                                                                           # algebra/polynomials.py:446-459
+        cf = [(1 + random.randrange(bound)) * (1 - 2 * random.randrange(2)) for _ in range(weight)] + [0] * (d - weight)
+        for i in range(d - 1, 0, -1):
+            j = random.randrange(i + 1)
+            cf[i], cf[j] = cf[j], cf[i]
+        assert row.tolist() == cf
+    lib.fz_ring_destroy(ring)
+
+
+@pytest.mark.parametrize("secpar", [128, 256])
+def test_generic_hashes_text_and_decoder(lib, orc, secpar):
+    import hashlib
+
+    c = Ctx(lib, secpar)
+    rng = np.random.default_rng(secpar + 3)
+    msgs = [rng.integers(0, 256, size=L, dtype=np.uint8).tobytes() for L in (0, 1, 135, 136, 137, 500)]
+    buf, offs = pack(msgs)
+    out32 = np.zeros((len(msgs), 32), dtype=np.uint8)
+    c.ok(lib.fz_sha3_256(c.h, P(buf), P(offs), SZ(len(msgs)), P(out32), None))
+    assert [bytes(x) for x in out32] == [hashlib.sha3_256(m).digest() for m in msgs]
+    xo = np.zeros((len(msgs), 300), dtype=np.uint8)
+    c.ok(lib.fz_shake256(c.h, P(buf), P(offs), SZ(len(msgs)), P(xo), SZ(300), None))
+    assert [bytes(x) for x in xo] == [hashlib.shake_256(m).digest(300) for m in msgs]
+    # the materialised texts of the buffered pipeline: mode 0 = the hash_ch message, mode 1 = one element of the hash_ag list
+    d = c.d
+    vl = rng.integers(-H, H + 1, size=(3, d)).astype(np.int32); vr = rng.integers(-H, H + 1, size=(3, d)).astype(np.int32)
+    ch = rng.integers(-H, H + 1, size=(3, d)).astype(np.int32)
+    dg = np.stack([np.frombuffer(orc.hash_msg(secpar, b"t%d" % i), dtype=np.uint8) for i in range(3)]).copy()
+    for mode in (0, 1):
+        stride = int(lib.fz_text_stride(c.h, C.c_int(mode)))
+        text = np.zeros((3, stride), dtype=np.uint8); tlen = np.zeros(3, dtype=np.uint32)
+        c.ok(lib.fz_format_text(c.h, C.c_int(mode), P(vl), P(vr), P(dg), P(ch), SZ(3), P(text), P(tlen), None))
+        for i in range(3):
+            vk, pre = orc.format_vk(secpar, vl[i], vr[i]), orc.format_prehash(bytes(dg[i]))
+            want = (bytes([3 if secpar == 256 else 1, 1]) + b"," + vk.encode() + b"," + pre.encode()) if mode == 0 else \
+                ("(" + vk + ", " + pre + ", " + orc.format_ch(secpar, ch[i]) + ")").encode()
+            assert bytes(text[i, :tlen[i]]) == want, (mode, i)
+    # decode_bytes_to_polynomial_coefficients through the ABI, and its "Too few bytes" error (-3)
+    blen = 12000 if secpar == 128 else 30000
+    data = np.ascontiguousarray(rng.integers(0, 256, size=(2, blen), dtype=np.uint8))
+    coef = c.i32(2, d)
+    c.ok(lib.fz_decode_poly(c.h, P(data), SZ(blen), SZ(blen), SZ(2), C.c_longlong(secpar), C.c_longlong(52), C.c_int(27), P(coef), None))
+    for i in range(2):
+        assert coef[i].tolist() == [int(x) for x in orc.decode_poly(secpar, bytes(data[i]), secpar, 52, 27)]
+    assert lib.fz_decode_poly(c.h, P(data), SZ(blen), SZ(10), SZ(2), C.c_longlong(secpar), C.c_longlong(52), C.c_int(27), P(coef), None) == -3
+    lib.fz_destroy(c.h)
+
+
+def test_host_pipelines_and_options(lib, orc):
+    """fz_ntt_host / fz_ntt_pass_host (chunked, double-buffered host pipelines) and the alternative implementations behind fz_set_option."""
+    secpar = 128
+    c = Ctx(lib, secpar)
+    rng = np.random.default_rng(77)
+    n = 70
+    a = rng.integers(-H, H + 1, size=(n, c.d)).astype(np.int32); b = rng.integers(-H, H + 1, size=(n, c.d)).astype(np.int32)
+    out = c.i32(n, c.d)
+    c.ok(lib.fz_ntt_host(c.h, C.c_int(0), P(a), P(out), SZ(n)))
+    assert np.array_equal(out, orc.ntt_fwd(secpar, a))
+    c.ok(lib.fz_ntt_pass_host(c.h, P(a), P(b), P(out), SZ(n)))
+    assert np.array_equal(out, orc.ntt_inv(secpar, orc.pointwise_mul(orc.ntt_fwd(secpar, a), b)))
+    # the buffered hashing pipeline and every sampler kernel give the bytes of the default ones
+    A = orc.setup_A(secpar, 42)
+    seeds = (3 * 10**6 + 2 * np.arange(3)).astype(np.uint64)
+    _, _, vk_l, vk_r = orc.keygen_batch(secpar, A, seeds)
+    msgs = [b"opt-%d" % i for i in range(3)]
+    dg = np.stack([np.frombuffer(orc.hash_msg(secpar, m), dtype=np.uint8) for m in msgs]).copy()
+    want_c = np.stack([orc.hash_ch(secpar, vk_l[i], vk_r[i], msgs[i]) for i in range(3)])
+    order = orc.sort_by_repr(secpar, vk_l, vk_r)
+    want_alpha = orc.hash_ag(secpar, vk_l[order], vk_r[order], [msgs[int(i)] for i in order])
+    agg_off = np.array([0, 3], dtype=np.uint64)
+    for buffered in (1, 0):
+        c.ok(lib.fz_set_option(c.h, b"buffered_hash", C.c_longlong(buffered)))
+        c_hat = c.i32(3, c.d)
+        ws, wsn = c.ws("fz_hash_ch_workspace", 3)
+        c.ok(lib.fz_hash_ch(c.h, P(vk_l), P(vk_r), P(dg), SZ(3), P(c_hat), P(ws), wsn, None))
+        assert np.array_equal(c_hat, want_c), buffered
+        for impl in (2, 3, 0):
+            c.ok(lib.fz_set_option(c.h, b"hash_ag_impl", C.c_longlong(impl)))
+            alpha = c.i32(3, c.d)
+            ws, wsn = c.ws("fz_hash_ag_workspace", 3, 1, 3)
+            vl_s, vr_s = np.ascontiguousarray(vk_l[order]), np.ascontiguousarray(vk_r[order])
+            c.ok(lib.fz_hash_ag(c.h, P(vl_s), P(vr_s), P(np.ascontiguousarray(dg[order])), P(np.ascontiguousarray(want_c[order])), P(agg_off), SZ(1), SZ(3), SZ(3),
+                                P(alpha), P(ws), wsn, None))
+            assert np.array_equal(alpha, want_alpha), (buffered, impl)
+    keys, klen = seed_keys([11, 2**33 + 5, 2**65 + 9])
+    import random
+
+    for impl in (0, 2, 1):
+        c.ok(lib.fz_set_option(c.h, b"sample_impl", C.c_longlong(impl)))
+        smp = c.i32(3, c.d)
+        c.ok(lib.fz_sample_coef(c.h, P(keys), C.c_int(8), P(klen), SZ(3), C.c_int(52), C.c_int(c.d), P(smp), None))
+        for s, row in zip([11, 2**33 + 5, 2**65 + 9], smp):
+            random.seed(s)
+            assert row.tolist() == [(1 + random.randrange(52)) * (1 - 2 * random.randrange(2)) for _ in range(c.d)], impl
+    lib.fz_destroy(c.h)
