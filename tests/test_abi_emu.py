@@ -335,3 +335,105 @@ def test_host_pipelines_and_options(lib, orc):
             random.seed(s)
             assert row.tolist() == [(1 + random.randrange(52)) * (1 - 2 * random.randrange(2)) for _ in range(c.d)], impl
     lib.fz_destroy(c.h)
+
+
+@pytest.mark.parametrize("mode", ["ring-thread", "ring-warp", "ring-sliced", "streaming-windows"])
+def test_windowed_aggregate_and_verify(lib, orc, mode):
+    """Engine.aggregate / Engine.verify's window loop (fusion_cryptography_b200/batch.py) restated over the C ABI: the aggregation hash advanced window by
+    window -- ring-fed (text / absorb_ring or the time-sliced absorb / squeeze_xof / decode) or through the streaming resumable kernels (begin / absorb /
+    squeeze) --, the weighted sums and the verify target accumulated per window with fz_pointwise_add, fz_verify_finish on the complete target,
+    fz_fold_partials over partial aggregates.  Three aggregates of 4, 1 and 3 signers, windows of two sorted positions (fusion.py:655-728)."""
+    secpar = 128
+    c = Ctx(lib, secpar)
+    for f in ("fz_hash_ag_state_bytes", "fz_hash_ag_ring_bytes", "fz_hash_ag_xof_bytes", "fz_hash_ag_text_workspace", "fz_verify_finish_workspace"):
+        getattr(lib, f).restype = C.c_size_t
+    d, ell = c.d, c.ell
+    counts, Pw = [4, 1, 3], 2
+    n, n_aggs = sum(counts), len(counts)
+    A = orc.setup_A(secpar, 42)
+    seeds = (4 * 10**6 + 2 * np.arange(n)).astype(np.uint64)
+    sk_l, sk_r, vk_l, vk_r = orc.keygen_batch(secpar, A, seeds)
+    msgs = [b"win-%d" % i for i in range(n)]
+    sigs = orc.sign_batch(secpar, sk_l, sk_r, vk_l, vk_r, msgs)
+    agg_off = np.zeros(n_aggs + 1, dtype=np.uint64); agg_off[1:] = np.cumsum(counts)
+    want_aggs, order = [], []
+    for j in range(n_aggs):
+        sl = slice(int(agg_off[j]), int(agg_off[j + 1]))
+        want_aggs.append(orc.aggregate(secpar, vk_l[sl], vk_r[sl], msgs[sl], sigs[sl]))
+        order += [sl.start + int(i) for i in orc.sort_by_repr(secpar, vk_l[sl], vk_r[sl])]
+    want_aggs = np.stack(want_aggs)
+    dg = np.stack([np.frombuffer(orc.hash_msg(secpar, m), dtype=np.uint8) for m in msgs]).copy()
+    c_hat = np.stack([orc.hash_ch(secpar, vk_l[i], vk_r[i], msgs[i]) for i in range(n)])
+    pos_sorted = np.array(order)                       # sorted position -> original position (what fz_sort_keys returns, checked in the one-shot test)
+
+    if mode == "ring-thread":
+        c.ok(lib.fz_set_option(c.h, b"hash_ag_impl", C.c_longlong(2)))
+    elif mode in ("ring-warp", "ring-sliced"):
+        c.ok(lib.fz_set_option(c.h, b"hash_ag_impl", C.c_longlong(3)))
+    state = np.zeros(n_aggs * int(lib.fz_hash_ag_state_bytes(c.h)), dtype=np.uint8)
+    c.ok(lib.fz_hash_ag_begin(c.h, P(state), P(agg_off), SZ(n_aggs), None))
+    ring_cap = int(lib.fz_hash_ag_ring_bytes(c.h, SZ(3 * Pw if mode == "ring-sliced" else Pw)))
+    ring = np.zeros(n_aggs * ring_cap, dtype=np.uint8)
+    text_pos = np.zeros(n_aggs, dtype=np.uint64)
+    wins = []
+    for w in range(0, max(counts), Pw):
+        cnt = np.clip(np.array(counts) - w, 0, Pw)
+        win_off = np.zeros(n_aggs + 1, dtype=np.uint64); win_off[1:] = np.cumsum(cnt)
+        idx = np.concatenate([pos_sorted[int(agg_off[j]) + w: int(agg_off[j]) + w + int(cnt[j])] for j in range(n_aggs)])
+        agg_of = np.repeat(np.arange(n_aggs, dtype=np.uint32), cnt)
+        vl_w, vr_w = np.ascontiguousarray(vk_l[idx]), np.ascontiguousarray(vk_r[idx])
+        dg_w, ch_w = np.ascontiguousarray(dg[idx]), np.ascontiguousarray(c_hat[idx])
+        n_win = len(idx)
+        if mode == "streaming-windows":
+            c.ok(lib.fz_hash_ag_absorb(c.h, P(state), P(vl_w), P(vr_w), P(dg_w), P(ch_w), P(win_off), SZ(n_aggs), None))
+        else:
+            wend = np.zeros(n_aggs, dtype=np.uint64)
+            tws = np.zeros(int(lib.fz_hash_ag_text_workspace(c.h, SZ(n_win))) + 256, dtype=np.uint8)
+            c.ok(lib.fz_hash_ag_text(c.h, P(vl_w), P(vr_w), P(dg_w), P(ch_w), P(win_off), P(agg_of), P(agg_off), SZ(n_aggs), SZ(n_win), C.c_uint32(w),
+                                     P(text_pos), P(ring), SZ(ring_cap), P(state), P(wend), P(tws), SZ(len(tws)), None))
+            if mode == "ring-sliced":      # two of the three chains advance per launch, the resting one rotates (fz_hash_ag_absorb_sliced)
+                c.ok(lib.fz_hash_ag_absorb_sliced(c.h, P(state), P(ring), SZ(ring_cap), P(wend), SZ(n_aggs), SZ((w // Pw + 1) % n_aggs), SZ(2), C.c_uint64(60), None))
+            else:
+                c.ok(lib.fz_hash_ag_absorb_ring(c.h, P(state), P(ring), SZ(ring_cap), P(wend), P(win_off), SZ(n_aggs), None))
+        wins.append((win_off, agg_of, idx, vl_w, vr_w, ch_w, n_win))
+    if mode == "ring-sliced":              # the text is complete: one launch over every chain without a budget closes what is left
+        c.ok(lib.fz_hash_ag_absorb_sliced(c.h, P(state), P(ring), SZ(ring_cap), P(wend), SZ(n_aggs), SZ(0), SZ(n_aggs), C.c_uint64(1 << 62), None))
+    assert (state.view(np.int32).reshape(n_aggs, 128)[:, 107] == 1).all(), "every sponge has closed its message"
+
+    xof_cap = int(lib.fz_hash_ag_xof_bytes(c.h, SZ(Pw)))
+    acc_agg, acc_target = None, None
+    for win_off, agg_of, idx, vl_w, vr_w, ch_w, n_win in wins:
+        alpha_w = c.i32(n_win, d)
+        if mode == "streaming-windows":
+            c.ok(lib.fz_hash_ag_squeeze(c.h, P(state), P(win_off), SZ(n_aggs), SZ(n_win), P(alpha_w), None))
+        else:
+            xof = np.zeros(n_aggs * xof_cap, dtype=np.uint8); bpos = np.zeros(n_aggs, dtype=np.uint32)
+            c.ok(lib.fz_hash_ag_squeeze_xof(c.h, P(state), P(win_off), SZ(n_aggs), P(xof), SZ(xof_cap), P(bpos), None))
+            c.ok(lib.fz_hash_ag_decode(c.h, P(xof), SZ(xof_cap), P(bpos), P(win_off), P(agg_of), SZ(n_win), P(alpha_w), None))
+        rows = np.ascontiguousarray(idx.astype(np.uint32))
+        part = c.i32(n_aggs, ell, d)
+        ws, wsn = c.ws("fz_aggregate_sum_workspace", n_aggs, Pw)
+        c.ok(lib.fz_aggregate_sum(c.h, P(sigs), P(rows), P(alpha_w), P(win_off), SZ(n_aggs), SZ(Pw), P(part), P(ws), wsn, None))
+        tgt = c.i32(n_aggs, d)
+        c.ok(lib.fz_verify_target(c.h, P(vl_w), P(vr_w), P(ch_w), P(alpha_w), P(win_off), SZ(n_aggs), P(tgt), None))
+        if acc_agg is None:
+            acc_agg, acc_target, parts = part, tgt, [part.copy()]
+        else:
+            parts.append(part.copy())
+            c.ok(lib.fz_pointwise_add(c.h, P(acc_agg), P(part), P(acc_agg), SZ(n_aggs * ell), None))
+            c.ok(lib.fz_pointwise_add(c.h, P(acc_target), P(tgt), P(acc_target), SZ(n_aggs), None))
+    assert np.array_equal(acc_agg, want_aggs)
+    # the same sum as the multi-GPU reduce forms it: partial aggregates [n_aggs][n_parts][ell][d] folded in one call
+    stacked = np.ascontiguousarray(np.stack(parts, axis=1))
+    folded = c.i32(n_aggs, ell, d)
+    c.ok(lib.fz_fold_partials(c.h, P(stacked), C.c_int(len(parts)), SZ(n_aggs), P(folded), None))
+    assert np.array_equal(folded, want_aggs)
+    codes = np.full(n_aggs, 99, dtype=np.uint8)
+    ws = np.zeros(int(lib.fz_verify_finish_workspace(c.h, SZ(n_aggs))) + 256, dtype=np.uint8)
+    c.ok(lib.fz_verify_finish(c.h, P(A), P(acc_target), P(acc_agg), SZ(n_aggs), P(codes), P(ws), SZ(len(ws)), None))
+    assert codes.tolist() == [0, 0, 0]
+    bad = acc_agg.copy(); bad[2, 5, 7] -= 1
+    c.ok(lib.fz_verify_finish(c.h, P(A), P(acc_target), P(bad), SZ(n_aggs), P(codes), P(ws), SZ(len(ws)), None))
+    assert codes.tolist() == [0, 0, 3]
+    c.ok(lib.fz_set_option(c.h, b"hash_ag_impl", C.c_longlong(0)))
+    lib.fz_destroy(c.h)
