@@ -54,32 +54,40 @@ def _null(*a, **k):
     yield
 
 
-def make_context(native, secpar):
-    """native.Context without its CUDA checks: the emulated library's fz_init, tensors on the host."""
-    ctx = object.__new__(native.Context)
-    ctx.lib = native.load_library()
-    ctx.secpar, ctx.device_index, ctx.device = secpar, 0, torch.device("cpu")
-    h = C.c_void_p()
-    rc = ctx.lib.fz_init(C.c_int(0), C.c_int(secpar), C.byref(h))
-    assert rc == 0, ctx.lib.fz_last_error()
-    ctx._h = h
-    ctx.d, ctx.ell, ctx.capacity = ctx.param("d"), ctx.param("ell"), ctx.param("capacity")
-    return ctx
+class _TorchProxy:
+    """`torch` as native.py sees it: torch.device("cuda", i) is the host."""
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
+
+    @staticmethod
+    def device(*a, **k):
+        return torch.device("cpu") if a and a[0] == "cuda" else torch.device(*a, **k)
 
 
-def install(monkeypatch):
-    """Patch torch.cuda and fusion_cryptography_b200.native for the running test; returns the native module."""
-    from fusion_cryptography_b200 import native
+class Permanent:
+    """monkeypatch.setattr for a whole process (the subprocess runs of the reference's own test files)."""
+
+    @staticmethod
+    def setattr(obj, name, value, raising=True):
+        setattr(obj, name, value)
+
+
+def install(monkeypatch, native=None):
+    """Patch torch.cuda and the native module (fusion_cryptography_b200.native unless given) for the running test; returns the native module."""
+    if native is None:
+        from fusion_cryptography_b200 import native
 
     emu = hostlib.load_emulated_library()
     monkeypatch.setattr(native, "LIB_PATH", emu._name)
     monkeypatch.setattr(native, "_lib", None)
     monkeypatch.setattr(native, "_contexts", {})
+    if hasattr(native, "_rings"):
+        monkeypatch.setattr(native, "_rings", {})
+    monkeypatch.setattr(native, "torch", _TorchProxy())
     for name, value in (("is_available", lambda: True), ("init", lambda: None), ("current_device", lambda: 0), ("synchronize", lambda *a: None),
                         ("empty_cache", lambda: None), ("current_stream", lambda *a: _Stream()), ("Stream", _Stream), ("Event", _Event),
                         ("stream", _null), ("device", _null)):
         monkeypatch.setattr(torch.cuda, name, value)
     monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None, raising=False)
-    for secpar in (128, 256):
-        native._contexts[(secpar, 0)] = make_context(native, secpar)
     return native
