@@ -1,20 +1,18 @@
 // cuda_emu.h -- a small CUDA-on-CPU emulator for the CPU test suite: the product's KERNELS (csrc/*.cu, compiled by g++ with FZ_HOST_EMULATION) and
-// their host launch code run unmodified, one CTA after the other; a CTA is a set of host threads, __syncthreads / __syncwarp / warp shuffles and votes
-// are barriers (std::barrier, so that lanes which have returned from the kernel drop out as on the device).  Shared memory is `static` storage
+// their host launch code run unmodified, one CTA after the other; the threads of a CTA are fibers of one host thread, __syncthreads / __syncwarp / warp
+// shuffles and votes are cooperative barriers (threads which have returned from the kernel drop out of them, as on the device).  Shared memory is `static` storage
 // (one CTA runs at a time); constant and device globals are plain globals; cudaMemcpyToSymbol is memcpy.  Test infrastructure only: nothing in the
 // product includes this file.
 #pragma once
 #define FZ_HOST_EMULATION 1
 
 #include <algorithm>
-#include <barrier>
 #include <cstddef>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
-#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>   // vector types (int4, uint4, dim3 ...), cudaError_t, cudaStream_t: declarations only, nothing is linked
@@ -40,29 +38,30 @@
 
 namespace fz_emu {
 
-struct Cta;
+// The threads of a CTA are FIBERS of one host thread, scheduled round-robin; a barrier is "count me in, let the others run until everybody has arrived".
+// The scheduler and the context switch (a dozen instructions of x86-64 assembly) are in emu/emu_runtime.cpp.
 struct Idx { unsigned x = 0, y = 0, z = 0; };
-inline thread_local Idx t_threadIdx;
-inline thread_local Cta* t_cta = nullptr;
-inline Idx g_blockIdx, g_blockDim, g_gridDim;
-
+struct Bar { int expected = 0, arrived = 0; unsigned gen = 0; };
+struct Fiber { void* sp = nullptr; Idx tid; bool done = false; };
 struct Cta {
-    int n_threads;
-    std::barrier<> block_bar;
-    std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
-    std::vector<uint32_t> slot;     // one exchange word per thread
-    explicit Cta(int n) : n_threads(n), block_bar(n), slot((size_t)((n + 31) / 32) * 32, 0u) {
-        for (int w = 0; w * 32 < n; ++w) warp_bar.emplace_back(new std::barrier<>(std::min(32, n - 32 * w)));
-    }
+    int n_threads = 0;
+    Bar block_bar;
+    Bar warp_bar[32];
+    uint32_t slot[1024];     // one exchange word per thread
 };
+extern Cta g_cta;            // the CTA that is running (one at a time)
+extern Fiber* g_cur;         // the thread that is running
+extern Idx g_blockIdx, g_blockDim, g_gridDim;
+void bar_wait(Bar& b);       // arrive and wait; threads that have left the kernel no longer count (as exited threads on the device)
+void run_cta(int n_threads, const std::function<void()>& body);
 
-inline int lane() { return (int)(t_threadIdx.x & 31u); }
-inline int warp() { return (int)(t_threadIdx.x >> 5); }
-inline void sync_warp() { t_cta->warp_bar[warp()]->arrive_and_wait(); }
-inline void sync_block() { t_cta->block_bar.arrive_and_wait(); }
+inline int lane() { return (int)(g_cur->tid.x & 31u); }
+inline int warp() { return (int)(g_cur->tid.x >> 5); }
+inline void sync_warp() { bar_wait(g_cta.warp_bar[warp()]); }
+inline void sync_block() { bar_wait(g_cta.block_bar); }
 
 inline uint32_t shfl(uint32_t v, int src) {
-    uint32_t* s = t_cta->slot.data() + 32 * warp();
+    uint32_t* s = g_cta.slot + 32 * warp();
     s[lane()] = v;
     sync_warp();
     const uint32_t r = s[src & 31];
@@ -84,26 +83,13 @@ void launch(G grid, B block, size_t /*dynamic shared memory: the arrays are defi
         for (unsigned by = 0; by < g_gridDim.y; ++by)
             for (unsigned bx = 0; bx < g_gridDim.x; ++bx) {
                 g_blockIdx.x = bx; g_blockIdx.y = by; g_blockIdx.z = bz;
-                Cta cta(n);
-                std::vector<std::thread> th;
-                for (int t = 0; t < n; ++t)
-                    th.emplace_back([&, t] {
-                        t_cta = &cta;
-                        t_threadIdx.x = (unsigned)t % g_blockDim.x;
-                        t_threadIdx.y = ((unsigned)t / g_blockDim.x) % g_blockDim.y;
-                        t_threadIdx.z = (unsigned)t / (g_blockDim.x * g_blockDim.y);
-                        body();
-                        // a thread that has left the kernel no longer takes part in any barrier (as an exited thread on the device)
-                        cta.warp_bar[(unsigned)t >> 5]->arrive_and_drop();
-                        cta.block_bar.arrive_and_drop();
-                    });
-                for (auto& x : th) x.join();
+                run_cta(n, body);
             }
 }
 
 }  // namespace fz_emu
 
-#define threadIdx (::fz_emu::t_threadIdx)
+#define threadIdx (::fz_emu::g_cur->tid)
 #define blockIdx (::fz_emu::g_blockIdx)
 #define blockDim (::fz_emu::g_blockDim)
 #define gridDim (::fz_emu::g_gridDim)

@@ -82,7 +82,7 @@ def host_decode(lib, b: bytes, log2_bias, d, norm_bound, weight):
 
 # ---- the whole library on the CUDA-on-CPU emulator (tests/host/cuda_emu.h)
 EMU_SOURCES = ["emu/api_emu.cpp", "emu/ntt_emu.cpp", "emu/ring_emu.cpp", "emu/sample_emu.cpp", "emu/scheme_emu.cpp", "emu/stream_emu.cpp", "emu/hash_emu.cpp",
-               "emu/hashstream_emu.cpp", "emu/smem_emu.cpp", "emu/pipeline_driver.cpp"]
+               "emu/hashstream_emu.cpp", "emu/smem_emu.cpp", "emu/emu_runtime.cpp", "emu/pipeline_driver.cpp"]
 
 
 def load_emulated_library() -> C.CDLL:
