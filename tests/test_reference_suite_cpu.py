@@ -4,6 +4,10 @@
 module attributes the mocks patch are ours; the calls the mirror makes to the device are served by the oracle stand-in of tests/refsuite, whose
 functions are the ones the CUDA kernels are compared with bit for bit (tests/test_gpu_ring.py, test_gpu_scheme.py, test_gpu_dropin.py).
 
+Every test runs with two backends behind the mirror: "standin" -- the oracle stand-in described above, which checks the host mirror alone -- and
+"emulated" -- the drop-in's REAL native module and the library compiled for the CUDA-on-CPU emulator (tests/host/cuda_emu.h, tests/emu_device.py),
+i.e. mirror, ctypes binding, C ABI, launch code and kernels on the CPU.
+
 Runs only where the reference checkout exists (the build container); the test files are read from there into a pytest scratch
 directory -- they are never copied into this repository."""
 import os
@@ -16,15 +20,29 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("FUSION_REFERENCE", "/root/reference")
 FILES = ["test_ntt.py", "test_polynomials.py", "test_matrices.py", "test_fusion.py"]
+BACKENDS = ["standin", "emulated"]
 
 
-@pytest.mark.skipif(not all(os.path.exists(os.path.join(REF, "tests", f)) for f in FILES), reason="no reference checkout here")
-def test_reference_unit_tests_pass_on_host_mirror(tmp_path):
-    mirror = tmp_path / "mirror"
+def make_mirror(tmp_path, backend):
+    """A directory to put on PYTHONPATH: `algebra` and `fusion` are the drop-in's packages, `native` is the chosen backend."""
+    mirror = tmp_path / ("mirror_" + backend)
     mirror.mkdir()
     os.symlink(os.path.join(ROOT, "fusion_cryptography_b200", "algebra"), mirror / "algebra")
     os.symlink(os.path.join(ROOT, "fusion_cryptography_b200", "fusion"), mirror / "fusion")
-    shutil.copy(os.path.join(ROOT, "tests", "refsuite", "device_standin.py"), mirror / "native.py")
+    src = "device_standin.py" if backend == "standin" else "emu_native_shim.py"
+    shutil.copy(os.path.join(ROOT, "tests", "refsuite", src), mirror / "native.py")
+    if backend == "emulated":
+        import hostlib
+
+        hostlib.load_emulated_library()      # built here (or the test is skipped here) rather than inside the subprocess
+        os.environ["FZ_EMU_LIBRARY"] = hostlib.load_emulated_library()._name
+    return mirror
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.skipif(not all(os.path.exists(os.path.join(REF, "tests", f)) for f in FILES), reason="no reference checkout here")
+def test_reference_unit_tests_pass_on_host_mirror(tmp_path, backend):
+    mirror = make_mirror(tmp_path, backend)
     tdir = tmp_path / "tests"
     tdir.mkdir()
     (tdir / "__init__.py").write_text("")   # test_matrices.py imports `tests.test_ntt`; a regular package beats any other `tests` on the path
@@ -46,20 +64,15 @@ GEN = os.path.join(REF, "KATs", "generate_KAT_values.py")
 @pytest.mark.skipif(not os.path.exists(GEN), reason="no reference checkout here")
 def test_reference_kat_generator_writes_identical_files(tmp_path):
     """The reference's KAT generator (KATs/generate_KAT_values.py, executed unmodified from the reference checkout with the global generator seeded)
-    run once against the reference and once against the host mirror (device calls served by the oracle stand-in): all 18 CSV files -- 64 MB of
-    text, among them the 12 kinds the reference's repository is missing -- must be byte-identical.  This also pins the state every call leaves
+    run once against the reference and once against the host mirror with each backend (the oracle stand-in; the real stack on the emulated device):
+    all 18 CSV files -- 64 MB of text, among them the 12 kinds the reference's repository is missing -- must be byte-identical.  This also pins the state every call leaves
     CPython's global generator in (the generator draws its seeds from it between calls)."""
     import hashlib
 
     runner = ("import random; random.seed(20231018)\n"
               f"exec(compile(open({GEN!r}).read(), 'generate_KAT_values', 'exec'))\n")
-    mirror = tmp_path / "mirror"
-    mirror.mkdir()
-    os.symlink(os.path.join(ROOT, "fusion_cryptography_b200", "algebra"), mirror / "algebra")
-    os.symlink(os.path.join(ROOT, "fusion_cryptography_b200", "fusion"), mirror / "fusion")
-    shutil.copy(os.path.join(ROOT, "tests", "refsuite", "device_standin.py"), mirror / "native.py")
     digests = {}
-    for name, path in (("reference", REF), ("mirror", str(mirror))):
+    for name, path in [("reference", REF)] + [(b, str(make_mirror(tmp_path, b))) for b in BACKENDS]:
         wd = tmp_path / ("run_" + name)
         wd.mkdir()
         env = dict(os.environ, PYTHONPATH=path, FUSION_B200_REPO=ROOT, PYTHONDONTWRITEBYTECODE="1")
@@ -68,29 +81,26 @@ def test_reference_kat_generator_writes_identical_files(tmp_path):
         out = wd / "KAT_values"
         digests[name] = {f: hashlib.sha256((out / f).read_bytes()).hexdigest() for f in sorted(os.listdir(out))}
     assert len(digests["reference"]) == 18
-    assert digests["mirror"] == digests["reference"]
+    for b in BACKENDS:
+        assert digests[b] == digests["reference"], b
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(REF, "fusion", "fusion.py")), reason="no reference checkout here")
 def test_differential_battery_against_the_reference(tmp_path):
     """tests/refsuite/differential_cases.py -- about 150 ordinary, edge and erroneous calls over algebra.ntt, algebra.polynomials, algebra.matrices
     and fusion.fusion (digests of str(result), or the exception's type and text) -- run with the names resolving to the unmodified reference and to
-    the host mirror: every outcome must be identical.  It found (and now pins) the reference's exact NotImplementedError texts for mixed-ring
+    the host mirror with each backend: every outcome must be identical.  It found (and now pins) the reference's exact NotImplementedError texts for mixed-ring
     operands, hash_ag's behaviour for unequal list lengths and for arbitrary key objects, and its handling of non-int seeds and non-str messages."""
     import json
 
-    mirror = tmp_path / "mirror"
-    mirror.mkdir()
-    os.symlink(os.path.join(ROOT, "fusion_cryptography_b200", "algebra"), mirror / "algebra")
-    os.symlink(os.path.join(ROOT, "fusion_cryptography_b200", "fusion"), mirror / "fusion")
-    shutil.copy(os.path.join(ROOT, "tests", "refsuite", "device_standin.py"), mirror / "native.py")
     script = os.path.join(ROOT, "tests", "refsuite", "differential_cases.py")
     out = {}
-    for name, path in (("reference", REF), ("mirror", str(mirror))):
+    for name, path in [("reference", REF)] + [(b, str(make_mirror(tmp_path, b))) for b in BACKENDS]:
         env = dict(os.environ, PYTHONPATH=path, FUSION_B200_REPO=ROOT, PYTHONDONTWRITEBYTECODE="1")
         r = subprocess.run([sys.executable, script], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=1500)
         assert r.returncode == 0, (name, (r.stdout + r.stderr)[-3000:])
         out[name] = json.loads(r.stdout.strip().splitlines()[-1])
     assert len(out["reference"]) >= 173
-    diff = {k: (v, out["mirror"].get(k)) for k, v in out["reference"].items() if out["mirror"].get(k) != v}
-    assert not diff, diff
+    for b in BACKENDS:
+        diff = {k: (v, out[b].get(k)) for k, v in out["reference"].items() if out[b].get(k) != v}
+        assert not diff, (b, diff)
