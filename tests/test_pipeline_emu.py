@@ -1,7 +1,7 @@
 """The ring-fed aggregation-hash pipeline of the library -- its KERNELS (agw_int_text / agw_len / agw_layout / agw_format, the resumable SHAKE256 chains
 in all three layouts: a thread, a warp, a lane pair per aggregate, agw_squeeze_*, agw_decode) and its host LAUNCH code (launch_agw_text,
 launch_agw_absorb, launch_agw_squeeze, launch_agw_decode), i.e. csrc/fz_hash.cu and csrc/fz_hashstream.cu as they are -- compiled by g++ on a small
-CUDA-on-CPU emulator (tests/host/cuda_emu.h: a CTA is a set of host threads, barriers and shuffles are std::barrier phases) and driven window by
+CUDA-on-CPU emulator (tests/host/cuda_emu.h: the threads of a CTA are fibers of one host thread, barriers and shuffles are cooperative) and driven window by
 window as Engine._hash_windows / _squeeze_windows drive it on the GPU (tests/host/emu/pipeline_driver.cpp).  The aggregation coefficients must equal
 the ones the unmodified reference decoded (fusion.py:573-629) for its golden aggregate at both levels -- windows shorter than the aggregate exercise
 the resumable sponge and the byte rings -- and the oracle's on a ragged batch of aggregates.  No GPU needed."""
