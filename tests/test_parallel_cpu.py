@@ -185,3 +185,47 @@ def test_one_aggregate_sharded_world2(tmp_path, secpar, n):
     port = _free_port()
     mp.spawn(_one_aggregate_worker, args=(2, port, secpar, n, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "one0.npy") and os.path.exists(tmp_path / "one1.npy")
+
+
+def _one_aggregate_worker_emulated(rank: int, world: int, port: int, secpar: int, n: int, out_dir: str):
+    """The same two sharded paths with NOTHING stood in: the real native.Context / batch.Engine over the library compiled for the CUDA-on-CPU
+    emulator (tests/emu_device.py), gloo between the two ranks."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import emu_device
+
+    emu_device.install(emu_device.Permanent)
+    from fusion_cryptography_b200.batch import Engine
+    from oracle import oracle as orc
+
+    eng = Engine(secpar, seed=42, device=0)
+    A = eng.A.numpy()
+    assert np.array_equal(A, orc.setup_A(secpar, 42))
+    seeds = (3 * 10**6 + 2 * np.arange(n)).astype(np.uint64)
+    msgs = [f"shard-{i}".encode() for i in range(n)]
+    sk_l, sk_r, vl, vr = orc.keygen_batch(secpar, A, seeds)
+    sigs = orc.sign_batch(secpar, sk_l, sk_r, vl, vr, msgs)
+    want = orc.aggregate(secpar, vl, vr, msgs, sigs)
+    lo, hi = parallel.shard_bounds(n, rank, world)
+    t_vl, t_vr = torch.from_numpy(vl), torch.from_numpy(vr)
+    agg = parallel.aggregate_one_sharded(eng, t_vl, t_vr, msgs, torch.from_numpy(sigs[lo:hi].copy()))
+    assert np.array_equal(agg[0].numpy(), want), "sharded aggregate differs from the oracle's aggregate"
+    assert parallel.verify_one_sharded(eng, t_vl, t_vr, msgs, agg).tolist() == [0]
+    bad = agg.clone()
+    bad[0, 1, 2] += 1
+    assert parallel.verify_one_sharded(eng, t_vl, t_vr, msgs, bad).tolist() == [3]
+    np.save(os.path.join(out_dir, f"emu{rank}.npy"), np.array([1]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("secpar,n", [(128, 5), (256, 3)])
+def test_one_aggregate_sharded_world2_on_the_emulated_device(tmp_path, secpar, n):
+    """SURVEY 8(e) rows 3 and 4 through the product's own kernels and host code on two gloo ranks (no stand-in)."""
+    import hostlib
+
+    os.environ["FZ_EMU_LIBRARY"] = hostlib.load_emulated_library()._name     # built once here; the two ranks load it
+    port = _free_port()
+    mp.spawn(_one_aggregate_worker_emulated, args=(2, port, secpar, n, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "emu0.npy") and os.path.exists(tmp_path / "emu1.npy")
