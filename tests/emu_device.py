@@ -90,4 +90,5 @@ def install(monkeypatch, native=None):
                         ("stream", _null), ("device", _null)):
         monkeypatch.setattr(torch.cuda, name, value)
     monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None, raising=False)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self, raising=False)      # callers that move their inputs "to the device"
     return native

@@ -70,3 +70,14 @@ def test_engine_pipelines_against_the_oracle(native):
     bad[1, 3, 5] += 1
     assert eng.verify(vk_l, vk_r, msgs, bad, counts, max_positions=3).tolist() == [0, 3, 0]
     eng.ctx.set_option("hash_ag_impl", 0)
+
+
+def test_graft_entry_smoke_on_the_emulated_device(native):
+    """__graft_entry__.smoke() -- what the driver runs on cuda:0 before the bench -- with the emulated device under it: its own checks against the
+    oracle (transforms, fused pass, matvec, keygen + sign, windowed aggregate / verify at both levels, a general ring) must hold here too."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("graft_entry_under_test", os.path.join(ROOT, "__graft_entry__.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.smoke()
