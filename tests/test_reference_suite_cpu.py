@@ -39,23 +39,40 @@ def make_mirror(tmp_path, backend):
     return mirror
 
 
-@pytest.mark.parametrize("backend", BACKENDS)
+def run_all(jobs, timeout=1500):
+    """jobs: name -> (argv, cwd, env); the subprocesses run side by side.  Returns name -> CompletedProcess-like (returncode, stdout, stderr)."""
+    procs = {name: subprocess.Popen(argv, cwd=cwd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for name, (argv, cwd, env) in jobs.items()}
+    out = {}
+    for name, p in procs.items():
+        try:
+            so, se = p.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            so, se = p.communicate()
+            se += "\n[timed out]"
+        out[name] = (p.returncode, so, se)
+    return out
+
+
 @pytest.mark.skipif(not all(os.path.exists(os.path.join(REF, "tests", f)) for f in FILES), reason="no reference checkout here")
-def test_reference_unit_tests_pass_on_host_mirror(tmp_path, backend):
-    mirror = make_mirror(tmp_path, backend)
-    tdir = tmp_path / "tests"
-    tdir.mkdir()
-    (tdir / "__init__.py").write_text("")   # test_matrices.py imports `tests.test_ntt`; a regular package beats any other `tests` on the path
-    shutil.copy(os.path.join(ROOT, "tests", "refsuite", "mocker_shim.py"), tdir / "conftest.py")
-    for f in FILES:
-        shutil.copy(os.path.join(REF, "tests", f), tdir / f)
-    env = dict(os.environ, PYTHONPATH=os.pathsep.join([str(mirror), str(tmp_path), str(tdir)]), FUSION_B200_REPO=ROOT, PYTHONDONTWRITEBYTECODE="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider"] + [str(tdir / f) for f in FILES], cwd=str(tmp_path), env=env,
-                       capture_output=True, text=True, timeout=1500)
-    tail = (r.stdout + r.stderr)[-3000:]
-    assert r.returncode == 0, tail
-    assert " passed" in r.stdout and "failed" not in r.stdout and "error" not in r.stdout.lower(), tail
-    assert "53 passed" in r.stdout, tail
+def test_reference_unit_tests_pass_on_host_mirror(tmp_path):
+    jobs = {}
+    for backend in BACKENDS:
+        mirror = make_mirror(tmp_path, backend)
+        top = tmp_path / ("suite_" + backend)
+        tdir = top / "tests"
+        tdir.mkdir(parents=True)
+        (tdir / "__init__.py").write_text("")   # test_matrices.py imports `tests.test_ntt`; a regular package beats any other `tests` on the path
+        shutil.copy(os.path.join(ROOT, "tests", "refsuite", "mocker_shim.py"), tdir / "conftest.py")
+        for f in FILES:
+            shutil.copy(os.path.join(REF, "tests", f), tdir / f)
+        env = dict(os.environ, PYTHONPATH=os.pathsep.join([str(mirror), str(top), str(tdir)]), FUSION_B200_REPO=ROOT, PYTHONDONTWRITEBYTECODE="1")
+        jobs[backend] = ([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider"] + [str(tdir / f) for f in FILES], str(top), env)
+    for backend, (rc, so, se) in run_all(jobs).items():
+        tail = (so + se)[-3000:]
+        assert rc == 0, (backend, tail)
+        assert " passed" in so and "failed" not in so and "error" not in so.lower(), (backend, tail)
+        assert "53 passed" in so, (backend, tail)
 
 
 GEN = os.path.join(REF, "KATs", "generate_KAT_values.py")
@@ -71,14 +88,15 @@ def test_reference_kat_generator_writes_identical_files(tmp_path):
 
     runner = ("import random; random.seed(20231018)\n"
               f"exec(compile(open({GEN!r}).read(), 'generate_KAT_values', 'exec'))\n")
-    digests = {}
+    jobs = {}
     for name, path in [("reference", REF)] + [(b, str(make_mirror(tmp_path, b))) for b in BACKENDS]:
         wd = tmp_path / ("run_" + name)
         wd.mkdir()
-        env = dict(os.environ, PYTHONPATH=path, FUSION_B200_REPO=ROOT, PYTHONDONTWRITEBYTECODE="1")
-        r = subprocess.run([sys.executable, "-c", runner], cwd=str(wd), env=env, capture_output=True, text=True, timeout=1500)
-        assert r.returncode == 0, (name, (r.stdout + r.stderr)[-3000:])
-        out = wd / "KAT_values"
+        jobs[name] = ([sys.executable, "-c", runner], str(wd), dict(os.environ, PYTHONPATH=path, FUSION_B200_REPO=ROOT, PYTHONDONTWRITEBYTECODE="1"))
+    digests = {}
+    for name, (rc, so, se) in run_all(jobs).items():
+        assert rc == 0, (name, (so + se)[-3000:])
+        out = tmp_path / ("run_" + name) / "KAT_values"
         digests[name] = {f: hashlib.sha256((out / f).read_bytes()).hexdigest() for f in sorted(os.listdir(out))}
     assert len(digests["reference"]) == 18
     for b in BACKENDS:
@@ -94,12 +112,12 @@ def test_differential_battery_against_the_reference(tmp_path):
     import json
 
     script = os.path.join(ROOT, "tests", "refsuite", "differential_cases.py")
+    jobs = {name: ([sys.executable, script], str(tmp_path), dict(os.environ, PYTHONPATH=path, FUSION_B200_REPO=ROOT, PYTHONDONTWRITEBYTECODE="1"))
+            for name, path in [("reference", REF)] + [(b, str(make_mirror(tmp_path, b))) for b in BACKENDS]}
     out = {}
-    for name, path in [("reference", REF)] + [(b, str(make_mirror(tmp_path, b))) for b in BACKENDS]:
-        env = dict(os.environ, PYTHONPATH=path, FUSION_B200_REPO=ROOT, PYTHONDONTWRITEBYTECODE="1")
-        r = subprocess.run([sys.executable, script], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=1500)
-        assert r.returncode == 0, (name, (r.stdout + r.stderr)[-3000:])
-        out[name] = json.loads(r.stdout.strip().splitlines()[-1])
+    for name, (rc, so, se) in run_all(jobs).items():
+        assert rc == 0, (name, (so + se)[-3000:])
+        out[name] = json.loads(so.strip().splitlines()[-1])
     assert len(out["reference"]) >= 173
     for b in BACKENDS:
         diff = {k: (v, out[b].get(k)) for k, v in out["reference"].items() if out[b].get(k) != v}
