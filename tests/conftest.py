@@ -11,6 +11,14 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# FZ_EMULATED_DEVICE=1: the `-m gpu` tests run with the library compiled for the CUDA-on-CPU emulator behind the product's Python layers
+# (tests/emu_device.py); used by tests/test_gpu_suite_on_emulator.py, which runs the lighter GPU test files that way in the CPU suite
+if os.environ.get("FZ_EMULATED_DEVICE") == "1":
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import emu_device
+
+    emu_device.install(emu_device.Permanent)
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")

@@ -54,6 +54,16 @@ def _null(*a, **k):
     yield
 
 
+def _on_host(factory):
+    def make(*args, **kwargs):
+        dev = kwargs.get("device")
+        if dev is not None and str(dev).startswith("cuda"):
+            kwargs["device"] = "cpu"
+        return factory(*args, **kwargs)
+
+    return make
+
+
 class _TorchProxy:
     """`torch` as native.py sees it: torch.device("cuda", i) is the host."""
 
@@ -91,4 +101,6 @@ def install(monkeypatch, native=None):
         monkeypatch.setattr(torch.cuda, name, value)
     monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None, raising=False)
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self, raising=False)      # callers that move their inputs "to the device"
+    for fname in ("empty", "zeros", "ones", "full", "arange", "tensor", "randint"):           # ... or create them there
+        monkeypatch.setattr(torch, fname, _on_host(getattr(torch, fname)))
     return native
