@@ -100,7 +100,7 @@ def install(monkeypatch, native=None):
                         ("stream", _null), ("device", _null)):
         monkeypatch.setattr(torch.cuda, name, value)
     monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None, raising=False)
-    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self, raising=False)      # callers that move their inputs "to the device"
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self.clone(), raising=False)   # moving inputs "to the device" copies them, as a real transfer does
     for fname in ("empty", "zeros", "ones", "full", "arange", "tensor", "randint"):           # ... or create them there
         monkeypatch.setattr(torch, fname, _on_host(getattr(torch, fname)))
     return native
